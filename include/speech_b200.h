@@ -1,0 +1,75 @@
+/* speech_b200 — C ABI of the B200-native (sm_100a) hot path of awni/speech.
+ *
+ * Boundary rules:
+ *   - plain C symbols, raw pointers and sizes, no torch / C++ types in any signature;
+ *   - every buffer is caller-owned (PyTorch allocates); the library never allocates device
+ *     memory, never synchronises the device, and never throws: each entry point returns an
+ *     int status (SB_OK == 0) and enqueues its kernels on the cudaStream_t passed as `stream`
+ *     (a void* so that this header needs no CUDA include);
+ *   - unless stated otherwise every pointer is a DEVICE pointer;
+ *   - re-entrant across streams; one process per GPU.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference tree, awni/speech @ a5909a3).
+ */
+#ifndef SPEECH_B200_H_
+#define SPEECH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_INVALID 1      /* bad argument */
+#define SB_ERR_CUDA 2         /* a CUDA runtime / driver call failed */
+#define SB_ERR_UNSUPPORTED 3  /* shape outside what the kernels implement */
+#define SB_ERR_WORKSPACE 4    /* caller-provided workspace too small */
+
+/* library / device introspection -------------------------------------------------------- */
+int sb_version(void);                 /* 100 * major + minor */
+const char* sb_status_string(int status);
+int sb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
+
+/* ---------------------------------------------------------------------------------------
+ * CTC loss + gradient.
+ * Replaces: functions.ctc.CTCLoss()(acts, labels, act_lens, label_lens)
+ *           (libs/warp-ctc pytorch_binding; call site speech/models/ctc_model.py:34-40;
+ *            un-vendored dependency cloned by Makefile:4-7).
+ *   acts        (B, T, V) float32, batch-first, UN-normalised (softmax is internal)
+ *   grads       (B, T, V) float32 out: d(sum_b cost_b)/d acts; may be NULL (costs only)
+ *   labels      flat int32 [sum(label_lens)], label_offsets = exclusive prefix sum of label_lens
+ *   act_lens    (B) int32 valid frames per utterance (reference passes T for all,
+ *               ctc_model.py:43-45); rows >= act_lens[b] get zero gradient
+ *   blank       blank class index (reference: V-1, ctc_model.py:18)
+ *   costs       (B) float32 out: -log p(labels_b | acts_b); +inf when no alignment exists
+ *   workspace   >= sb_ctc_workspace_size(...) bytes
+ * ------------------------------------------------------------------------------------- */
+int sb_ctc_workspace_size(int B, int T, int V, int max_label_len, size_t* bytes);
+int sb_ctc_fwd_bwd(const float* acts, float* grads, const int* labels, const int* label_offsets,
+                   const int* label_lens, const int* act_lens, int B, int T, int V, int blank,
+                   int max_label_len, float* costs, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 tensor cores:
+ *     C[M,N] (f32)  (+)=  A[M,K] (bf16, row-major) * B[N,K]^T (bf16, row-major)  (+ bias[N])
+ * Replaces: the cuBLAS/cuDNN GEMMs reached through nn.GRU / nn.Linear
+ *           (speech/models/model.py:35-39, 115-133).
+ *   lda/ldb/ldc  leading dimensions in ELEMENTS; A and B rows must be 16-byte aligned
+ *   flags        SB_GEMM_ACCUMULATE: C += (atomic adds; required when split_k > 1)
+ *                SB_GEMM_ROW_REMAP : row m = t*remap_B + b is stored at row b*remap_T + t
+ *                                    (time-major -> batch-first), rows with b >= valid_B dropped
+ * ------------------------------------------------------------------------------------- */
+#define SB_GEMM_ACCUMULATE 1
+#define SB_GEMM_ROW_REMAP 2
+int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, float* C,
+                    long long ldc, const float* bias, int M, int N, int K, int flags, int split_k,
+                    int remap_B, int remap_T, int valid_B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEECH_B200_H_ */

@@ -1,0 +1,386 @@
+// sb_ctc_fwd_bwd: CTC negative log-likelihood + gradient w.r.t. the UN-normalised activations.
+//
+// Replaces functions.ctc.CTCLoss (libs/warp-ctc binding; call site speech/models/ctc_model.py:34-40,
+// un-vendored dependency Makefile:4-7).  Semantics: activations (B, T, V) batch-first raw logits,
+// softmax is internal, blank index is a parameter (the reference uses the LAST class,
+// ctc_model.py:18), labels are a flat int32 array, per-utterance costs are returned and the
+// caller reduces them (sum over the minibatch by default).
+//
+// One CTA per utterance, 512 threads = two "sides" of 256:
+//   side 0 runs the alpha recursion forward in time, side 1 runs the beta recursion backward in
+//   time, CONCURRENTLY, so the serial dependency chain is T steps instead of 2T.  They meet in the
+//   middle (t = T/2): log p(y|x) is formed there from alpha_t and beta_t, and each side then
+//   continues into the half the other side already covered, fusing the gradient
+//     dL/da[t,k] = softmax_t(k) - (1/p) * sum_{s: l'_s = k} alpha_t(s) beta_t(s) / softmax_t(k)
+//   with its recursion.  Only half of each lattice is ever spilled (to an L2-resident workspace).
+//   The (T x V) log-softmax of the utterance is staged ONCE in shared memory with coalesced
+//   reads of the logits (116 KB at T=1000, V=29); lattice rows ping-pong in shared memory.
+//
+// Roofline: nominally HBM (read logits + write grads = 2*B*T*V*4 bytes), in practice bound by
+// the T-step serial chain.
+#include "common.cuh"
+#include <math.h>
+
+#include "../../include/speech_b200.h"
+
+namespace sb {
+
+static constexpr int CTC_SIDE = 256;
+#define CTC_NEG_INF (-INFINITY)
+
+struct CtcParams {
+  const float* acts;    // (B, T, V)
+  float* grads;         // (B, T, V) or nullptr
+  const int* labels;    // flat
+  const int* label_off; // (B) exclusive prefix sum of label_lens
+  const int* label_lens;
+  const int* act_lens;
+  float* costs;         // (B)
+  float* ws;            // (B, T, S_stride) lattice spill
+  int B, T, V, blank, S_stride;
+};
+
+SB_DEVINL float lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == CTC_NEG_INF) return CTC_NEG_INF;
+  return m + __logf(__expf(a - m) + __expf(b - m));
+}
+SB_DEVINL float lse3(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, b), c);
+  if (m == CTC_NEG_INF) return CTC_NEG_INF;
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
+SB_DEVINL void side_barrier(int side) {
+  asm volatile("bar.sync %0, %1;" ::"r"(side + 1), "r"(CTC_SIDE) : "memory");
+}
+
+template <int NS, bool STAGED>
+__global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcParams p) {
+  extern __shared__ float smem[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int side = tid / CTC_SIDE;  // 0: alpha, 1: beta
+  const int i = tid % CTC_SIDE;
+  const int V = p.V;
+  const int T = min(p.act_lens[b], p.T);
+  const int L = p.label_lens[b];
+  const int S = 2 * L + 1;
+  const int* lab = p.labels + p.label_off[b];
+  const float* acts = p.acts + (size_t)b * p.T * V;
+  float* grads = p.grads ? p.grads + (size_t)b * p.T * V : nullptr;
+  float* ws = p.ws + (size_t)b * p.T * p.S_stride;
+
+  // ---- shared memory carve-up ----
+  constexpr int SP = NS * CTC_SIDE + 4;        // padded lattice row (2 pads each end)
+  float* row_buf = smem;                        // [2 sides][2][SP]
+  float* occ = row_buf + 4 * SP;                // [2 sides][2][V]
+  float* red = occ + 4 * V;                     // [32] reduction scratch
+  float* lse_t = red + 32;                      // [T] (only !STAGED)
+  float* lp = STAGED ? (red + 32) : nullptr;    // [T*V] (only STAGED)
+
+  for (int k = tid; k < 4 * SP; k += 2 * CTC_SIDE) row_buf[k] = CTC_NEG_INF;
+  for (int k = tid; k < 4 * V; k += 2 * CTC_SIDE) occ[k] = 0.f;
+
+  // zero the gradient rows beyond this utterance's length
+  if (grads) {
+    for (int k = T * V + tid; k < p.T * V; k += 2 * CTC_SIDE) grads[k] = 0.f;
+  }
+
+  // ---- log-softmax of the whole utterance (coalesced read of the logits) ----
+  const int warp = tid >> 5, lane = tid & 31;
+  if (STAGED) {
+    for (int k = tid; k < T * V; k += 2 * CTC_SIDE) lp[k] = __ldg(acts + k);
+    __syncthreads();
+    for (int t = warp; t < T; t += (2 * CTC_SIDE) / 32) {
+      float m = CTC_NEG_INF;
+      for (int k = lane; k < V; k += 32) m = fmaxf(m, lp[t * V + k]);
+      m = warp_max(m);
+      float s = 0.f;
+      for (int k = lane; k < V; k += 32) s += __expf(lp[t * V + k] - m);
+      s = warp_sum(s);
+      const float lz = m + __logf(s);
+      for (int k = lane; k < V; k += 32) lp[t * V + k] -= lz;
+    }
+  } else {
+    for (int t = warp; t < T; t += (2 * CTC_SIDE) / 32) {
+      float m = CTC_NEG_INF;
+      for (int k = lane; k < V; k += 32) m = fmaxf(m, __ldg(acts + t * V + k));
+      m = warp_max(m);
+      float s = 0.f;
+      for (int k = lane; k < V; k += 32) s += __expf(__ldg(acts + t * V + k) - m);
+      s = warp_sum(s);
+      if (lane == 0) lse_t[t] = m + __logf(s);
+    }
+  }
+  __syncthreads();
+
+  auto emit = [&](int t, int k) -> float {
+    if (STAGED) return lp[t * V + k];
+    return __ldg(acts + t * V + k) - lse_t[t];
+  };
+
+  // degenerate: no frames
+  if (T <= 0) {
+    if (tid == 0) p.costs[b] = (L == 0) ? 0.f : INFINITY;
+    return;
+  }
+
+  // ---- per-thread lattice states: s = i + 256*q ----
+  int cls[NS];      // class emitted in state s
+  bool skip[NS];    // transition s-2 -> s allowed (alpha) ; for beta: s -> s+2 allowed
+  bool valid[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    const int s = i + CTC_SIDE * q;
+    valid[q] = s < S;
+    cls[q] = p.blank;
+    skip[q] = false;
+    if (valid[q] && (s & 1)) {
+      const int li = (s - 1) >> 1;
+      cls[q] = lab[li];
+      if (side == 0) skip[q] = (li > 0) && (lab[li - 1] != cls[q]);
+      else skip[q] = (li + 1 < L) && (lab[li + 1] != cls[q]);
+    }
+  }
+
+  float* my_rows = row_buf + side * 2 * SP + 2;  // +2: leading pad so [s-2] is addressable
+  float* my_occ = occ + side * 2 * V;
+  const int Th = T / 2;
+
+  // ------------------------------------------------------------------------------------------
+  // phase 1: alpha rows [0, Th), beta rows [Th, T) ; each row is spilled to the workspace
+  // ------------------------------------------------------------------------------------------
+  {
+    const int nsteps = side == 0 ? Th : (T - Th);
+    for (int it = 0; it < nsteps; ++it) {
+      const int t = side == 0 ? it : (T - 1 - it);
+      float* cur = my_rows + (it & 1) * SP;
+      const float* prev = my_rows + ((it & 1) ^ 1) * SP;
+#pragma unroll
+      for (int q = 0; q < NS; ++q) {
+        const int s = i + CTC_SIDE * q;
+        float v = CTC_NEG_INF;
+        if (valid[q]) {
+          if (it == 0) {
+            if (side == 0) { if (s <= 1) v = 0.f; }
+            else { if (s >= S - 2) v = 0.f; }
+          } else if (side == 0) {
+            v = lse3(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : CTC_NEG_INF);
+          } else {
+            v = lse3(prev[s], prev[s + 1], skip[q] ? prev[s + 2] : CTC_NEG_INF);
+          }
+          v += emit(t, cls[q]);
+          cur[s] = v;
+          ws[(size_t)t * p.S_stride + s] = v;
+        }
+      }
+      side_barrier(side);
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------------------------------
+  // meet in the middle: alpha_Th (side 0) x beta_Th (side 1's last row) -> log p(y|x)
+  // ------------------------------------------------------------------------------------------
+  const int beta_last_slot = ((T - Th) - 1) & 1;           // slot holding beta_Th
+  const float* beta_Th = row_buf + 2 * SP + 2 + beta_last_slot * SP;
+  float a_reg[NS];
+  if (side == 0) {
+    float* cur = my_rows + (Th & 1) * SP;
+    const float* prev = my_rows + ((Th & 1) ^ 1) * SP;
+    float local_max = CTC_NEG_INF;
+    float contrib[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const int s = i + CTC_SIDE * q;
+      float v = CTC_NEG_INF;
+      contrib[q] = CTC_NEG_INF;
+      if (valid[q]) {
+        const float e = emit(Th, cls[q]);
+        if (Th == 0) { if (s <= 1) v = 0.f; }
+        else v = lse3(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : CTC_NEG_INF);
+        v += e;
+        cur[s] = v;
+        contrib[q] = v + beta_Th[s] - e;
+        local_max = fmaxf(local_max, contrib[q]);
+      }
+      a_reg[q] = v;
+    }
+    // block logsumexp over the 256 alpha-side threads
+    float m = warp_max(local_max);
+    if (lane == 0) red[warp] = m;
+    side_barrier(0);
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < CTC_SIDE / 32; ++w) m = fmaxf(m, red[w]);
+    float sum = 0.f;
+    if (m != CTC_NEG_INF) {
+#pragma unroll
+      for (int q = 0; q < NS; ++q) sum += __expf(contrib[q] - m);
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[8 + warp] = sum;
+    side_barrier(0);
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < CTC_SIDE / 32; ++w) tot += red[8 + w];
+      const float logp = (m == CTC_NEG_INF) ? CTC_NEG_INF : m + logf(tot);
+      red[16] = logp;
+      p.costs[b] = -logp;
+    }
+  }
+  __syncthreads();
+  const float logp = red[16];
+  if (grads == nullptr) return;
+  if (logp == CTC_NEG_INF) {
+    // infeasible alignment: cost = +inf, gradient defined as zero
+    for (int k = tid; k < T * V; k += 2 * CTC_SIDE) grads[k] = 0.f;
+    return;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // phase 2: alpha continues over [Th, T) using spilled beta rows; beta continues over [0, Th)
+  // using spilled alpha rows.  Gradient rows are produced on the fly.
+  // ------------------------------------------------------------------------------------------
+  {
+    const int nsteps = side == 0 ? (T - Th) : Th;
+    // beta side restarts its ping-pong so that "prev" of its first step is beta_Th
+    const int base = side == 0 ? Th : (beta_last_slot + 1);
+    float other[NS];  // spilled row of the other lattice, prefetched one step ahead
+    if (nsteps > 0) {
+      const int t0 = side == 0 ? Th : (Th - 1);
+#pragma unroll
+      for (int q = 0; q < NS; ++q) {
+        const int s = i + CTC_SIDE * q;
+        other[q] = valid[q] ? ld_cg_f(ws + (size_t)t0 * p.S_stride + s) : CTC_NEG_INF;
+      }
+    }
+    for (int it = 0; it < nsteps; ++it) {
+      const int t = side == 0 ? (Th + it) : (Th - 1 - it);
+      const int slot = (base + it) & 1;
+      float* cur = my_rows + slot * SP;
+      const float* prev = my_rows + (slot ^ 1) * SP;
+      float* occ_t = my_occ + (it & 1) * V;
+      float other_next[NS];
+      const bool more = it + 1 < nsteps;
+      const int tn = side == 0 ? (t + 1) : (t - 1);
+#pragma unroll
+      for (int q = 0; q < NS; ++q) {
+        const int s = i + CTC_SIDE * q;
+        other_next[q] = (more && valid[q]) ? ld_cg_f(ws + (size_t)tn * p.S_stride + s)
+                                           : CTC_NEG_INF;
+      }
+      float blank_sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < NS; ++q) {
+        const int s = i + CTC_SIDE * q;
+        if (valid[q]) {
+          const float e = emit(t, cls[q]);
+          float v;
+          if (side == 0 && it == 0) {
+            v = a_reg[q];
+          } else {
+            if (side == 0) v = lse3(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : CTC_NEG_INF);
+            else v = lse3(prev[s], prev[s + 1], skip[q] ? prev[s + 2] : CTC_NEG_INF);
+            v += e;
+            cur[s] = v;
+          }
+          const float g = __expf(v + other[q] - e - logp);
+          if (s & 1) atomicAdd(occ_t + cls[q], g);
+          else blank_sum += g;
+        }
+      }
+      // even threads own the blank states: one shared atomic per warp
+      blank_sum = warp_sum(blank_sum);
+      if (lane == 0 && blank_sum != 0.f) atomicAdd(occ_t + p.blank, blank_sum);
+      side_barrier(side);
+      for (int k = i; k < V; k += CTC_SIDE) {
+        grads[t * V + k] = __expf(emit(t, k)) - occ_t[k];
+        occ_t[k] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < NS; ++q) other[q] = other_next[q];
+    }
+  }
+}
+
+template <int NS, bool STAGED>
+static int launch_ctc(const CtcParams& p, size_t smem_bytes, cudaStream_t stream) {
+  static size_t configured = 0;
+  if (smem_bytes > configured) {
+    if (cudaFuncSetAttribute(ctc_fwd_bwd_kernel<NS, STAGED>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem_bytes) != cudaSuccess)
+      return SB_ERR_CUDA;
+    configured = smem_bytes;
+  }
+  ctc_fwd_bwd_kernel<NS, STAGED><<<p.B, 2 * CTC_SIDE, smem_bytes, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+static int ctc_ns_for(int max_label_len) {
+  const int S = 2 * max_label_len + 1;
+  int ns = (S + CTC_SIDE - 1) / CTC_SIDE;
+  if (ns <= 1) return 1;
+  if (ns <= 2) return 2;
+  if (ns <= 4) return 4;
+  if (ns <= 8) return 8;
+  return -1;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int sb_ctc_workspace_size(int B, int T, int V, int max_label_len, size_t* bytes) {
+  if (!bytes || B <= 0 || T < 0 || V <= 0 || max_label_len < 0) return SB_ERR_INVALID;
+  const int ns = ctc_ns_for(max_label_len);
+  if (ns < 0) return SB_ERR_UNSUPPORTED;
+  *bytes = (size_t)B * (size_t)(T > 0 ? T : 1) * (size_t)(ns * CTC_SIDE) * sizeof(float) + 256;
+  return SB_OK;
+}
+
+extern "C" int sb_ctc_fwd_bwd(const float* acts, float* grads, const int* labels_dev,
+                              const int* label_offsets_dev, const int* label_lens_dev,
+                              const int* act_lens_dev, int B, int T, int V, int blank,
+                              int max_label_len, float* costs, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+  if (!acts || !labels_dev || !label_offsets_dev || !label_lens_dev || !act_lens_dev || !costs ||
+      !workspace)
+    return SB_ERR_INVALID;
+  if (B <= 0 || T <= 0 || V <= 0 || blank < 0 || blank >= V) return SB_ERR_INVALID;
+  size_t need = 0;
+  int rc = sb_ctc_workspace_size(B, T, V, max_label_len, &need);
+  if (rc != SB_OK) return rc;
+  if (workspace_bytes < need) return SB_ERR_WORKSPACE;
+  const int ns = ctc_ns_for(max_label_len);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+
+  CtcParams p;
+  p.acts = acts; p.grads = grads; p.labels = labels_dev; p.label_off = label_offsets_dev;
+  p.label_lens = label_lens_dev; p.act_lens = act_lens_dev; p.costs = costs;
+  p.ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  p.B = B; p.T = T; p.V = V; p.blank = blank; p.S_stride = ns * CTC_SIDE;
+
+  const size_t fixed = (size_t)(4 * (ns * CTC_SIDE + 4) + 4 * V + 32) * sizeof(float);
+  const size_t staged_bytes = fixed + (size_t)T * V * sizeof(float);
+  const size_t unstaged_bytes = fixed + (size_t)T * sizeof(float);
+  const size_t limit = 220 * 1024;
+  const bool staged = staged_bytes <= limit;
+  if (!staged && unstaged_bytes > limit) return SB_ERR_UNSUPPORTED;
+  const size_t smem = staged ? staged_bytes : unstaged_bytes;
+
+#define SB_CTC_CASE(NSV)                                                      \
+  case NSV:                                                                   \
+    return staged ? launch_ctc<NSV, true>(p, smem, stream)                    \
+                  : launch_ctc<NSV, false>(p, smem, stream);
+  switch (ns) {
+    SB_CTC_CASE(1)
+    SB_CTC_CASE(2)
+    SB_CTC_CASE(4)
+    SB_CTC_CASE(8)
+  }
+#undef SB_CTC_CASE
+  return SB_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,352 @@
+// sb_gemm_bf16_tn: C[M,N] (f32) (+)= A[M,K] (bf16, K-major) * B[N,K]^T (bf16, K-major) (+ bias[N])
+//
+// Hand-written sm_100a GEMM used for every dense contraction on the encoder path
+// (GRU input projections X*W_ih^T, their dgrad/wgrad, the output projection and its grads;
+//  reference: nn.GRU / LinearND in speech/models/model.py:35-39,115-133, which reach cuDNN/cuBLAS).
+//
+//   * persistent grid (one CTA per SM), static tile schedule, N-fastest rasterisation so the
+//     A row-panel is served from L2 to the CTAs working on its N tiles
+//   * warp 0   : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes of 64 bf16 along K)
+//   * warp 1   : tcgen05.mma issuer (one elected lane), accumulators in TMEM, 2 accumulator stages
+//   * warps 2-5: epilogue (tcgen05.ld 32x32b -> bias / row-remap -> st.global or red.add)
+//   * smem ring of kStages {A 128x64, B BNx64} tiles, full/empty mbarriers
+//
+// Roofline: tensor (bf16 dense).  Algorithmic FLOPs = 2*M*N*K per launch.
+#include "common.cuh"
+#include <cuda.h>
+#include <stdio.h>
+
+#include "../../include/speech_b200.h"
+
+namespace sb {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+
+struct GemmParams {
+  float* C;
+  const float* bias;
+  long long ldc;
+  int M, N, K;
+  int k_blocks_total;   // ceil(K / 64)
+  int split_k;          // >= 1
+  int flags;            // SB_GEMM_ACCUMULATE | SB_GEMM_ROW_REMAP
+  int remap_B, remap_T, valid_B;
+  int m_tiles, n_tiles;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytes = (BM + BN) * BK * 2;
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);  // 2 accumulator stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned tile ring (SWIZZLE_128B requirement)
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                  // [kStages]
+  uint64_t* empty_bar = bars + kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;   // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total_work = tiles_mn * p.split_k;
+  const int kb_per_split = (p.k_blocks_total + p.split_k - 1) / p.split_k;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w / tiles_mn;
+        const int t = w - split * tiles_mn;
+        const int m_blk = t / p.n_tiles;
+        const int n_blk = t - m_blk * p.n_tiles;
+        const int kb0 = split * kb_per_split;
+        int kb1 = kb0 + kb_per_split;
+        if (kb1 > p.k_blocks_total) kb1 = p.k_blocks_total;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * Cfg::kStageBytes;
+          uint8_t* sb_ = sa + BM * BK * 2;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sb_, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w / tiles_mn;
+      const int kb0 = split * kb_per_split;
+      int kb1 = kb0 + kb_per_split;
+      if (kb1 > p.k_blocks_total) kb1 = p.k_blocks_total;
+      if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      __syncwarp();
+      tc_fence_after_sync();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (lane == 0) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint32_t sb_ = sa + BM * BK * 2;
+          const uint64_t da = umma_desc_sw128_kmajor(sa);
+          const uint64_t db = umma_desc_sw128_kmajor(sb_);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the >>4 field
+            umma_bf16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (kb1 <= kb0 && lane == 0) {
+        // empty K range (can only happen with an over-split K): nothing accumulated
+        umma_commit(&tfull_bar[acc]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w / tiles_mn;
+      const int t = w - split * tiles_mn;
+      const int m_blk = t / p.n_tiles;
+      const int n_blk = t - m_blk * p.n_tiles;
+      const int kb0 = split * kb_per_split;
+      const bool has_k = kb0 < p.k_blocks_total;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const int m = m_blk * BM + sub * 32 + lane;
+      bool row_ok = m < p.M;
+      long long out_row = m;
+      if (p.flags & SB_GEMM_ROW_REMAP) {
+        const int b = m % p.remap_B;
+        const int tt = m / p.remap_B;
+        row_ok = row_ok && (b < p.valid_B);
+        out_row = (long long)b * p.remap_T + tt;
+      }
+      float* crow = p.C + out_row * p.ldc;
+      const bool add_bias = (p.bias != nullptr) && (split == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * BN + c * 32;
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (row_ok && has_k && n0 < p.N) {
+          if (p.flags & SB_GEMM_ACCUMULATE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + j;
+              if (n < p.N) {
+                float x = __uint_as_float(v[j]);
+                if (add_bias) x += __ldg(p.bias + n);
+                atomicAdd(crow + n, x);
+              }
+            }
+          } else if (vec_ok && n0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              o.x = __uint_as_float(v[j + 0]);
+              o.y = __uint_as_float(v[j + 1]);
+              o.z = __uint_as_float(v[j + 2]);
+              o.w = __uint_as_float(v[j + 3]);
+              if (add_bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              }
+              *reinterpret_cast<float4*>(crow + n0 + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + j;
+              if (n < p.N) {
+                float x = __uint_as_float(v[j]);
+                if (add_bias) x += __ldg(p.bias + n);
+                crow[n] = x;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements);
+// box = 64 columns x box_rows rows, SWIZZLE_128B, out-of-bounds reads return zero.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
+                      long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return SB_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld * 2) & 15) != 0) return SB_ERR_INVALID;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SB_OK : SB_ERR_CUDA;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return SB_ERR_CUDA;
+    attr_set = true;
+  }
+  p.n_tiles = (p.N + BN - 1) / BN;
+  const int total = p.m_tiles * p.n_tiles * p.split_k;
+  int grid = device_sm_count();
+  if (grid > total) grid = total;
+  gemm_bf16_tn_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, float* C,
+                               long long ldc, const float* bias, int M, int N, int K, int flags,
+                               int split_k, int remap_B, int remap_T, int valid_B,
+                               void* stream_) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return SB_ERR_INVALID;
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1 && !(flags & SB_GEMM_ACCUMULATE)) return SB_ERR_INVALID;
+  if ((flags & SB_GEMM_ROW_REMAP) && (remap_B <= 0 || remap_T <= 0)) return SB_ERR_INVALID;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  GemmParams p;
+  p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
+  p.k_blocks_total = (K + BK - 1) / BK;
+  if (split_k > p.k_blocks_total) split_k = p.k_blocks_total;
+  p.split_k = split_k; p.flags = flags;
+  p.remap_B = remap_B; p.remap_T = remap_T; p.valid_B = valid_B;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = 0;
+
+  // tile-N choice: the widest tile that still leaves >= ~1 wave of work
+  const int sms = device_sm_count();
+  int bn;
+  if (N <= 32) bn = 32;
+  else if (N <= 64) bn = 64;
+  else if (N <= 128) bn = 128;
+  else {
+    const long long tiles256 = (long long)p.m_tiles * ((N + 255) / 256) * split_k;
+    bn = (tiles256 >= sms || N > 2048) ? 256 : 128;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, BM);
+  if (rc != SB_OK) return rc;
+  rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, bn);
+  if (rc != SB_OK) return rc;
+  switch (bn) {
+    case 32: return launch_gemm<32>(ta, tb, p, stream);
+    case 64: return launch_gemm<64>(ta, tb, p, stream);
+    case 128: return launch_gemm<128>(ta, tb, p, stream);
+    default: return launch_gemm<256>(ta, tb, p, stream);
+  }
+}
