@@ -69,6 +69,39 @@ int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, 
                     long long ldc, const float* bias, int M, int N, int K, int flags, int split_k,
                     int remap_B, int remap_T, int valid_B, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * GRU recurrence (T-serial part of nn.GRU; the time-batched input projection is sb_gemm_bf16_tn).
+ * Replaces: cuDNN RNN behind self.rnn in speech/models/model.py:35-39,73 (gate order r,z,n;
+ *           bidirectional) and Transducer.dec_rnn, speech/models/transducer_model.py:23-26,68.
+ * Internal layout is TIME-MAJOR with the batch padded to a multiple of 8: row m = t*Bp + b.
+ *   gi     [T*Bp][ndir*3H] f32   X W_ih^T + b_ih (forward-direction gates first)
+ *   whh    [ndir][3H][H]   bf16  recurrent weights;   bhh [ndir][3H] f32
+ *   y      [T*Bp][ndir*H]  f32   h_t (out)
+ *   xn     [T*Bp][ndir*H]  bf16  h_t (out; operand of the next projection)
+ *   xnT    [ndir*H][(T+2)*Bp] bf16 h_t transposed, column (t+1)*Bp+b; columns of t=-1 and t=T
+ *          must be zero on entry (out; may be NULL)
+ *   gates  [T*Bp][ndir][4][H] f32 saved r,z,n,(W_hn h + b_hn) for backward (out; may be NULL)
+ *   barrier [ndir] u32 scratch for the per-direction grid barrier
+ * Constraints: H % 16 == 0, Bp % 8 == 0, Bp <= 128, ndir*H/16 <= number of SMs.
+ * ------------------------------------------------------------------------------------- */
+int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bhh, float* y, void* xn_bf16,
+               void* xnT_bf16, float* gates, unsigned int* barrier, int T, int Bp, int H, int ndir,
+               void* stream);
+
+/* Backward through the recurrence.
+ *   dy     [T*Bp][ndir*H] f32  gradient w.r.t. y
+ *   whhT   [ndir][H][3H] bf16  W_hh transposed
+ *   dgi    [T*Bp][ndir*3H] bf16 (out) gradient w.r.t. gi        -> dX = dgi * W_ih
+ *   dgiT   [ndir*3H][T*Bp] bf16 (out) same, transposed          -> dW_ih, dW_hh (r,z rows)
+ *   dghnT  [ndir][H][T*Bp] bf16 (out) r * dn_pre, transposed    -> dW_hh (n rows)
+ *   dbih, dbhh [ndir*3H] f32 accumulated (+=)
+ */
+int sb_gru_bwd_workspace_size(int Bp, int H, int ndir, size_t* bytes);
+int sb_gru_bwd(const float* dy, const float* y, const float* gates, const void* whhT_bf16,
+               void* dgi_bf16, void* dgiT_bf16, void* dghnT_bf16, float* dbih, float* dbhh,
+               void* workspace, size_t workspace_bytes, unsigned int* barrier, int T, int Bp, int H,
+               int ndir, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

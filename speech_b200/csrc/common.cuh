@@ -23,6 +23,9 @@ enum : int {
   SB_ERR_WORKSPACE = 4,
 };
 
+// host helper (defined in gemm.cu): number of SMs of the current device
+int device_sm_count();
+
 // A spin-wait that can never hang the GPU box: after ~2^31 polls (seconds) the kernel traps.
 #define SB_SPIN_LIMIT (1u << 30)
 

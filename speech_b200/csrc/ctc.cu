@@ -16,6 +16,10 @@
 //   The (T x V) log-softmax of the utterance is staged ONCE in shared memory with coalesced
 //   reads of the logits (116 KB at T=1000, V=29); lattice rows ping-pong in shared memory.
 //
+// Precision: lattice rows are renormalised every 32 steps (the row maximum is subtracted and
+// accumulated into a per-side scalar kept in double), so fp32 log-space values stay O(10) even for
+// T in the thousands and the 1e-4 parity bar holds for long utterances.
+//
 // Roofline: nominally HBM (read logits + write grads = 2*B*T*V*4 bytes), in practice bound by
 // the T-step serial chain.
 #include "common.cuh"
@@ -36,7 +40,8 @@ struct CtcParams {
   const int* label_lens;
   const int* act_lens;
   float* costs;         // (B)
-  float* ws;            // (B, T, S_stride) lattice spill
+  float* ws;            // (B, T, S_stride) lattice spill (rows stored relative to offs)
+  double* offs;         // (B, T) scalar offset of each spilled row
   int B, T, V, blank, S_stride;
 };
 
@@ -70,14 +75,16 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
   const float* acts = p.acts + (size_t)b * p.T * V;
   float* grads = p.grads ? p.grads + (size_t)b * p.T * V : nullptr;
   float* ws = p.ws + (size_t)b * p.T * p.S_stride;
+  double* offs = p.offs + (size_t)b * p.T;
 
   // ---- shared memory carve-up ----
   constexpr int SP = NS * CTC_SIDE + 4;        // padded lattice row (2 pads each end)
   float* row_buf = smem;                        // [2 sides][2][SP]
   float* occ = row_buf + 4 * SP;                // [2 sides][2][V]
-  float* red = occ + 4 * V;                     // [32] reduction scratch
-  float* lse_t = red + 32;                      // [T] (only !STAGED)
-  float* lp = STAGED ? (red + 32) : nullptr;    // [T*V] (only STAGED)
+  float* red = occ + 4 * V;                     // [48] reduction scratch
+  float* nred = red + 32;                       // [2 sides][8] renormalisation maxima
+  float* lse_t = red + 48;                      // [T] (only !STAGED)
+  float* lp = STAGED ? (red + 48) : nullptr;    // [T*V] (only STAGED)
 
   for (int k = tid; k < 4 * SP; k += 2 * CTC_SIDE) row_buf[k] = CTC_NEG_INF;
   for (int k = tid; k < 4 * V; k += 2 * CTC_SIDE) occ[k] = 0.f;
@@ -146,7 +153,31 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
 
   float* my_rows = row_buf + side * 2 * SP + 2;  // +2: leading pad so [s-2] is addressable
   float* my_occ = occ + side * 2 * V;
+  float* my_nred = nred + side * 8;
   const int Th = T / 2;
+  const int swarp = i >> 5;  // warp index inside the side
+  double C = 0.0;            // offset of this side's smem rows: true value = stored + C
+
+  // Subtract the row maximum from the row just written (values in vals[]) and fold it into C.
+  // Two side barriers; executed every 32 steps by all 256 threads of the side.
+  auto renormalise = [&](float* cur, float (&vals)[NS]) {
+    float m = CTC_NEG_INF;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) m = fmaxf(m, vals[q]);
+    m = warp_max(m);
+    if (lane == 0) my_nred[swarp] = m;
+    side_barrier(side);
+    m = my_nred[0];
+#pragma unroll
+    for (int w = 1; w < CTC_SIDE / 32; ++w) m = fmaxf(m, my_nred[w]);
+    if (m != CTC_NEG_INF) {
+#pragma unroll
+      for (int q = 0; q < NS; ++q)
+        if (valid[q]) cur[i + CTC_SIDE * q] = vals[q] - m;
+      C += (double)m;
+    }
+    side_barrier(side);
+  };
 
   // ------------------------------------------------------------------------------------------
   // phase 1: alpha rows [0, Th), beta rows [Th, T) ; each row is spilled to the workspace
@@ -157,6 +188,7 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
       const int t = side == 0 ? it : (T - 1 - it);
       float* cur = my_rows + (it & 1) * SP;
       const float* prev = my_rows + ((it & 1) ^ 1) * SP;
+      float vals[NS];
 #pragma unroll
       for (int q = 0; q < NS; ++q) {
         const int s = i + CTC_SIDE * q;
@@ -174,17 +206,19 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
           cur[s] = v;
           ws[(size_t)t * p.S_stride + s] = v;
         }
+        vals[q] = v;
       }
+      if (i == 0) offs[t] = C;
       side_barrier(side);
+      if ((it & 31) == 31) renormalise(cur, vals);
     }
   }
   __syncthreads();
 
   // ------------------------------------------------------------------------------------------
-  // meet in the middle: alpha_Th (side 0) x beta_Th (side 1's last row) -> log p(y|x)
+  // meet in the middle: alpha_Th (side 0) x beta_Th (spilled by side 1) -> log p(y|x)
   // ------------------------------------------------------------------------------------------
-  const int beta_last_slot = ((T - Th) - 1) & 1;           // slot holding beta_Th
-  const float* beta_Th = row_buf + 2 * SP + 2 + beta_last_slot * SP;
+  const int beta_last_slot = ((T - Th) - 1) & 1;           // smem slot holding beta_Th
   float a_reg[NS];
   if (side == 0) {
     float* cur = my_rows + (Th & 1) * SP;
@@ -202,7 +236,7 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
         else v = lse3(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : CTC_NEG_INF);
         v += e;
         cur[s] = v;
-        contrib[q] = v + beta_Th[s] - e;
+        contrib[q] = v + ld_cg_f(ws + (size_t)Th * p.S_stride + s) - e;
         local_max = fmaxf(local_max, contrib[q]);
       }
       a_reg[q] = v;
@@ -225,15 +259,16 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
     if (tid == 0) {
       float tot = 0.f;
       for (int w = 0; w < CTC_SIDE / 32; ++w) tot += red[8 + w];
-      const float logp = (m == CTC_NEG_INF) ? CTC_NEG_INF : m + logf(tot);
-      red[16] = logp;
-      p.costs[b] = -logp;
+      double logp = -INFINITY;
+      if (m != CTC_NEG_INF) logp = (double)m + (double)logf(tot) + C + offs[Th];
+      reinterpret_cast<double*>(red + 16)[0] = logp;   // red is 8-byte aligned (see carve-up)
+      p.costs[b] = (float)(-logp);
     }
   }
   __syncthreads();
-  const float logp = red[16];
+  const double logp = reinterpret_cast<const double*>(red + 16)[0];
   if (grads == nullptr) return;
-  if (logp == CTC_NEG_INF) {
+  if (logp == -INFINITY) {
     // infeasible alignment: cost = +inf, gradient defined as zero
     for (int k = tid; k < T * V; k += 2 * CTC_SIDE) grads[k] = 0.f;
     return;
@@ -248,6 +283,7 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
     // beta side restarts its ping-pong so that "prev" of its first step is beta_Th
     const int base = side == 0 ? Th : (beta_last_slot + 1);
     float other[NS];  // spilled row of the other lattice, prefetched one step ahead
+    double other_off = 0.0;
     if (nsteps > 0) {
       const int t0 = side == 0 ? Th : (Th - 1);
 #pragma unroll
@@ -255,6 +291,7 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
         const int s = i + CTC_SIDE * q;
         other[q] = valid[q] ? ld_cg_f(ws + (size_t)t0 * p.S_stride + s) : CTC_NEG_INF;
       }
+      other_off = offs[t0];
     }
     for (int it = 0; it < nsteps; ++it) {
       const int t = side == 0 ? (Th + it) : (Th - 1 - it);
@@ -263,6 +300,7 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
       const float* prev = my_rows + (slot ^ 1) * SP;
       float* occ_t = my_occ + (it & 1) * V;
       float other_next[NS];
+      double other_off_next = 0.0;
       const bool more = it + 1 < nsteps;
       const int tn = side == 0 ? (t + 1) : (t - 1);
 #pragma unroll
@@ -271,13 +309,17 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
         other_next[q] = (more && valid[q]) ? ld_cg_f(ws + (size_t)tn * p.S_stride + s)
                                            : CTC_NEG_INF;
       }
+      if (more) other_off_next = offs[tn];
+      // scalar part of the exponent, formed in double: C_own + C_other(t) - log p
+      const float delta = (float)(C + other_off - logp);
       float blank_sum = 0.f;
+      float vals[NS];
 #pragma unroll
       for (int q = 0; q < NS; ++q) {
         const int s = i + CTC_SIDE * q;
+        float v = CTC_NEG_INF;
         if (valid[q]) {
           const float e = emit(t, cls[q]);
-          float v;
           if (side == 0 && it == 0) {
             v = a_reg[q];
           } else {
@@ -286,10 +328,11 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
             v += e;
             cur[s] = v;
           }
-          const float g = __expf(v + other[q] - e - logp);
+          const float g = __expf((v + other[q] - e) + delta);
           if (s & 1) atomicAdd(occ_t + cls[q], g);
           else blank_sum += g;
         }
+        vals[q] = v;
       }
       // even threads own the blank states: one shared atomic per warp
       blank_sum = warp_sum(blank_sum);
@@ -299,8 +342,10 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
         grads[t * V + k] = __expf(emit(t, k)) - occ_t[k];
         occ_t[k] = 0.f;
       }
+      if ((it & 31) == 31) renormalise(cur, vals);
 #pragma unroll
       for (int q = 0; q < NS; ++q) other[q] = other_next[q];
+      other_off = other_off_next;
     }
   }
 }
@@ -337,7 +382,8 @@ extern "C" int sb_ctc_workspace_size(int B, int T, int V, int max_label_len, siz
   if (!bytes || B <= 0 || T < 0 || V <= 0 || max_label_len < 0) return SB_ERR_INVALID;
   const int ns = ctc_ns_for(max_label_len);
   if (ns < 0) return SB_ERR_UNSUPPORTED;
-  *bytes = (size_t)B * (size_t)(T > 0 ? T : 1) * (size_t)(ns * CTC_SIDE) * sizeof(float) + 256;
+  const size_t Tn = (size_t)(T > 0 ? T : 1);
+  *bytes = (size_t)B * Tn * (size_t)(ns * CTC_SIDE) * sizeof(float) + (size_t)B * Tn * sizeof(double) + 512;
   return SB_OK;
 }
 
@@ -360,10 +406,11 @@ extern "C" int sb_ctc_fwd_bwd(const float* acts, float* grads, const int* labels
   CtcParams p;
   p.acts = acts; p.grads = grads; p.labels = labels_dev; p.label_off = label_offsets_dev;
   p.label_lens = label_lens_dev; p.act_lens = act_lens_dev; p.costs = costs;
-  p.ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  p.offs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  p.ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.offs + (size_t)B * T) + 255) & ~(uintptr_t)255);
   p.B = B; p.T = T; p.V = V; p.blank = blank; p.S_stride = ns * CTC_SIDE;
 
-  const size_t fixed = (size_t)(4 * (ns * CTC_SIDE + 4) + 4 * V + 32) * sizeof(float);
+  const size_t fixed = (size_t)(4 * (ns * CTC_SIDE + 4) + 4 * V + 48) * sizeof(float) + 8;
   const size_t staged_bytes = fixed + (size_t)T * V * sizeof(float);
   const size_t unstaged_bytes = fixed + (size_t)T * sizeof(float);
   const size_t limit = 220 * 1024;

@@ -1,0 +1,629 @@
+// Persistent GRU recurrence kernels (forward and backward in time) for sm_100a.
+//
+// Replaces the cuDNN RNN reached through nn.GRU in the reference encoder
+// (speech/models/model.py:35-39 construction, :73 call; gate order r,z,n; bidirectional halves
+// are summed by the caller, model.py:75-77) and the pred-net GRU of the transducer
+// (speech/models/transducer_model.py:23-26,68).
+//
+// The time-batched input projection gi = X W_ih^T + b_ih is done for all T at once by
+// sb_gemm_bf16_tn; these kernels run the T-serial part.  One cooperative launch per layer covers
+// BOTH directions:
+//   * CTA c of direction d owns 16 hidden units j0..j0+15: its 48 rows of W_hh (r,z,n) stay
+//     resident in shared memory (bf16, UMMA K-major SWIZZLE_128B chunks) for all T steps;
+//   * per step the CTA all-gathers h_{t-1} (bf16, written by every CTA of the direction in the
+//     previous step) from L2 into a 4-slot smem ring, and one thread issues tcgen05.mma
+//     D[batch(128) x 48] += h_{t-1}[batch x 64] * Wslice[48 x 64]^T per K chunk, accumulating
+//     in TMEM; loads and MMAs are pipelined through full/empty mbarriers;
+//   * thread b (= TMEM lane = batch row) reads its 48 accumulators with tcgen05.ld, applies the
+//     gate math in fp32 (h_{t-1} of its own units lives in registers across steps) and writes
+//     h_t as fp32 (Y), bf16 (next GEMM operand) and bf16-transposed (wgrad operand);
+//   * a per-direction grid barrier (red.release / ld.acquire on a global counter) separates steps.
+// The backward kernel has the same structure with W_hh^T resident (16 rows x 3H) and the
+// all-gather over the pre-activation gradients dgh_t (batch x 3H).
+//
+// Roofline: the MMAs are tensor work but each step is bound by the all-gather + barrier latency;
+// DESIGN.md reports us/step next to the tensor-pipe share.
+#include "common.cuh"
+#include <cooperative_groups.h>
+
+#include "../../include/speech_b200.h"
+
+namespace sb {
+
+static constexpr int GRU_HC = 16;           // hidden units per CTA
+static constexpr int GRU_RING = 4;          // smem ring slots for the gathered operand
+static constexpr int GRU_SLOT_BYTES = 128 * 128;  // [128 rows x 64 bf16] SWIZZLE_128B tile
+static constexpr int GRU_LOADERS = 256;     // warps 0..7 gather; warps 0..3 also run the epilogue
+static constexpr int GRU_THREADS = GRU_LOADERS + 32;  // + warp 8: MMA issuer / TMEM owner
+
+typedef __nv_bfloat16 bf16;
+
+struct GruFwdParams {
+  const float* gi;     // [T*Bp][ndir*3H]  input projections (b_ih already added)
+  const bf16* whh;     // [ndir][3H][H]    recurrent weights, bf16
+  const float* bhh;    // [ndir][3H]
+  float* y;            // [T*Bp][ndir*H]   h_t fp32
+  bf16* xn;            // [T*Bp][ndir*H]   h_t bf16 (operand of the next projection)
+  bf16* xnT;           // [ndir*H][(T+2)*Bp] h_t bf16 transposed, column (t+1)*Bp+b ; may be null
+  float* gates;        // [T*Bp][ndir][4][H] saved r,z,n,hn for backward ; may be null
+  unsigned int* barrier;  // [ndir] zero-initialised counters
+  int T, Bp, H, ndir;
+};
+
+struct GruBwdParams {
+  const float* dy;     // [T*Bp][ndir*H]   gradient w.r.t. this layer's output
+  const float* y;      // [T*Bp][ndir*H]   forward h_t (fp32)
+  const float* gates;  // [T*Bp][ndir][4][H]
+  const bf16* whhT;    // [ndir][H][3H]    W_hh^T, bf16
+  bf16* dgi;           // [T*Bp][ndir*3H]  d(pre-activation) of the input projection, bf16
+  bf16* dgiT;          // [ndir*3H][T*Bp]  same, transposed (wgrad operand)
+  bf16* dghnT;         // [ndir][H][T*Bp]  dn_pre * r, transposed (wgrad of W_hn)
+  bf16* xchg;          // [ndir][2][Bp][3H] per-step exchange of dgh_t
+  float* dbih;         // [ndir*3H] += sum_{t,b} dgi
+  float* dbhh;         // [ndir*3H] += sum_{t,b} dgh
+  unsigned int* barrier;  // [ndir]
+  int T, Bp, H, ndir;
+};
+
+// ---- per-direction grid barrier ------------------------------------------------------------
+SB_DEVINL void grid_arrive(unsigned int* ctr) { red_release_gpu_add(ctr, 1u); }
+SB_DEVINL void grid_wait(const unsigned int* ctr, unsigned int target) {
+  unsigned int spins = 0;
+  while (ld_acquire_gpu(ctr) < target) {
+    if (++spins > SB_SPIN_LIMIT) __trap();
+  }
+}
+SB_DEVINL void loaders_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(GRU_LOADERS) : "memory");
+}
+
+struct GruSmem {
+  uint8_t* wtile;   // resident weight chunks
+  uint8_t* ring;    // GRU_RING slots
+  uint64_t* full;   // [GRU_RING]
+  uint64_t* empty;  // [GRU_RING]
+  uint64_t* accfull;
+  uint32_t* tmem_slot;
+  float* scratch;   // [64]
+};
+
+SB_DEVINL GruSmem carve(uint8_t* raw, int wbytes) {
+  GruSmem s;
+  s.wtile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) &
+                                       ~static_cast<uintptr_t>(1023));
+  s.ring = s.wtile + wbytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.ring + GRU_RING * GRU_SLOT_BYTES);
+  s.full = bars;
+  s.empty = bars + GRU_RING;
+  s.accfull = bars + 2 * GRU_RING;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GRU_RING + 1);
+  s.scratch = reinterpret_cast<float*>(bars + 2 * GRU_RING + 2);
+  return s;
+}
+
+// Gather a [Bp x Kdim] bf16 row-major operand (row stride src_ld elements) from L2 into the smem
+// ring, chunk by chunk (64 columns each), for the MMA warp.  Executed by the 256 loader threads.
+// `fill` is the running chunk counter (ring position / phase) shared with the MMA warp.
+SB_DEVINL void gather_operand(const GruSmem& s, const bf16* src, long long src_ld, int Bp, int Kdim,
+                              int nchunks, unsigned int& fill) {
+  const int tid = threadIdx.x;
+  const int pieces = Bp * 8;  // 16-byte pieces per chunk
+  for (int c0 = 0; c0 < nchunks; c0 += 2) {
+    // issue all global loads of two chunks first (MLP), then commit them to shared memory
+    uint4 v[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = c0 + u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int pc = tid + q * GRU_LOADERS;
+        v[u][q] = make_uint4(0, 0, 0, 0);
+        if (c < nchunks && pc < pieces) {
+          const int row = pc >> 3, c16 = pc & 7;
+          const int k = c * 64 + c16 * 8;
+          if (k < Kdim) v[u][q] = ld_cg_u4(src + (long long)row * src_ld + k);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = c0 + u;
+      if (c >= nchunks) break;
+      const unsigned int slot = fill % GRU_RING;
+      const unsigned int par = (fill / GRU_RING) & 1u;
+      mbar_wait(&s.empty[slot], par ^ 1u);
+      uint8_t* dst = s.ring + slot * GRU_SLOT_BYTES;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int pc = tid + q * GRU_LOADERS;
+        if (pc < pieces) {
+          const int row = pc >> 3, c16 = pc & 7;
+          *reinterpret_cast<uint4*>(dst + sw128_offset(row, c16)) = v[u][q];
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&s.full[slot]);
+      ++fill;
+    }
+  }
+}
+
+// MMA warp: consume `nchunks` ring slots against the resident weight chunks (rows_w rows each).
+template <int N>
+SB_DEVINL void mma_consume(const GruSmem& s, uint32_t tmem_d, int nchunks, int wchunk_bytes,
+                           unsigned int& fill) {
+  constexpr uint32_t idesc = umma_idesc_bf16_f32(128, N);
+  for (int c = 0; c < nchunks; ++c) {
+    const unsigned int slot = fill % GRU_RING;
+    const unsigned int par = (fill / GRU_RING) & 1u;
+    mbar_wait(&s.full[slot], par);
+    tc_fence_after_sync();
+    const uint64_t da = umma_desc_sw128_kmajor(smem_u32(s.ring + slot * GRU_SLOT_BYTES));
+    const uint64_t db = umma_desc_sw128_kmajor(smem_u32(s.wtile + c * wchunk_bytes));
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                   (c > 0 || k > 0) ? 1u : 0u);
+    umma_commit(&s.empty[slot]);
+    ++fill;
+  }
+  umma_commit(s.accfull);
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+__global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int H = p.H, Bp = p.Bp, T = p.T;
+  const int nC = H / GRU_HC;
+  const int dir = blockIdx.x / nC;
+  const int j0 = (blockIdx.x % nC) * GRU_HC;
+  const int nchunks = (H + 63) / 64;
+  constexpr int WCHUNK = 48 * 128;  // 48 rows x 64 bf16
+  const GruSmem s = carve(smem_raw, nchunks * WCHUNK);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int D = p.ndir * H;
+  const long long ldT = (long long)(T + 2) * Bp;
+
+  // ---- one-time setup: zero the ring, stage this CTA's 48 weight rows, barriers, TMEM ----
+  for (int k = tid; k < GRU_RING * GRU_SLOT_BYTES / 16; k += GRU_THREADS)
+    reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
+  {
+    const int pieces_per_row = nchunks * 8;
+    for (int k = tid; k < 48 * pieces_per_row; k += GRU_THREADS) {
+      const int r = k / pieces_per_row, pc = k % pieces_per_row;
+      const int g = r / GRU_HC, jj = r % GRU_HC;
+      const int col = pc * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (col < H)
+        v = *reinterpret_cast<const uint4*>(p.whh + ((long long)dir * 3 * H + g * H + j0 + jj) * H +
+                                            col);
+      *reinterpret_cast<uint4*>(s.wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+    }
+    if (tid < 48) {
+      const int g = tid / GRU_HC, jj = tid % GRU_HC;
+      s.scratch[tid] = p.bhh[dir * 3 * H + g * H + j0 + jj];
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < GRU_RING; ++i) {
+      mbar_init(&s.full[i], GRU_LOADERS);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(s.accfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(s.tmem_slot, 64);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s.tmem_slot;
+  unsigned int* ctr = p.barrier + dir;
+
+  if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if ((tid & 31) == 0) {
+      unsigned int fill = 0;
+      for (int step = 1; step < T; ++step) mma_consume<48>(s, tmem_base, nchunks, WCHUNK, fill);
+    }
+  } else {
+    // ===================== loaders (+ epilogue on warps 0..3) =====================
+    unsigned int fill = 0;
+    float hprev[GRU_HC];
+#pragma unroll
+    for (int jj = 0; jj < GRU_HC; ++jj) hprev[jj] = 0.f;
+    float bias[48];
+    if (tid < 128) {
+#pragma unroll
+      for (int r = 0; r < 48; ++r) bias[r] = s.scratch[r];
+    }
+    for (int step = 0; step < T; ++step) {
+      const int t = dir == 0 ? step : (T - 1 - step);
+      // prefetch this step's input projections (independent of the recurrence)
+      float gi[48];
+      const bool active = tid < 128 && tid < Bp;
+      if (active) {
+        const float* g = p.gi + ((long long)t * Bp + tid) * (p.ndir * 3 * H) + dir * 3 * H + j0;
+#pragma unroll
+        for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(g + gg * H) + q);
+            gi[gg * 16 + q * 4 + 0] = v.x; gi[gg * 16 + q * 4 + 1] = v.y;
+            gi[gg * 16 + q * 4 + 2] = v.z; gi[gg * 16 + q * 4 + 3] = v.w;
+          }
+      }
+      if (step > 0) {
+        if (tid == 0) grid_wait(ctr, (unsigned int)nC * step);
+        loaders_barrier();
+        const int tp = dir == 0 ? t - 1 : t + 1;
+        gather_operand(s, p.xn + (long long)tp * Bp * D + dir * H, D, Bp, H, nchunks, fill);
+      }
+      if (tid < 128) {
+        float acc[48];
+        if (step > 0) {
+          mbar_wait(s.accfull, (step - 1) & 1);
+          tc_fence_after_sync();
+          uint32_t v[16];
+#pragma unroll
+          for (int gg = 0; gg < 3; ++gg) {
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + gg * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) acc[gg * 16 + jj] = __uint_as_float(v[jj]);
+          }
+          tc_fence_before_sync();
+        } else {
+#pragma unroll
+          for (int r = 0; r < 48; ++r) acc[r] = 0.f;
+        }
+        if (active) {
+          const long long m = (long long)t * Bp + tid;
+          float hn[GRU_HC], rr[GRU_HC], zz[GRU_HC], nn[GRU_HC];
+#pragma unroll
+          for (int jj = 0; jj < GRU_HC; ++jj) {
+            rr[jj] = sigmoidf_fast(gi[jj] + acc[jj] + bias[jj]);
+            zz[jj] = sigmoidf_fast(gi[16 + jj] + acc[16 + jj] + bias[16 + jj]);
+            hn[jj] = acc[32 + jj] + bias[32 + jj];
+            nn[jj] = tanhf_fast(gi[32 + jj] + rr[jj] * hn[jj]);
+            hprev[jj] = (1.f - zz[jj]) * nn[jj] + zz[jj] * hprev[jj];
+          }
+          float* yo = p.y + m * D + dir * H + j0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            reinterpret_cast<float4*>(yo)[q] =
+                make_float4(hprev[q * 4], hprev[q * 4 + 1], hprev[q * 4 + 2], hprev[q * 4 + 3]);
+          uint4 pk[2];
+          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(hprev[2 * q], hprev[2 * q + 1]);
+          uint4* xo = reinterpret_cast<uint4*>(p.xn + m * D + dir * H + j0);
+          xo[0] = pk[0];
+          xo[1] = pk[1];
+          if (p.xnT) {
+            bf16* xt = p.xnT + (long long)(dir * H + j0) * ldT + (long long)(t + 1) * Bp + tid;
+#pragma unroll
+            for (int jj = 0; jj < GRU_HC; ++jj) xt[jj * ldT] = __float2bfloat16_rn(hprev[jj]);
+          }
+          if (p.gates) {
+            float* go = p.gates + ((m * p.ndir + dir) * 4) * H + j0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              reinterpret_cast<float4*>(go)[q] =
+                  make_float4(rr[q * 4], rr[q * 4 + 1], rr[q * 4 + 2], rr[q * 4 + 3]);
+              reinterpret_cast<float4*>(go + H)[q] =
+                  make_float4(zz[q * 4], zz[q * 4 + 1], zz[q * 4 + 2], zz[q * 4 + 3]);
+              reinterpret_cast<float4*>(go + 2 * H)[q] =
+                  make_float4(nn[q * 4], nn[q * 4 + 1], nn[q * 4 + 2], nn[q * 4 + 3]);
+              reinterpret_cast<float4*>(go + 3 * H)[q] =
+                  make_float4(hn[q * 4], hn[q * 4 + 1], hn[q * 4 + 2], hn[q * 4 + 3]);
+            }
+          }
+          __threadfence();
+        }
+      }
+      loaders_barrier();
+      if (tid == 0) grid_arrive(ctr);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// =============================================================================================
+// backward (reverse of the forward time order of each direction)
+// =============================================================================================
+__global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int H = p.H, Bp = p.Bp, T = p.T;
+  const int nC = H / GRU_HC;
+  const int dir = blockIdx.x / nC;
+  const int j0 = (blockIdx.x % nC) * GRU_HC;
+  const int K3 = 3 * H;
+  const int nchunks = (K3 + 63) / 64;
+  constexpr int WCHUNK = 16 * 128;  // 16 rows x 64 bf16
+  const GruSmem s = carve(smem_raw, nchunks * WCHUNK);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = p.ndir * H;
+  const long long M = (long long)T * Bp;
+
+  for (int k = tid; k < GRU_RING * GRU_SLOT_BYTES / 16; k += GRU_THREADS)
+    reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
+  {
+    // resident operand: rows = the 16 hidden units k0..k0+15 of W_hh^T, K = 3H
+    const int pieces_per_row = nchunks * 8;
+    for (int k = tid; k < 16 * pieces_per_row; k += GRU_THREADS) {
+      const int r = k / pieces_per_row, pc = k % pieces_per_row;
+      const int col = pc * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (col < K3)
+        v = *reinterpret_cast<const uint4*>(p.whhT + ((long long)dir * H + j0 + r) * K3 + col);
+      *reinterpret_cast<uint4*>(s.wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < GRU_RING; ++i) {
+      mbar_init(&s.full[i], GRU_LOADERS);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(s.accfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(s.tmem_slot, 32);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s.tmem_slot;
+  unsigned int* ctr = p.barrier + dir;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      unsigned int fill = 0;
+      // the recurrent product is needed for every step except the last one processed
+      for (int step = 0; step + 1 < T; ++step) mma_consume<16>(s, tmem_base, nchunks, WCHUNK, fill);
+    }
+  } else {
+    unsigned int fill = 0;
+    const bool active = tid < 128 && tid < Bp;
+    float dh_rec[GRU_HC];   // dL/dh_t arriving through the recurrence (own 16 units)
+    float db_i[48], db_hn[GRU_HC];
+#pragma unroll
+    for (int jj = 0; jj < GRU_HC; ++jj) { dh_rec[jj] = 0.f; db_hn[jj] = 0.f; }
+#pragma unroll
+    for (int r = 0; r < 48; ++r) db_i[r] = 0.f;
+
+    for (int step = 0; step < T; ++step) {
+      // forward order of dir 0 is t=0..T-1, so its backward order is T-1..0; dir 1 mirrored
+      const int t = dir == 0 ? (T - 1 - step) : step;
+      const int tp = dir == 0 ? t - 1 : t + 1;       // time index of h_{prev} in forward order
+      const bool has_prev = dir == 0 ? (t > 0) : (t < T - 1);
+      bf16* xb = p.xchg + ((long long)(dir * 2 + (step & 1)) * Bp) * K3;
+      float dhz[GRU_HC];
+      if (active) {
+        const long long m = (long long)t * Bp + tid;
+        const float* go = p.gates + ((m * p.ndir + dir) * 4) * H + j0;
+        const float* dyo = p.dy + m * D + dir * H + j0;
+        float rr[GRU_HC], zz[GRU_HC], nn[GRU_HC], hn[GRU_HC], dh[GRU_HC], hp[GRU_HC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(go) + q);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(go + H) + q);
+          const float4 c = __ldg(reinterpret_cast<const float4*>(go + 2 * H) + q);
+          const float4 d = __ldg(reinterpret_cast<const float4*>(go + 3 * H) + q);
+          const float4 e = __ldg(reinterpret_cast<const float4*>(dyo) + q);
+          rr[q * 4] = a.x; rr[q * 4 + 1] = a.y; rr[q * 4 + 2] = a.z; rr[q * 4 + 3] = a.w;
+          zz[q * 4] = b.x; zz[q * 4 + 1] = b.y; zz[q * 4 + 2] = b.z; zz[q * 4 + 3] = b.w;
+          nn[q * 4] = c.x; nn[q * 4 + 1] = c.y; nn[q * 4 + 2] = c.z; nn[q * 4 + 3] = c.w;
+          hn[q * 4] = d.x; hn[q * 4 + 1] = d.y; hn[q * 4 + 2] = d.z; hn[q * 4 + 3] = d.w;
+          dh[q * 4] = e.x; dh[q * 4 + 1] = e.y; dh[q * 4 + 2] = e.z; dh[q * 4 + 3] = e.w;
+        }
+        if (has_prev) {
+          const float* yo = p.y + ((long long)tp * Bp + tid) * D + dir * H + j0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(yo) + q);
+            hp[q * 4] = a.x; hp[q * 4 + 1] = a.y; hp[q * 4 + 2] = a.z; hp[q * 4 + 3] = a.w;
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < GRU_HC; ++jj) hp[jj] = 0.f;
+        }
+        float dr[GRU_HC], dz[GRU_HC], dn[GRU_HC], dnr[GRU_HC];
+#pragma unroll
+        for (int jj = 0; jj < GRU_HC; ++jj) {
+          const float g = dh[jj] + dh_rec[jj];
+          dn[jj] = g * (1.f - zz[jj]) * (1.f - nn[jj] * nn[jj]);
+          dz[jj] = g * (hp[jj] - nn[jj]) * zz[jj] * (1.f - zz[jj]);
+          dr[jj] = dn[jj] * hn[jj] * rr[jj] * (1.f - rr[jj]);
+          dnr[jj] = dn[jj] * rr[jj];
+          dhz[jj] = g * zz[jj];
+          db_i[jj] += dr[jj];
+          db_i[16 + jj] += dz[jj];
+          db_i[32 + jj] += dn[jj];
+          db_hn[jj] += dnr[jj];
+        }
+        // dgi (bf16) row-major for the dX GEMM
+        {
+          bf16* o = p.dgi + m * (p.ndir * K3) + dir * K3 + j0;
+          uint4 pk[2];
+          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dr[2 * q], dr[2 * q + 1]);
+          reinterpret_cast<uint4*>(o)[0] = pk[0]; reinterpret_cast<uint4*>(o)[1] = pk[1];
+          // exchange buffer rows are [dr | dz | dn*r]
+          bf16* x = xb + (long long)tid * K3 + j0;
+          reinterpret_cast<uint4*>(x)[0] = pk[0]; reinterpret_cast<uint4*>(x)[1] = pk[1];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dz[2 * q], dz[2 * q + 1]);
+          reinterpret_cast<uint4*>(o + H)[0] = pk[0]; reinterpret_cast<uint4*>(o + H)[1] = pk[1];
+          reinterpret_cast<uint4*>(x + H)[0] = pk[0]; reinterpret_cast<uint4*>(x + H)[1] = pk[1];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dn[2 * q], dn[2 * q + 1]);
+          reinterpret_cast<uint4*>(o + 2 * H)[0] = pk[0];
+          reinterpret_cast<uint4*>(o + 2 * H)[1] = pk[1];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dnr[2 * q], dnr[2 * q + 1]);
+          reinterpret_cast<uint4*>(x + 2 * H)[0] = pk[0];
+          reinterpret_cast<uint4*>(x + 2 * H)[1] = pk[1];
+        }
+        // transposed copies for the weight-gradient GEMMs (column = t*Bp + b, coalesced over b)
+        {
+          bf16* gt = p.dgiT + ((long long)dir * K3 + j0) * M + m;
+          bf16* nt = p.dghnT + ((long long)dir * H + j0) * M + m;
+#pragma unroll
+          for (int jj = 0; jj < GRU_HC; ++jj) {
+            gt[(long long)jj * M] = __float2bfloat16_rn(dr[jj]);
+            gt[(long long)(H + jj) * M] = __float2bfloat16_rn(dz[jj]);
+            gt[(long long)(2 * H + jj) * M] = __float2bfloat16_rn(dn[jj]);
+            nt[(long long)jj * M] = __float2bfloat16_rn(dnr[jj]);
+          }
+        }
+        __threadfence();
+      }
+      if (step + 1 < T) {
+        loaders_barrier();
+        if (tid == 0) {
+          grid_arrive(ctr);
+          grid_wait(ctr, (unsigned int)nC * (step + 1));
+        }
+        loaders_barrier();
+        gather_operand(s, xb, K3, Bp, K3, nchunks, fill);
+        if (tid < 128) {
+          mbar_wait(s.accfull, step & 1);
+          tc_fence_after_sync();
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+#pragma unroll
+          for (int jj = 0; jj < GRU_HC; ++jj) dh_rec[jj] = __uint_as_float(v[jj]) + dhz[jj];
+        }
+        // all TMEM reads of this step are done before the next step's MMAs may overwrite it:
+        // the next gather only starts after the next grid barrier, which follows this point.
+      }
+    }
+    // ---- bias gradients: reduce the per-batch-row partial sums over the CTA ----
+    loaders_barrier();
+    float* red = s.scratch;  // 64 floats
+    if (tid < 64) red[tid] = 0.f;
+    loaders_barrier();
+    if (tid < 128) {
+#pragma unroll
+      for (int r = 0; r < 48; ++r) {
+        const float v = warp_sum(active ? db_i[r] : 0.f);
+        if (lane == 0) atomicAdd(&red[r], v);
+      }
+#pragma unroll
+      for (int jj = 0; jj < GRU_HC; ++jj) {
+        const float v = warp_sum(active ? db_hn[jj] : 0.f);
+        if (lane == 0) atomicAdd(&red[48 + jj], v);
+      }
+    }
+    loaders_barrier();
+    if (tid < 48) {
+      const int g = tid / GRU_HC, jj = tid % GRU_HC;
+      const int idx = dir * K3 + g * H + j0 + jj;
+      atomicAdd(p.dbih + idx, red[tid]);
+      atomicAdd(p.dbhh + idx, g < 2 ? red[tid] : red[48 + jj]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+static size_t gru_smem_bytes(int wbytes) {
+  return (size_t)wbytes + GRU_RING * GRU_SLOT_BYTES + 1024 /*align*/ + 512 /*barriers+scratch*/;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+static int gru_check(int T, int Bp, int H, int ndir) {
+  if (T <= 0 || Bp <= 0 || H <= 0 || (ndir != 1 && ndir != 2)) return SB_ERR_INVALID;
+  if (H % GRU_HC != 0 || Bp % 8 != 0 || Bp > 128) return SB_ERR_UNSUPPORTED;
+  if (ndir * (H / GRU_HC) > sb::device_sm_count()) return SB_ERR_UNSUPPORTED;
+  return SB_OK;
+}
+
+extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bhh, float* y,
+                          void* xn_bf16, void* xnT_bf16, float* gates, unsigned int* barrier,
+                          int T, int Bp, int H, int ndir, void* stream_) {
+  int rc = gru_check(T, Bp, H, ndir);
+  if (rc != SB_OK) return rc;
+  if (!gi || !whh_bf16 || !bhh || !y || !xn_bf16 || !barrier) return SB_ERR_INVALID;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  GruFwdParams p;
+  p.gi = gi; p.whh = reinterpret_cast<const bf16*>(whh_bf16); p.bhh = bhh; p.y = y;
+  p.xn = reinterpret_cast<bf16*>(xn_bf16); p.xnT = reinterpret_cast<bf16*>(xnT_bf16);
+  p.gates = gates; p.barrier = barrier; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
+  const int nchunks = (H + 63) / 64;
+  const size_t smem = gru_smem_bytes(nchunks * 48 * 128);
+  if (smem > 227 * 1024) return SB_ERR_UNSUPPORTED;
+  if (cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem) != cudaSuccess)
+    return SB_ERR_CUDA;
+  if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * ndir, stream) != cudaSuccess)
+    return SB_ERR_CUDA;
+  void* args[] = {(void*)&p};
+  const int grid = ndir * (H / GRU_HC);
+  if (cudaLaunchCooperativeKernel((void*)gru_fwd_kernel, dim3(grid), dim3(GRU_THREADS), args, smem,
+                                  stream) != cudaSuccess)
+    return SB_ERR_CUDA;
+  return SB_OK;
+}
+
+extern "C" int sb_gru_bwd_workspace_size(int Bp, int H, int ndir, size_t* bytes) {
+  if (!bytes || Bp <= 0 || H <= 0) return SB_ERR_INVALID;
+  *bytes = (size_t)ndir * 2 * Bp * 3 * H * sizeof(bf16) + 256;
+  return SB_OK;
+}
+
+extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
+                          const void* whhT_bf16, void* dgi_bf16, void* dgiT_bf16,
+                          void* dghnT_bf16, float* dbih, float* dbhh, void* workspace,
+                          size_t workspace_bytes, unsigned int* barrier, int T, int Bp, int H,
+                          int ndir, void* stream_) {
+  int rc = gru_check(T, Bp, H, ndir);
+  if (rc != SB_OK) return rc;
+  if (!dy || !y || !gates || !whhT_bf16 || !dgi_bf16 || !dgiT_bf16 || !dghnT_bf16 || !dbih ||
+      !dbhh || !workspace || !barrier)
+    return SB_ERR_INVALID;
+  size_t need = 0;
+  sb_gru_bwd_workspace_size(Bp, H, ndir, &need);
+  if (workspace_bytes < need) return SB_ERR_WORKSPACE;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  GruBwdParams p;
+  p.dy = dy; p.y = y; p.gates = gates; p.whhT = reinterpret_cast<const bf16*>(whhT_bf16);
+  p.dgi = reinterpret_cast<bf16*>(dgi_bf16); p.dgiT = reinterpret_cast<bf16*>(dgiT_bf16);
+  p.dghnT = reinterpret_cast<bf16*>(dghnT_bf16);
+  p.xchg = reinterpret_cast<bf16*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  p.dbih = dbih; p.dbhh = dbhh; p.barrier = barrier; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
+  const int nchunks = (3 * H + 63) / 64;
+  const size_t smem = gru_smem_bytes(nchunks * 16 * 128);
+  if (smem > 227 * 1024) return SB_ERR_UNSUPPORTED;
+  if (cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem) != cudaSuccess)
+    return SB_ERR_CUDA;
+  if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * ndir, stream) != cudaSuccess)
+    return SB_ERR_CUDA;
+  void* args[] = {(void*)&p};
+  const int grid = ndir * (H / GRU_HC);
+  if (cudaLaunchCooperativeKernel((void*)gru_bwd_kernel, dim3(grid), dim3(GRU_THREADS), args, smem,
+                                  stream) != cudaSuccess)
+    return SB_ERR_CUDA;
+  return SB_OK;
+}

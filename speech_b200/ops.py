@@ -1,0 +1,198 @@
+"""Host-side operators over the C ABI: dense contraction and the (bi)GRU stack.
+
+PyTorch is used here for device memory, streams and autograd plumbing only; the arithmetic of
+the recurrence and of every projection runs in the hand-written sm_100a kernels of csrc/.
+Internal activations are TIME-MAJOR with the batch padded to a multiple of 8 (row m = t*Bp + b).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+GEMM_ACCUMULATE = 1
+GEMM_ROW_REMAP = 2
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=None):
+    """out[M,N] (f32) (+)= A[M,K] (bf16) @ B[N,K]^T (bf16) (+ bias).  A/B may be row-strided views.
+
+    remap=(Bp, T, valid_B): rows m = t*Bp + b are written batch-first to row b*T + t.
+    """
+    lib = _lib.load()
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    assert A.stride(1) == 1 and B.stride(1) == 1 and A.shape[1] == B.shape[1]
+    M, K = A.shape
+    N = B.shape[0]
+    flags = 0
+    rB = rT = vB = 0
+    if remap is not None:
+        rB, rT, vB = remap
+        flags |= GEMM_ROW_REMAP
+        rows = vB * rT
+    else:
+        rows = M
+    if out is None:
+        assert not accumulate
+        out = torch.empty(rows, N, dtype=torch.float32, device=A.device)
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and out.shape[0] >= rows
+    if accumulate:
+        flags |= GEMM_ACCUMULATE
+    _lib.check(lib.sb_gemm_bf16_tn(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+                                   out.data_ptr(), out.stride(0), _lib.ptr(bias), M, N, K, flags,
+                                   split_k, rB, rT, vB, _lib.stream_ptr()), "sb_gemm_bf16_tn")
+    return out
+
+
+def _wgrad_split(M, N, K):
+    """split-K factor for the K = T*B weight-gradient contractions (few output tiles, long K)."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    kb = (K + 63) // 64
+    s = max(1, min(kb // 8, (2 * 148) // max(tiles, 1)))
+    return int(s)
+
+
+class GRUStackFunction(torch.autograd.Function):
+    """Multi-layer (bi)directional GRU, semantics of nn.GRU(batch_first=True) with h0 = 0.
+
+    forward(x (B,T,In) f32 cuda, ndir, H, train, *weights) -> (B,T,ndir*H) f32
+    weights: per layer, per direction: w_ih (3H,In_l), w_hh (3H,H), b_ih (3H), b_hh (3H)
+    (the parameter order of nn.GRU: weight_ih_l{k}[_reverse], weight_hh_..., bias_ih_..., bias_hh_...)
+    """
+
+    @staticmethod
+    def forward(ctx, x, ndir, H, *weights):
+        _lib.require_cuda(x, "x")
+        lib = _lib.load()
+        B, T, In = x.shape
+        dev = x.device
+        L = len(weights) // (4 * ndir)
+        Bp = _round_up(B, 8)
+        if Bp > 128:
+            raise _lib.SpeechB200Error("per-GPU batch > 128 not supported by the GRU kernel yet")
+        M = T * Bp
+        D = ndir * H
+        need_grad = any(w.requires_grad for w in weights) or x.requires_grad
+
+        # layer-0 operand: time-major, batch padded, K padded to a multiple of 8, bf16
+        Inp = _round_up(In, 8)
+        X = torch.zeros(T, Bp, Inp, dtype=torch.bfloat16, device=dev)
+        X[:, :B, :In] = x.transpose(0, 1)
+        X = X.view(M, Inp)
+        barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+        saved = []
+        y = None
+        for l in range(L):
+            wl = weights[l * 4 * ndir:(l + 1) * 4 * ndir]
+            w_ih = [wl[d * 4 + 0] for d in range(ndir)]
+            w_hh = [wl[d * 4 + 1] for d in range(ndir)]
+            b_ih = [wl[d * 4 + 2] for d in range(ndir)]
+            b_hh = [wl[d * 4 + 3] for d in range(ndir)]
+            Kl = X.shape[1]
+            wih_cat = torch.zeros(ndir * 3 * H, Kl, dtype=torch.bfloat16, device=dev)
+            wih_cat[:, :w_ih[0].shape[1]] = torch.cat([w.detach() for w in w_ih], 0)
+            bih_cat = torch.cat([b.detach() for b in b_ih]).float().contiguous()
+            whh = torch.stack([w.detach() for w in w_hh]).to(torch.bfloat16).contiguous()
+            bhh = torch.stack([b.detach() for b in b_hh]).float().contiguous()
+            gi = gemm_bf16_tn(X, wih_cat, bias=bih_cat)
+            y = torch.empty(M, D, dtype=torch.float32, device=dev)
+            xn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+            xnT = gates = None
+            if need_grad:
+                xnT = torch.zeros(D, (T + 2) * Bp, dtype=torch.bfloat16, device=dev)
+                gates = torch.empty(M, ndir, 4, H, dtype=torch.float32, device=dev)
+            _lib.check(lib.sb_gru_fwd(gi.data_ptr(), whh.data_ptr(), bhh.data_ptr(), y.data_ptr(),
+                                      xn.data_ptr(), _lib.ptr(xnT), _lib.ptr(gates),
+                                      barrier.data_ptr(), T, Bp, H, ndir, _lib.stream_ptr()),
+                       "sb_gru_fwd")
+            if need_grad:
+                saved.append((X, y, gates, xnT))
+            X = xn
+        ctx.saved = saved
+        ctx.weights = weights
+        ctx.dims = (B, T, In, Bp, H, ndir, L)
+        ctx.top_bf16 = X  # bf16 copy of the top layer output (time-major), used by fused heads
+        out = y.view(T, Bp, D)[:, :B].transpose(0, 1).contiguous()
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        B, T, In, Bp, H, ndir, L = ctx.dims
+        weights = ctx.weights
+        dev = dout.device
+        M = T * Bp
+        D = ndir * H
+        K3 = 3 * H
+        dY = torch.zeros(T, Bp, D, dtype=torch.float32, device=dev)
+        dY[:, :B] = dout.transpose(0, 1)
+        dY = dY.view(M, D)
+        barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.sb_gru_bwd_workspace_size(Bp, H, ndir, ctypes.byref(nbytes)), "ws")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        grads = [None] * len(weights)
+        for l in reversed(range(L)):
+            X, y, gates, xnT = ctx.saved[l]
+            wl = weights[l * 4 * ndir:(l + 1) * 4 * ndir]
+            Kl = X.shape[1]
+            In_l = wl[0].shape[1]
+            whhT = torch.stack([wl[d * 4 + 1].detach().t() for d in range(ndir)]) \
+                .to(torch.bfloat16).contiguous()                        # [ndir][H][3H]
+            dgi = torch.empty(M, ndir * K3, dtype=torch.bfloat16, device=dev)
+            dgiT = torch.empty(ndir * K3, M, dtype=torch.bfloat16, device=dev)
+            dghnT = torch.empty(ndir, H, M, dtype=torch.bfloat16, device=dev)
+            dbih = torch.zeros(ndir * K3, dtype=torch.float32, device=dev)
+            dbhh = torch.zeros(ndir * K3, dtype=torch.float32, device=dev)
+            _lib.check(lib.sb_gru_bwd(dY.data_ptr(), y.data_ptr(), gates.data_ptr(),
+                                      whhT.data_ptr(), dgi.data_ptr(), dgiT.data_ptr(),
+                                      dghnT.data_ptr(), dbih.data_ptr(), dbhh.data_ptr(),
+                                      ws.data_ptr(), nbytes.value, barrier.data_ptr(), T, Bp, H,
+                                      ndir, _lib.stream_ptr()), "sb_gru_bwd")
+            # ---- weight gradients: K = T*Bp contractions on the transposed copies ----
+            if l > 0:
+                XT = ctx.saved[l - 1][3][:, Bp:Bp + M]                   # [In_l][M] view
+            else:
+                XT = X.t().contiguous()                                   # [Kl][M]
+            dwih = torch.zeros(ndir * K3, XT.shape[0], dtype=torch.float32, device=dev)
+            gemm_bf16_tn(dgiT, XT, out=dwih, accumulate=True,
+                         split_k=_wgrad_split(ndir * K3, XT.shape[0], M))
+            for d in range(ndir):
+                hprevT = xnT[d * H:(d + 1) * H, (0 if d == 0 else 2 * Bp):][:, :M]
+                dwhh = torch.zeros(K3, H, dtype=torch.float32, device=dev)
+                sk = _wgrad_split(2 * H, H, M)
+                gemm_bf16_tn(dgiT[d * K3:d * K3 + 2 * H], hprevT, out=dwhh[:2 * H],
+                             accumulate=True, split_k=sk)
+                gemm_bf16_tn(dghnT[d], hprevT, out=dwhh[2 * H:], accumulate=True, split_k=sk)
+                grads[l * 4 * ndir + d * 4 + 0] = dwih[d * K3:(d + 1) * K3, :In_l]
+                grads[l * 4 * ndir + d * 4 + 1] = dwhh
+                grads[l * 4 * ndir + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
+                grads[l * 4 * ndir + d * 4 + 3] = dbhh[d * K3:(d + 1) * K3]
+            # ---- gradient w.r.t. the layer input ----
+            if l > 0 or ctx.needs_input_grad[0]:
+                wihT = torch.zeros(Kl, ndir * K3, dtype=torch.bfloat16, device=dev)
+                wihT[:In_l] = torch.cat([wl[d * 4].detach() for d in range(ndir)], 0).t()
+                dY = gemm_bf16_tn(dgi, wihT)                              # [M][Kl] f32
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = dY.view(T, Bp, -1)[:, :B, :In].transpose(0, 1).contiguous()
+        ctx.saved = None
+        return (dx, None, None) + tuple(grads)
+
+
+def gru_stack(x, rnn):
+    """Run the sm_100a GRU stack with the parameters of an nn.GRU module (batch_first, h0 = 0)."""
+    ndir = 2 if rnn.bidirectional else 1
+    weights = []
+    for l in range(rnn.num_layers):
+        for d in range(ndir):
+            sfx = "_l%d%s" % (l, "_reverse" if d == 1 else "")
+            if not rnn.bias:
+                raise _lib.SpeechB200Error("GRU without bias is not supported")
+            weights += [getattr(rnn, "weight_ih" + sfx), getattr(rnn, "weight_hh" + sfx),
+                        getattr(rnn, "bias_ih" + sfx), getattr(rnn, "bias_hh" + sfx)]
+    return GRUStackFunction.apply(x, ndir, rnn.hidden_size, *weights)

@@ -1,0 +1,60 @@
+"""GPU parity: persistent GRU kernels (through the C ABI) vs torch.nn.GRU in fp32/fp64 on CPU.
+
+The kernels use bf16 tensor-core operands with fp32 accumulation and fp32 gate math, so the
+tolerance is the bf16 operand rounding (2^-9 relative per product), not fp32 epsilon:
+outputs within 2e-2 absolute of the fp64 reference (|h| <= 1), gradients within 3% of the
+largest reference gradient entry.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_and_ours(B, T, In, H, L, bidir, seed):
+    from speech_b200.ops import gru_stack
+    torch.manual_seed(seed)
+    rnn = torch.nn.GRU(In, H, L, batch_first=True, bidirectional=bidir)
+    x = torch.randn(B, T, In)
+    # fp64 CPU reference
+    rnn64 = torch.nn.GRU(In, H, L, batch_first=True, bidirectional=bidir).double()
+    rnn64.load_state_dict({k: v.double() for k, v in rnn.state_dict().items()})
+    x64 = x.double().requires_grad_(True)
+    y64, _ = rnn64(x64)
+    w = torch.randn_like(y64)
+    (y64 * w).sum().backward()
+    # ours
+    rnn_c = rnn.cuda()
+    xc = x.cuda().requires_grad_(True)
+    yc = gru_stack(xc, rnn_c)
+    (yc * w.float().cuda()).sum().backward()
+    torch.cuda.synchronize()
+    return rnn64, x64, y64, rnn_c, xc, yc
+
+
+@pytest.mark.parametrize("B,T,In,H,L,bidir", [
+    (4, 12, 160, 16, 1, False),    # tests/shared.py tiny config (uni, dim 16)
+    (3, 9, 40, 32, 2, True),       # ragged batch (padded to 8), 2 layers bi
+    (8, 20, 64, 128, 2, True),     # several CTAs per direction
+    (16, 31, 480, 256, 3, True),   # shipped-config width
+])
+def test_gru_stack_forward_backward(cuda_lib, B, T, In, H, L, bidir):
+    rnn64, x64, y64, rnn_c, xc, yc = _ref_and_ours(B, T, In, H, L, bidir, seed=B + T + H)
+    err = (yc.double().cpu() - y64).abs().max().item()
+    assert err < 2e-2, err
+    gx = xc.grad.double().cpu()
+    assert (gx - x64.grad).abs().max().item() < 3e-2 * x64.grad.abs().max().item() + 1e-4
+    for (n, p64), (_, pc) in zip(rnn64.named_parameters(), rnn_c.named_parameters()):
+        g = pc.grad.double().cpu()
+        ref = p64.grad
+        tol = 3e-2 * ref.abs().max().item() + 1e-4
+        assert (g - ref).abs().max().item() < tol, n
+
+
+def test_gru_north_star_width_short(cuda_lib):
+    """H=1024 (64 CTAs per direction, both directions resident), B=64, short T."""
+    rnn64, x64, y64, rnn_c, xc, yc = _ref_and_ours(64, 6, 480, 1024, 1, True, seed=5)
+    assert (yc.double().cpu() - y64).abs().max().item() < 2e-2
+    for (n, p64), (_, pc) in zip(rnn64.named_parameters(), rnn_c.named_parameters()):
+        ref = p64.grad
+        assert (pc.grad.double().cpu() - ref).abs().max().item() < 3e-2 * ref.abs().max().item() + 1e-4, n
