@@ -102,6 +102,24 @@ int sb_gru_bwd(const float* dy, const float* y, const float* gates, const void* 
                void* workspace, size_t workspace_bytes, unsigned int* barrier, int T, int Bp, int H,
                int ndir, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * CTC prefix beam search, one CTA per utterance.
+ * Replaces: speech.models.ctc_decoder.decode(probs, beam_size, blank)
+ *           (speech/models/ctc_decoder.py:38-113; called per utterance by CTC.infer,
+ *            speech/models/ctc_model.py:55-60).
+ *   logp        (B, T, S) float32 LOG-probabilities (the reference takes np.log of its input
+ *               first, ctc_decoder.py:52)
+ *   lens        (B) int32 frames to decode per utterance (<= T)
+ *   out_labels  (B, T) int32, out_lens (B) int32: best prefix of each utterance
+ *   out_scores  (B) float64: negative log-likelihood of that prefix (ctc_decoder.py:112-113)
+ * beam_size <= 32.  Lattice arithmetic is float64, ties are broken like the reference's
+ * stable sort over dict insertion order.
+ * ------------------------------------------------------------------------------------- */
+int sb_ctc_prefix_beam_workspace_size(int B, int T, int beam_size, size_t* bytes);
+int sb_ctc_prefix_beam(const float* logp, const int* lens, int B, int T, int S, int beam_size,
+                       int blank, int* out_labels, int* out_lens, double* out_scores,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

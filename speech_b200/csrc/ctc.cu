@@ -16,9 +16,10 @@
 //   The (T x V) log-softmax of the utterance is staged ONCE in shared memory with coalesced
 //   reads of the logits (116 KB at T=1000, V=29); lattice rows ping-pong in shared memory.
 //
-// Precision: lattice rows are renormalised every 32 steps (the row maximum is subtracted and
-// accumulated into a per-side scalar kept in double), so fp32 log-space values stay O(10) even for
-// T in the thousands and the 1e-4 parity bar holds for long utterances.
+// Precision: every row is stored relative to the maximum of the previous row (per-warp maxima are
+// published before the step barrier, so this costs no extra synchronisation); the subtracted
+// amounts accumulate in a per-side double.  fp32 log-space values therefore stay O(1) for any T
+// and the 1e-4 parity bar holds for long utterances.
 //
 // Roofline: nominally HBM (read logits + write grads = 2*B*T*V*4 bytes), in practice bound by
 // the T-step serial chain.
@@ -82,9 +83,9 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
   float* row_buf = smem;                        // [2 sides][2][SP]
   float* occ = row_buf + 4 * SP;                // [2 sides][2][V]
   float* red = occ + 4 * V;                     // [48] reduction scratch
-  float* nred = red + 32;                       // [2 sides][8] renormalisation maxima
-  float* lse_t = red + 48;                      // [T] (only !STAGED)
-  float* lp = STAGED ? (red + 48) : nullptr;    // [T*V] (only STAGED)
+  float* nred = red + 32;                       // [2 sides][2][8] per-warp row maxima
+  float* lse_t = red + 64;                      // [T] (only !STAGED)
+  float* lp = STAGED ? (red + 64) : nullptr;    // [T*V] (only STAGED)
 
   for (int k = tid; k < 4 * SP; k += 2 * CTC_SIDE) row_buf[k] = CTC_NEG_INF;
   for (int k = tid; k < 4 * V; k += 2 * CTC_SIDE) occ[k] = 0.f;
@@ -153,30 +154,49 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
 
   float* my_rows = row_buf + side * 2 * SP + 2;  // +2: leading pad so [s-2] is addressable
   float* my_occ = occ + side * 2 * V;
-  float* my_nred = nred + side * 8;
+  float* my_nred = nred + side * 16;             // [2][8] warp maxima of the last two rows
   const int Th = T / 2;
   const int swarp = i >> 5;  // warp index inside the side
-  double C = 0.0;            // offset of this side's smem rows: true value = stored + C
+  double C = 0.0;            // offset of the newest row of this side: true value = stored + C
 
-  // Subtract the row maximum from the row just written (values in vals[]) and fold it into C.
-  // Two side barriers; executed every 32 steps by all 256 threads of the side.
-  auto renormalise = [&](float* cur, float (&vals)[NS]) {
-    float m = CTC_NEG_INF;
+  // Row n of this side (time t) from row n-1 (smem ping-pong slot n&1).  The maximum of row n-1
+  // (gathered from per-warp maxima published before the previous barrier) is subtracted, so
+  // stored values stay O(1); the subtracted amounts accumulate in C (double).  One barrier per
+  // row, issued by the caller.
+  auto step_row = [&](int n, int t, float (&vals)[NS]) {
+    float* cur = my_rows + (n & 1) * SP;
+    const float* prev = my_rows + ((n & 1) ^ 1) * SP;
+    float m_prev = 0.f;
+    if (n > 0) {
+      const float* w = my_nred + ((n - 1) & 1) * 8;
+      m_prev = w[0];
 #pragma unroll
-    for (int q = 0; q < NS; ++q) m = fmaxf(m, vals[q]);
-    m = warp_max(m);
-    if (lane == 0) my_nred[swarp] = m;
-    side_barrier(side);
-    m = my_nred[0];
-#pragma unroll
-    for (int w = 1; w < CTC_SIDE / 32; ++w) m = fmaxf(m, my_nred[w]);
-    if (m != CTC_NEG_INF) {
-#pragma unroll
-      for (int q = 0; q < NS; ++q)
-        if (valid[q]) cur[i + CTC_SIDE * q] = vals[q] - m;
-      C += (double)m;
+      for (int k = 1; k < CTC_SIDE / 32; ++k) m_prev = fmaxf(m_prev, w[k]);
+      if (m_prev == CTC_NEG_INF) m_prev = 0.f;
     }
-    side_barrier(side);
+    C += (double)m_prev;
+    float wm = CTC_NEG_INF;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const int s = i + CTC_SIDE * q;
+      float v = CTC_NEG_INF;
+      if (valid[q]) {
+        if (n == 0) {
+          if (side == 0) { if (s <= 1) v = 0.f; }
+          else { if (s >= S - 2) v = 0.f; }
+        } else if (side == 0) {
+          v = lse3(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : CTC_NEG_INF) - m_prev;
+        } else {
+          v = lse3(prev[s], prev[s + 1], skip[q] ? prev[s + 2] : CTC_NEG_INF) - m_prev;
+        }
+        v += emit(t, cls[q]);
+        cur[s] = v;
+        wm = fmaxf(wm, v);
+      }
+      vals[q] = v;
+    }
+    wm = warp_max(wm);
+    if (lane == 0) my_nred[(n & 1) * 8 + swarp] = wm;
   };
 
   // ------------------------------------------------------------------------------------------
@@ -184,33 +204,15 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
   // ------------------------------------------------------------------------------------------
   {
     const int nsteps = side == 0 ? Th : (T - Th);
-    for (int it = 0; it < nsteps; ++it) {
-      const int t = side == 0 ? it : (T - 1 - it);
-      float* cur = my_rows + (it & 1) * SP;
-      const float* prev = my_rows + ((it & 1) ^ 1) * SP;
+    for (int n = 0; n < nsteps; ++n) {
+      const int t = side == 0 ? n : (T - 1 - n);
       float vals[NS];
+      step_row(n, t, vals);
 #pragma unroll
-      for (int q = 0; q < NS; ++q) {
-        const int s = i + CTC_SIDE * q;
-        float v = CTC_NEG_INF;
-        if (valid[q]) {
-          if (it == 0) {
-            if (side == 0) { if (s <= 1) v = 0.f; }
-            else { if (s >= S - 2) v = 0.f; }
-          } else if (side == 0) {
-            v = lse3(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : CTC_NEG_INF);
-          } else {
-            v = lse3(prev[s], prev[s + 1], skip[q] ? prev[s + 2] : CTC_NEG_INF);
-          }
-          v += emit(t, cls[q]);
-          cur[s] = v;
-          ws[(size_t)t * p.S_stride + s] = v;
-        }
-        vals[q] = v;
-      }
+      for (int q = 0; q < NS; ++q)
+        if (valid[q]) ws[(size_t)t * p.S_stride + i + CTC_SIDE * q] = vals[q];
       if (i == 0) offs[t] = C;
       side_barrier(side);
-      if ((it & 31) == 31) renormalise(cur, vals);
     }
   }
   __syncthreads();
@@ -218,28 +220,19 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
   // ------------------------------------------------------------------------------------------
   // meet in the middle: alpha_Th (side 0) x beta_Th (spilled by side 1) -> log p(y|x)
   // ------------------------------------------------------------------------------------------
-  const int beta_last_slot = ((T - Th) - 1) & 1;           // smem slot holding beta_Th
   float a_reg[NS];
   if (side == 0) {
-    float* cur = my_rows + (Th & 1) * SP;
-    const float* prev = my_rows + ((Th & 1) ^ 1) * SP;
+    step_row(Th, Th, a_reg);
     float local_max = CTC_NEG_INF;
     float contrib[NS];
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
       const int s = i + CTC_SIDE * q;
-      float v = CTC_NEG_INF;
       contrib[q] = CTC_NEG_INF;
       if (valid[q]) {
-        const float e = emit(Th, cls[q]);
-        if (Th == 0) { if (s <= 1) v = 0.f; }
-        else v = lse3(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : CTC_NEG_INF);
-        v += e;
-        cur[s] = v;
-        contrib[q] = v + ld_cg_f(ws + (size_t)Th * p.S_stride + s) - e;
+        contrib[q] = a_reg[q] + ld_cg_f(ws + (size_t)Th * p.S_stride + s) - emit(Th, cls[q]);
         local_max = fmaxf(local_max, contrib[q]);
       }
-      a_reg[q] = v;
     }
     // block logsumexp over the 256 alpha-side threads
     float m = warp_max(local_max);
@@ -280,8 +273,7 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
   // ------------------------------------------------------------------------------------------
   {
     const int nsteps = side == 0 ? (T - Th) : Th;
-    // beta side restarts its ping-pong so that "prev" of its first step is beta_Th
-    const int base = side == 0 ? Th : (beta_last_slot + 1);
+    const int n0 = side == 0 ? Th : (T - Th);   // row index of this side at it == 0
     float other[NS];  // spilled row of the other lattice, prefetched one step ahead
     double other_off = 0.0;
     if (nsteps > 0) {
@@ -295,9 +287,6 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
     }
     for (int it = 0; it < nsteps; ++it) {
       const int t = side == 0 ? (Th + it) : (Th - 1 - it);
-      const int slot = (base + it) & 1;
-      float* cur = my_rows + slot * SP;
-      const float* prev = my_rows + (slot ^ 1) * SP;
       float* occ_t = my_occ + (it & 1) * V;
       float other_next[NS];
       double other_off_next = 0.0;
@@ -310,29 +299,24 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
                                            : CTC_NEG_INF;
       }
       if (more) other_off_next = offs[tn];
+      float vals[NS];
+      if (side == 0 && it == 0) {
+#pragma unroll
+        for (int q = 0; q < NS; ++q) vals[q] = a_reg[q];   // row Th was formed at the meeting point
+      } else {
+        step_row(n0 + it, t, vals);
+      }
       // scalar part of the exponent, formed in double: C_own + C_other(t) - log p
       const float delta = (float)(C + other_off - logp);
       float blank_sum = 0.f;
-      float vals[NS];
 #pragma unroll
       for (int q = 0; q < NS; ++q) {
         const int s = i + CTC_SIDE * q;
-        float v = CTC_NEG_INF;
         if (valid[q]) {
-          const float e = emit(t, cls[q]);
-          if (side == 0 && it == 0) {
-            v = a_reg[q];
-          } else {
-            if (side == 0) v = lse3(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : CTC_NEG_INF);
-            else v = lse3(prev[s], prev[s + 1], skip[q] ? prev[s + 2] : CTC_NEG_INF);
-            v += e;
-            cur[s] = v;
-          }
-          const float g = __expf((v + other[q] - e) + delta);
+          const float g = __expf((vals[q] + other[q] - emit(t, cls[q])) + delta);
           if (s & 1) atomicAdd(occ_t + cls[q], g);
           else blank_sum += g;
         }
-        vals[q] = v;
       }
       // even threads own the blank states: one shared atomic per warp
       blank_sum = warp_sum(blank_sum);
@@ -342,7 +326,6 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
         grads[t * V + k] = __expf(emit(t, k)) - occ_t[k];
         occ_t[k] = 0.f;
       }
-      if ((it & 31) == 31) renormalise(cur, vals);
 #pragma unroll
       for (int q = 0; q < NS; ++q) other[q] = other_next[q];
       other_off = other_off_next;
@@ -410,7 +393,7 @@ extern "C" int sb_ctc_fwd_bwd(const float* acts, float* grads, const int* labels
   p.ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.offs + (size_t)B * T) + 255) & ~(uintptr_t)255);
   p.B = B; p.T = T; p.V = V; p.blank = blank; p.S_stride = ns * CTC_SIDE;
 
-  const size_t fixed = (size_t)(4 * (ns * CTC_SIDE + 4) + 4 * V + 48) * sizeof(float) + 8;
+  const size_t fixed = (size_t)(4 * (ns * CTC_SIDE + 4) + 4 * V + 64) * sizeof(float) + 8;
   const size_t staged_bytes = fixed + (size_t)T * V * sizeof(float);
   const size_t unstaged_bytes = fixed + (size_t)T * sizeof(float);
   const size_t limit = 220 * 1024;

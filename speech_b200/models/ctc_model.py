@@ -1,0 +1,61 @@
+"""CTC model - host-side mirror of speech/models/ctc_model.py:13-70 (reference)."""
+import numpy as np
+import torch
+
+from . import model
+from .ctc_decoder import decode, decode_batch
+from ..functions import ctc
+
+
+class CTC(model.Model):
+
+    def __init__(self, freq_dim, output_dim, config):
+        super().__init__(freq_dim, config)
+        self.blank = output_dim                      # blank is the LAST class (ctc_model.py:18)
+        self.fc = model.LinearND(self.encoder_dim, output_dim + 1)
+
+    def forward(self, batch):
+        x, y, x_lens, y_lens = self.collate(*batch)
+        with self._grad_ctx():
+            return self.forward_impl(x)
+
+    def forward_impl(self, x, softmax=False):
+        if self.is_cuda:
+            x = x.cuda(non_blocking=True)
+        x = self.encode(x)
+        x = self.fc(x)
+        if softmax:
+            return torch.nn.functional.softmax(x, dim=2)
+        return x
+
+    def loss(self, batch):
+        x, y, x_lens, y_lens = self.collate(*batch)
+        with self._grad_ctx():
+            out = self.forward_impl(x)
+            return ctc.CTCLoss()(out, y, x_lens, y_lens)
+
+    def collate(self, inputs, labels):
+        # every utterance is scored over the full padded T' (reference ctc_model.py:43-45)
+        max_t = self.conv_out_size(max(i.shape[0] for i in inputs), 0)
+        x_lens = torch.IntTensor([max_t] * len(inputs))
+        x = torch.from_numpy(model.zero_pad_concat(inputs))
+        y_lens = torch.IntTensor([len(l) for l in labels])
+        y = torch.IntTensor([int(t) for label in labels for t in label])
+        return [x, y, x_lens, y_lens]
+
+    def infer(self, batch, beam_size=1):
+        x, y, x_lens, y_lens = self.collate(*batch)
+        with torch.no_grad():
+            probs = self.forward_impl(x, softmax=True)
+        return decode_batch(probs, beam_size=beam_size, blank=self.blank)
+
+    @staticmethod
+    def max_decode(pred, blank):
+        """Greedy collapse: merge repeats, then drop blanks (reference ctc_model.py:62-70)."""
+        seq = []
+        prev = None
+        for p in pred:
+            if p != blank and p != prev:
+                seq.append(p)
+            prev = p
+        return seq

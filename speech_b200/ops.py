@@ -65,7 +65,7 @@ class GRUStackFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, ndir, H, *weights):
+    def forward(ctx, x, ndir, H, dropout, *weights):
         _lib.require_cuda(x, "x")
         lib = _lib.load()
         B, T, In = x.shape
@@ -109,8 +109,13 @@ class GRUStackFunction(torch.autograd.Function):
                                       xn.data_ptr(), _lib.ptr(xnT), _lib.ptr(gates),
                                       barrier.data_ptr(), T, Bp, H, ndir, _lib.stream_ptr()),
                        "sb_gru_fwd")
+            mask = None
+            if dropout > 0.0 and l + 1 < L:
+                # inter-layer dropout of nn.GRU(dropout=p): applied to every layer output but the last
+                mask = (torch.rand(M, D, device=dev) >= dropout).to(torch.bfloat16) / (1.0 - dropout)
+                xn = xn * mask
             if need_grad:
-                saved.append((X, y, gates, xnT))
+                saved.append((X, y, gates, xnT, mask))
             X = xn
         ctx.saved = saved
         ctx.weights = weights
@@ -137,7 +142,9 @@ class GRUStackFunction(torch.autograd.Function):
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
         grads = [None] * len(weights)
         for l in reversed(range(L)):
-            X, y, gates, xnT = ctx.saved[l]
+            X, y, gates, xnT, mask = ctx.saved[l]
+            if mask is not None:
+                dY = dY * mask
             wl = weights[l * 4 * ndir:(l + 1) * 4 * ndir]
             Kl = X.shape[1]
             In_l = wl[0].shape[1]
@@ -154,7 +161,7 @@ class GRUStackFunction(torch.autograd.Function):
                                       ws.data_ptr(), nbytes.value, barrier.data_ptr(), T, Bp, H,
                                       ndir, _lib.stream_ptr()), "sb_gru_bwd")
             # ---- weight gradients: K = T*Bp contractions on the transposed copies ----
-            if l > 0:
+            if l > 0 and ctx.saved[l - 1][4] is None:
                 XT = ctx.saved[l - 1][3][:, Bp:Bp + M]                   # [In_l][M] view
             else:
                 XT = X.t().contiguous()                                   # [Kl][M]
@@ -181,10 +188,10 @@ class GRUStackFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = dY.view(T, Bp, -1)[:, :B, :In].transpose(0, 1).contiguous()
         ctx.saved = None
-        return (dx, None, None) + tuple(grads)
+        return (dx, None, None, None) + tuple(grads)
 
 
-def gru_stack(x, rnn):
+def gru_stack(x, rnn, dropout=0.0):
     """Run the sm_100a GRU stack with the parameters of an nn.GRU module (batch_first, h0 = 0)."""
     ndir = 2 if rnn.bidirectional else 1
     weights = []
@@ -195,4 +202,17 @@ def gru_stack(x, rnn):
                 raise _lib.SpeechB200Error("GRU without bias is not supported")
             weights += [getattr(rnn, "weight_ih" + sfx), getattr(rnn, "weight_hh" + sfx),
                         getattr(rnn, "bias_ih" + sfx), getattr(rnn, "bias_hh" + sfx)]
-    return GRUStackFunction.apply(x, ndir, rnn.hidden_size, *weights)
+    return GRUStackFunction.apply(x, ndir, rnn.hidden_size, float(dropout), *weights)
+
+
+def conv_stack(x, conv, training):
+    """Conv2d+ReLU(+Dropout) front-end of the encoder (reference model.py:19-29,60-71).
+
+    x (B, T, F) -> (B, T', C*F') with the reference's channel-major feature flattening
+    (transpose(1,2) of (B,C,T',F') then view, model.py:66-71).
+    INTERIM (round 1): runs the nn.Conv2d modules through cuDNN; <1% of the step FLOPs.
+    The hand-written implicit-GEMM conv is listed as the next kernel in DESIGN.md.
+    """
+    y = conv(x.unsqueeze(1))
+    b, c, t, f = y.shape
+    return y.transpose(1, 2).reshape(b, t, c * f)

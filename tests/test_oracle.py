@@ -1,0 +1,109 @@
+"""CPU tests (-m "not gpu"): the oracle restatements against the reference's golden vectors and
+against independent implementations; host-side logic; the C-ABI library's exported symbols."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc_decoder_ref, ctc_ref
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_decoder_oracle_matches_reference_golden_vectors():
+    g = np.load(os.path.join(GOLD, "ctc_decode.npz"))
+    cases = [("demo", 0, (10, 8, 1)), ("f32", 11, (1, 4, 10)), ("peaky", 4, (1, 3, 8)),
+             ("tie", 0, (1, 3))]
+    for name, blank, beams in cases:
+        probs = g[name + "_probs"]
+        if name == "f32":
+            probs = probs.astype(np.float64)
+        for b in beams:
+            lab, sc = ctc_decoder_ref.prefix_beam_search(probs, beam_size=b, blank=blank)
+            assert list(lab) == list(g["%s_b%d_labels" % (name, b)]), (name, b)
+            assert abs(sc - float(g["%s_b%d_score" % (name, b)])) < 1e-9
+
+
+def test_decoder_demo_matches_survey_captured_values():
+    # the reference file's own __main__ demo, captured during the survey
+    g = np.load(os.path.join(GOLD, "ctc_decode.npz"))
+    assert list(g["demo_b10_labels"]) == [5, 12, 8, 2, 16, 13, 3, 7, 8, 3, 10, 4, 11, 19, 10, 14, 9,
+                                          8, 6, 5, 19, 4, 5, 4, 6]
+    assert abs(float(g["demo_b10_score"]) - 100.601941) < 1e-5
+    assert abs(float(g["demo_b8_score"]) - 102.401333) < 1e-5
+    assert abs(float(g["demo_b1_score"]) - 112.415479) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,V,seed", [(3, 20, 7, 0), (4, 48, 11, 1), (2, 35, 29, 2)])
+def test_ctc_oracle_matches_torch_ctc_loss(B, T, V, seed):
+    rng = np.random.RandomState(seed)
+    acts = rng.randn(B, T, V).astype(np.float32)
+    llen = rng.randint(0, 9, size=B).astype(np.int32)
+    flat = np.concatenate([rng.randint(0, V - 1, size=L) for L in llen] + [np.zeros(0, int)]).astype(np.int32)
+    alen = rng.randint(T // 2 + 9, T + 1, size=B).astype(np.int32)
+    c, g = ctc_ref.ctc_loss_and_grad(acts, flat, alen, llen)
+    a = torch.from_numpy(acts).double().requires_grad_(True)
+    lp = torch.log_softmax(a, 2).transpose(0, 1)
+    loss = torch.nn.functional.ctc_loss(lp, torch.from_numpy(flat).long(), torch.from_numpy(alen).long(),
+                                        torch.from_numpy(llen).long(), blank=V - 1, reduction="none")
+    loss.sum().backward()
+    np.testing.assert_allclose(c, loss.detach().numpy(), rtol=1e-10)
+    assert np.abs(g - a.grad.numpy()).max() < 1e-10
+
+
+def test_max_decode_known_answers():
+    # reference tests/ctc_test.py:31-43
+    from speech_b200.models import CTC
+    assert CTC.max_decode([1, 2, 2, 0, 0, 0, 2, 1], 0) == [1, 2, 2, 1]
+    assert CTC.max_decode([2, 2, 2], 0) == [2]
+    assert CTC.max_decode([0, 0, 0], 0) == []
+
+
+def test_model_class_surface_and_state_dict_names():
+    from speech_b200.models import CTC, Model
+    cfg = {"dropout": 0.0, "encoder": {"conv": [[32, 5, 32, 2]],
+                                       "rnn": {"dim": 16, "bidirectional": False, "layers": 1}}}
+    m = Model(40, cfg)
+    assert m.conv_out_size(100, 0) == 48 and m.conv_out_size(40, 1) == 5
+    assert m.encoder_dim == 16 and not m.is_cuda
+    g = np.load(os.path.join(GOLD, "encoder_tiny.npz"))
+    ref_keys = {k[len("tiny__sd__"):].replace("__", ".") for k in g.files if k.startswith("tiny__sd__")}
+    assert set(m.state_dict().keys()) == ref_keys
+    c = CTC(40, 10, cfg)
+    assert c.blank == 10 and c.fc.fc.weight.shape == (11, 16)
+    x, y, xl, yl = c.collate([np.zeros((100, 40)), np.zeros((90, 40))], [[1, 2, 3], [4]])
+    assert x.shape == (2, 100, 40) and x.dtype == torch.float32
+    assert xl.tolist() == [48, 48] and yl.tolist() == [3, 1] and y.tolist() == [1, 2, 3, 4]
+    with pytest.raises(Exception):
+        c.loss(([np.zeros((100, 40))], [[1]]))     # CPU model: must fail loudly, no fallback
+
+
+def test_same_seed_same_init_as_reference():
+    """identical construction order => identical weights under the same torch seed."""
+    from speech_b200.models import Model
+    cfg = {"dropout": 0.0, "encoder": {"conv": [[32, 5, 32, 2]],
+                                       "rnn": {"dim": 16, "bidirectional": False, "layers": 1}}}
+    torch.manual_seed(0)
+    m = Model(40, cfg)
+    g = np.load(os.path.join(GOLD, "encoder_tiny.npz"))
+    for k, v in m.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), g["tiny__sd__" + k.replace(".", "__")])
+
+
+def test_library_exports_every_declared_symbol():
+    from speech_b200.csrc import build
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    hdr = open(os.path.join(ROOT, "include", "speech_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), n
+    from speech_b200 import _lib
+    assert set(_lib.SIGNATURES) == names
+    assert lib.sb_version() >= 100
