@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU arm
+
+metric   utterances/sec of a full training step (train.py:28-35 of the reference:
+         zero_grad -> model.loss(batch) -> backward -> [all-reduce] -> clip(200) -> SGD step)
+workload SURVEY.md §8d north-star config: global batch B=64, T=1000 frames, F=80 features,
+         28 symbols + blank, conv [[32,5,8,2],[32,5,8,2]], 5-layer biGRU-1024 (84.9 M parameters),
+         synthetic data, random-init weights, dropout 0.
+value    device-timed (CUDA events) with the input batch already resident in HBM.
+e2e      the same step through the public API `model.loss(batch)` with HOST numpy inputs
+         (pinned staging + H2D copy and the D2H read of the loss inside the timed region).
+Under torchrun (N>1) the global batch is sharded B/N per rank (strong scaling), gradients are
+summed with one NCCL all-reduce per step; time is the max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL_CFG = {"dropout": 0.0,
+             "encoder": {"conv": [[32, 5, 8, 2], [32, 5, 8, 2]],
+                         "rnn": {"dim": 1024, "bidirectional": True, "layers": 5}}}
+GLOBAL_B, T_IN, F_IN, VOCAB = 64, 1000, 80, 28
+WORKLOAD = "LibriSpeech-clean-100 CTC: 5-layer biGRU-1024, |V|=29, B=64, T=1000, 80 feat (synthetic)"
+
+
+def synth_batch(nutt, seed=0):
+    rng = np.random.RandomState(seed)
+    inputs = [rng.randn(T_IN, F_IN).astype(np.float32) for _ in range(GLOBAL_B)]
+    labels = [rng.randint(0, VOCAB, size=rng.randint(40, 121)).tolist() for _ in range(GLOBAL_B)]
+    return inputs[:nutt], labels[:nutt]
+
+
+def flops_per_step(nutt):
+    """Algorithmic FLOPs of one training step for `nutt` utterances (126.7 GF/utt)."""
+    return 126.7e9 * nutt
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (recipe: /opt/skills/guides/B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx = [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm restated over torch CPU ops (oracle/model_ref.py)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_time(nutt, iters, warm, threads):
+    from oracle.model_ref import RefCTC
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = RefCTC(F_IN, VOCAB, MODEL_CFG)
+    inputs, labels = synth_batch(nutt)
+    x = torch.from_numpy(np.stack(inputs))
+    flat = torch.tensor([t for l in labels for t in l], dtype=torch.int32)
+    llen = torch.tensor([len(l) for l in labels], dtype=torch.int32)
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.0)
+    times = []
+    for i in range(warm + iters):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = m.loss(x, flat, llen)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 200)
+        opt.step()
+        _ = loss.item()
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    nutt = 8
+    times = cpu_step_time(nutt, args.steps, args.warmup, threads)
+    total = sum(times)
+    val = nutt * len(times) / total
+    line = {
+        "impl": "reference", "metric": "utterances/sec (training step, B=64,T=1000,80-feat)",
+        "value": val, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "global_batch": GLOBAL_B,
+                                        "seq_len": T_IN, "parallelism": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "utt/s", "cores": threads, "kind": "port",
+                         "sample": "%d utterances of the B=64 batch per step (oracle/model_ref.py: "
+                                   "torch CPU conv+GRU+fc+ctc_loss fwd+bwd+SGD, as the reference "
+                                   "runs on the host)" % nutt},
+        "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from speech_b200 import _lib, ops
+    from speech_b200.models import CTC
+    from speech_b200.parallel import GradSync
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert GLOBAL_B % world == 0
+    nutt = GLOBAL_B // world
+
+    torch.manual_seed(0)
+    model = CTC(F_IN, VOCAB, MODEL_CFG).cuda()
+    model.set_train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.0)
+    sync = GradSync(model, world)
+    inputs, labels = synth_batch(GLOBAL_B)
+    inputs = inputs[rank * nutt:(rank + 1) * nutt]
+    labels = labels[rank * nutt:(rank + 1) * nutt]
+    batch = (tuple(inputs), tuple(labels))
+    x_host, y, x_lens, y_lens = model.collate(*batch)
+    x_dev = x_host.cuda()
+
+    def step_device():
+        opt.zero_grad(set_to_none=False)
+        out = model.forward_impl(x_dev)
+        loss = model.ctc_loss(out, y, x_lens, y_lens)
+        loss.backward()
+        sync.all_reduce()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 200)
+        opt.step()
+        return loss
+
+    def step_e2e():
+        opt.zero_grad(set_to_none=False)
+        loss = model.loss(batch)          # host numpy in: pinned staging + H2D inside
+        loss.backward()
+        sync.all_reduce()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 200)
+        opt.step()
+        return loss.item()                # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- device-resident value, with per-kernel CUDA events and clock sampling ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.profile_begin()
+    _lib.launch_count = 0
+    ms_dev = timed(step_device, args.steps, 0)
+    launches = _lib.launch_count
+    prof = ops.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(step_device().item())
+
+    # ---- end to end through the public API ----
+    ms_e2e = timed(step_e2e, args.steps, 2)
+
+    if rank == 0:
+        utt = GLOBAL_B * args.steps
+        value = utt / (ms_dev * 1e-3)
+        e2e = utt / (ms_e2e * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else \
+            "fallback (B200_PROFILING.md sustained)"
+        kernels = {}
+        for name, (n, ms, fl) in prof.items():
+            kernels[name] = {"launches_per_step": n / args.steps, "ms_per_step": ms / args.steps,
+                             "tflops": (fl / 1e12) / (ms * 1e-3) if ms > 0 else None,
+                             "frac_of_peak": ((fl / 1e12) / (ms * 1e-3)) / peak_tf if ms > 0 else None}
+        dom = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+        roof = None
+        if dom:
+            n, ms, fl = prof[dom]
+            ach = (fl / 1e12) / (ms * 1e-3)
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "peak_source": peak_src,
+                    "avg_launch_ms": ms / n if n else None}
+        line = {
+            "metric": "utterances/sec (training step, B=64,T=1000,80-feat)",
+            "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": GLOBAL_B, "seq_len": T_IN,
+                       "parallelism": "dp%d" % world,
+                       "precision": "bf16 tensor-core operands, fp32 accumulate/state/master weights",
+                       "l2": "inputs larger than L2: ~10 GB of activations touched per step"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "utt/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(x_host.numel() * 4 + y.numel() * 4 + 8 * nutt) * world,
+                    "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches,
+            "loss": loss_val,
+            "step_tflops": flops_per_step(GLOBAL_B) / 1e12 / (ms_dev / args.steps * 1e-3),
+            "roofline": roof,
+            "kernels": kernels,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            nb = 8
+            times = cpu_step_time(nb, 2, 1, threads)
+            line["cpu_baseline"] = {
+                "value": nb * len(times) / sum(times), "unit": "utt/s", "cores": threads,
+                "kind": "port",
+                "sample": "%d utterances of the B=64 batch, 1 warm-up + 2 timed steps "
+                          "(oracle/model_ref.py on the host cores)" % nb}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,7 @@ SIGNATURES = {
 }
 
 _lib = None
+launch_count = 0   # C-ABI kernel launches issued by this process (bench.py: gpu_launches)
 
 
 class SpeechB200Error(RuntimeError):

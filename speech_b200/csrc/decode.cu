@@ -28,6 +28,9 @@ struct DecParams {
   const float* logp;   // (B, T, S)
   const int* lens;     // (B) frames per utterance (<= T)
   int* nodes;          // (B, 2*(T*K+1)) trie arena: parent, symbol
+  unsigned long long* hkeys;  // (B, hcap) (parent, symbol) -> node id map: keys (0 = empty)
+  int* hvals;                 // (B, hcap)
+  int hcap;                   // power of two >= 2*(T*K+1)
   int* out_labels;     // (B, T)
   int* out_lens;       // (B)
   double* out_scores;  // (B)  negative log-likelihood of the best prefix
@@ -119,7 +122,12 @@ __global__ void __launch_bounds__(DEC_THREADS) ctc_prefix_beam_kernel(const DecP
   __shared__ int nsel;
 
   int* nodes = p.nodes + (size_t)b * 2 * ((size_t)p.T * K + 1);
+  unsigned long long* hkeys = p.hkeys + (size_t)b * p.hcap;
+  int* hvals = p.hvals + (size_t)b * p.hcap;
   const float* logp = p.logp + (size_t)b * p.T * S;
+  // Node ids must be CANONICAL over the whole utterance: a prefix that is pruned and later
+  // re-created has to get its old id back, because surviving descendants still name it as parent.
+  for (int k = tid; k < p.hcap; k += DEC_THREADS) hkeys[k] = 0ull;
 
   if (tid == 0) {
     beams[0].size = 1;
@@ -202,9 +210,27 @@ __global__ void __launch_bounds__(DEC_THREADS) ctc_prefix_beam_kernel(const DecP
         const int i = c / S, s = c - i * S;
         double x; int rk;
         ext_value(cur, i, s, lp, K, x, rk);
-        const int id = 1 + t * K + tid;
-        nodes[2 * id] = cur.node[i];
-        nodes[2 * id + 1] = s;
+        // find-or-insert (parent node, symbol) in the utterance's hash map
+        const unsigned long long key =
+            ((unsigned long long)(unsigned int)cur.node[i] << 32) | (unsigned int)(s + 1);
+        unsigned int h = (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> 32) & (p.hcap - 1);
+        int id = -1;
+        for (int probe = 0; probe < p.hcap; ++probe) {
+          const unsigned long long k = hkeys[h];
+          if (k == key) { id = hvals[h]; break; }
+          if (k == 0ull) {
+            const unsigned long long old = atomicCAS(&hkeys[h], 0ull, key);
+            if (old == 0ull) {
+              id = 1 + t * K + tid;
+              hvals[h] = id;
+              nodes[2 * id] = cur.node[i];
+              nodes[2 * id + 1] = s;
+              break;
+            }
+            if (old == key) { id = hvals[h]; break; }
+          }
+          h = (h + 1) & (p.hcap - 1);
+        }
         nxt.pb[tid] = d_neg_inf();
         nxt.pnb[tid] = x;
         nxt.node[tid] = id;
@@ -243,9 +269,18 @@ __global__ void __launch_bounds__(DEC_THREADS) ctc_prefix_beam_kernel(const DecP
 
 using namespace sb;
 
+static int dec_hash_cap(int T, int K) {
+  size_t need = 2 * ((size_t)T * K + 1);
+  size_t cap = 64;
+  while (cap < need) cap <<= 1;
+  return (int)cap;
+}
+
 extern "C" int sb_ctc_prefix_beam_workspace_size(int B, int T, int K, size_t* bytes) {
   if (!bytes || B <= 0 || T < 0 || K <= 0) return SB_ERR_INVALID;
-  *bytes = (size_t)B * 2 * ((size_t)T * K + 1) * sizeof(int) + 256;
+  const size_t cap = (size_t)dec_hash_cap(T, K);
+  *bytes = (size_t)B * 2 * ((size_t)T * K + 1) * sizeof(int) + 256 +
+           (size_t)B * cap * (sizeof(unsigned long long) + sizeof(int)) + 512;
   return SB_OK;
 }
 
@@ -271,6 +306,11 @@ extern "C" int sb_ctc_prefix_beam(const float* logp, const int* lens, int B, int
   DecParams p;
   p.logp = logp; p.lens = lens;
   p.nodes = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  p.hcap = dec_hash_cap(T, beam_size);
+  p.hkeys = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(p.nodes + (size_t)B * 2 * ((size_t)T * beam_size + 1)) + 255) &
+      ~(uintptr_t)255);
+  p.hvals = reinterpret_cast<int*>(p.hkeys + (size_t)B * p.hcap);
   p.out_labels = out_labels; p.out_lens = out_lens; p.out_scores = out_scores;
   p.B = B; p.T = T; p.S = S; p.K = beam_size; p.blank = blank;
   ctc_prefix_beam_kernel<<<B, DEC_THREADS, smem, stream>>>(p);

@@ -60,13 +60,14 @@ def ctc_costs_and_grads(acts, labels, act_lens, label_lens, blank=None, need_gra
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
     costs = torch.empty(B, dtype=torch.float32, device=dev)
     grads = torch.empty_like(acts) if need_grad else None
+    from .. import ops
     with torch.cuda.device(dev):
-        _lib.check(
-            lib.sb_ctc_fwd_bwd(acts.data_ptr(), _lib.ptr(grads), d_lab.data_ptr(),
-                               d_off.data_ptr(), d_llen.data_ptr(), d_alen.data_ptr(),
-                               B, T, V, int(blank), max_l, costs.data_ptr(), ws.data_ptr(),
-                               nbytes.value, _lib.stream_ptr()),
-            "sb_ctc_fwd_bwd")
+        sp = _lib.stream_ptr()
+        ops._launch("ctc_fwd_bwd", 0.0,
+                    lambda: lib.sb_ctc_fwd_bwd(acts.data_ptr(), _lib.ptr(grads), d_lab.data_ptr(),
+                                               d_off.data_ptr(), d_llen.data_ptr(),
+                                               d_alen.data_ptr(), B, T, V, int(blank), max_l,
+                                               costs.data_ptr(), ws.data_ptr(), nbytes.value, sp))
     return costs, grads
 
 

@@ -32,13 +32,18 @@ class CTC(model.Model):
         x, y, x_lens, y_lens = self.collate(*batch)
         with self._grad_ctx():
             out = self.forward_impl(x)
-            return ctc.CTCLoss()(out, y, x_lens, y_lens)
+            return self.ctc_loss(out, y, x_lens, y_lens)
+
+    def ctc_loss(self, out, y, x_lens, y_lens):
+        """warp-ctc call of the reference (ctc_model.py:38-39): raw logits, blank = last class."""
+        return ctc.CTCLoss()(out, y, x_lens, y_lens)
 
     def collate(self, inputs, labels):
         # every utterance is scored over the full padded T' (reference ctc_model.py:43-45)
         max_t = self.conv_out_size(max(i.shape[0] for i in inputs), 0)
         x_lens = torch.IntTensor([max_t] * len(inputs))
-        x = torch.from_numpy(model.zero_pad_concat(inputs))
+        x = model.zero_pad_concat_pinned(inputs) if self.is_cuda else \
+            torch.from_numpy(model.zero_pad_concat(inputs))
         y_lens = torch.IntTensor([len(l) for l in labels])
         y = torch.IntTensor([int(t) for label in labels for t in label])
         return [x, y, x_lens, y_lens]

@@ -111,3 +111,25 @@ def zero_pad_concat(inputs):
     for e, inp in enumerate(inputs):
         out[e, :inp.shape[0], :] = inp
     return out
+
+
+_pinned = {}
+
+
+def zero_pad_concat_pinned(inputs):
+    """zero_pad_concat into a reused PINNED staging tensor so the H2D copy can be asynchronous
+    (batch assembly becomes the critical path once the step is ms-scale)."""
+    max_t = max(inp.shape[0] for inp in inputs)
+    shape = (len(inputs), max_t, inputs[0].shape[1])
+    buf = _pinned.get(shape)
+    if buf is None:
+        buf = torch.zeros(shape, dtype=torch.float32).pin_memory()
+        _pinned.clear()
+        _pinned[shape] = buf
+    arr = buf.numpy()
+    for e, inp in enumerate(inputs):
+        n = inp.shape[0]
+        arr[e, :n, :] = inp
+        if n < max_t:
+            arr[e, n:, :] = 0.0
+    return buf

@@ -18,6 +18,41 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+# ---- optional per-kernel timing (CUDA events on the launching stream; used by bench.py) ----
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {kernel class: (launches, total ms, total algorithmic FLOPs)}"""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, flops, e0, e1 in rec or []:
+        n, ms, fl = out.get(name, (0, 0.0, 0.0))
+        out[name] = (n + 1, ms + e0.elapsed_time(e1), fl + flops)
+    return out
+
+
+def _launch(name, flops, fn):
+    """Run one C-ABI launch; counts it and, when profiling, brackets it with CUDA events."""
+    _lib.launch_count += 1
+    if _prof is None:
+        return _lib.check(fn(), name)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn()
+    e1.record()
+    _prof.append((name, flops, e0, e1))
+    return _lib.check(rc, name)
+
+
 def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=None):
     """out[M,N] (f32) (+)= A[M,K] (bf16) @ B[N,K]^T (bf16) (+ bias).  A/B may be row-strided views.
 
@@ -42,9 +77,11 @@ def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=N
     assert out.dtype == torch.float32 and out.stride(1) == 1 and out.shape[0] >= rows
     if accumulate:
         flags |= GEMM_ACCUMULATE
-    _lib.check(lib.sb_gemm_bf16_tn(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
-                                   out.data_ptr(), out.stride(0), _lib.ptr(bias), M, N, K, flags,
-                                   split_k, rB, rT, vB, _lib.stream_ptr()), "sb_gemm_bf16_tn")
+    sp = _lib.stream_ptr()
+    _launch("gemm_bf16_tn", 2.0 * M * N * K,
+            lambda: lib.sb_gemm_bf16_tn(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+                                        out.data_ptr(), out.stride(0), _lib.ptr(bias), M, N, K,
+                                        flags, split_k, rB, rT, vB, sp))
     return out
 
 
@@ -105,10 +142,11 @@ class GRUStackFunction(torch.autograd.Function):
             if need_grad:
                 xnT = torch.zeros(D, (T + 2) * Bp, dtype=torch.bfloat16, device=dev)
                 gates = torch.empty(M, ndir, 4, H, dtype=torch.float32, device=dev)
-            _lib.check(lib.sb_gru_fwd(gi.data_ptr(), whh.data_ptr(), bhh.data_ptr(), y.data_ptr(),
-                                      xn.data_ptr(), _lib.ptr(xnT), _lib.ptr(gates),
-                                      barrier.data_ptr(), T, Bp, H, ndir, _lib.stream_ptr()),
-                       "sb_gru_fwd")
+            sp = _lib.stream_ptr()
+            _launch("gru_fwd", 2.0 * M * 3 * H * H * ndir,
+                    lambda: lib.sb_gru_fwd(gi.data_ptr(), whh.data_ptr(), bhh.data_ptr(),
+                                           y.data_ptr(), xn.data_ptr(), _lib.ptr(xnT),
+                                           _lib.ptr(gates), barrier.data_ptr(), T, Bp, H, ndir, sp))
             mask = None
             if dropout > 0.0 and l + 1 < L:
                 # inter-layer dropout of nn.GRU(dropout=p): applied to every layer output but the last
@@ -155,11 +193,13 @@ class GRUStackFunction(torch.autograd.Function):
             dghnT = torch.empty(ndir, H, M, dtype=torch.bfloat16, device=dev)
             dbih = torch.zeros(ndir * K3, dtype=torch.float32, device=dev)
             dbhh = torch.zeros(ndir * K3, dtype=torch.float32, device=dev)
-            _lib.check(lib.sb_gru_bwd(dY.data_ptr(), y.data_ptr(), gates.data_ptr(),
-                                      whhT.data_ptr(), dgi.data_ptr(), dgiT.data_ptr(),
-                                      dghnT.data_ptr(), dbih.data_ptr(), dbhh.data_ptr(),
-                                      ws.data_ptr(), nbytes.value, barrier.data_ptr(), T, Bp, H,
-                                      ndir, _lib.stream_ptr()), "sb_gru_bwd")
+            sp = _lib.stream_ptr()
+            _launch("gru_bwd", 2.0 * M * 3 * H * H * ndir,
+                    lambda dY=dY: lib.sb_gru_bwd(dY.data_ptr(), y.data_ptr(), gates.data_ptr(),
+                                                 whhT.data_ptr(), dgi.data_ptr(), dgiT.data_ptr(),
+                                                 dghnT.data_ptr(), dbih.data_ptr(), dbhh.data_ptr(),
+                                                 ws.data_ptr(), nbytes.value, barrier.data_ptr(),
+                                                 T, Bp, H, ndir, sp))
             # ---- weight gradients: K = T*Bp contractions on the transposed copies ----
             if l > 0 and ctx.saved[l - 1][4] is None:
                 XT = ctx.saved[l - 1][3][:, Bp:Bp + M]                   # [In_l][M] view
