@@ -159,6 +159,15 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repo
 # ------------------------------------------------------------------------------------------------
+def _log(msg):
+    if os.environ.get("SB_BENCH_VERBOSE"):
+        sys.stderr.write("[bench %.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
 def run_ours(args):
     import torch.distributed as dist
     from speech_b200 import _lib, ops
@@ -230,8 +239,11 @@ def run_ours(args):
         return ms
 
     # ---- device-resident value, with per-kernel CUDA events and clock sampling ----
-    for _ in range(args.warmup):
+    _log("model built; warm-up")
+    for i in range(args.warmup):
         step_device()
+        torch.cuda.synchronize()
+        _log("warm-up step %d done" % i)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -243,9 +255,11 @@ def run_ours(args):
     prof = ops.profile_end()
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(step_device().item())
+    _log("device-timed region done: %.2f ms/step" % (ms_dev / args.steps))
 
     # ---- end to end through the public API ----
     ms_e2e = timed(step_e2e, args.steps, 2)
+    _log("e2e region done: %.2f ms/step" % (ms_e2e / args.steps))
 
     if rank == 0:
         utt = GLOBAL_B * args.steps

@@ -26,8 +26,8 @@ enum : int {
 // host helper (defined in gemm.cu): number of SMs of the current device
 int device_sm_count();
 
-// A spin-wait that can never hang the GPU box: after ~2^31 polls (seconds) the kernel traps.
-#define SB_SPIN_LIMIT (1u << 30)
+// A spin-wait that can never hang the GPU box: after 2^24 polls (a few seconds) the kernel traps.
+#define SB_SPIN_LIMIT (1u << 24)
 
 SB_DEVINL uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -107,3 +107,17 @@ def test_library_exports_every_declared_symbol():
     from speech_b200 import _lib
     assert set(_lib.SIGNATURES) == names
     assert lib.sb_version() >= 100
+
+
+def test_c_oracle_matches_numpy_oracle():
+    from oracle import build as ob
+    rng = np.random.RandomState(4)
+    B, T, V = 5, 40, 9
+    acts = rng.randn(B, T, V).astype(np.float32)
+    llen = np.array([0, 3, 7, 12, 19], np.int32)
+    flat = np.concatenate([rng.randint(0, 3, size=L) for L in llen]).astype(np.int32)
+    alen = np.array([40, 33, 40, 25, 38], np.int32)
+    c1, g1 = ctc_ref.ctc_loss_and_grad(acts, flat, alen, llen)
+    c2, g2 = ob.ctc(acts, flat, llen, alen, V - 1)
+    np.testing.assert_allclose(c2, c1, rtol=1e-12)
+    assert np.abs(g2 - g1).max() < 1e-6
