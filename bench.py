@@ -37,6 +37,15 @@ GLOBAL_B, T_IN, F_IN, VOCAB = 64, 1000, 80, 28
 WORKLOAD = "LibriSpeech-clean-100 CTC: 5-layer biGRU-1024, |V|=29, B=64, T=1000, 80 feat (synthetic)"
 
 
+_T0 = time.perf_counter()
+
+
+def _log(msg):
+    if os.environ.get("SB_BENCH_VERBOSE"):
+        sys.stderr.write("[bench %.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
+
 def synth_batch(nutt, seed=0):
     rng = np.random.RandomState(seed)
     inputs = [rng.randn(T_IN, F_IN).astype(np.float32) for _ in range(GLOBAL_B)]
@@ -107,11 +116,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm restated over torch CPU ops (oracle/model_ref.py)
 # ------------------------------------------------------------------------------------------------
-def cpu_step_time(nutt, iters, warm, threads):
+def cpu_step_time(nutt, iters, warm, threads, layers=None):
     from oracle.model_ref import RefCTC
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    m = RefCTC(F_IN, VOCAB, MODEL_CFG)
+    cfg = MODEL_CFG
+    if layers is not None:
+        cfg = json.loads(json.dumps(MODEL_CFG))
+        cfg["encoder"]["rnn"]["layers"] = layers
+    m = RefCTC(F_IN, VOCAB, cfg)
     inputs, labels = synth_batch(nutt)
     x = torch.from_numpy(np.stack(inputs))
     flat = torch.tensor([t for l in labels for t in l], dtype=torch.int32)
@@ -131,11 +144,30 @@ def cpu_step_time(nutt, iters, warm, threads):
     return times
 
 
+def pick_threads():
+    """Thread count for the CPU arm: the fastest of a few candidates on a short probe (4 utterances,
+    1 GRU layer).  All hardware threads is often NOT the fastest for the T'-serial GRU on a
+    many-core host, so the baseline gets the best setting rather than the largest."""
+    ncpu = os.cpu_count() or 1
+    try:
+        ncpu = min(ncpu, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = cands[0], None
+    for c in cands:
+        t = sum(cpu_step_time(4, 1, 1, c, layers=1))
+        _log("cpu probe: %d threads -> %.2f s" % (c, t))
+        if best_t is None or t < best_t:
+            best, best_t = c, t
+    return best
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = pick_threads()
     nutt = 8
     times = cpu_step_time(nutt, args.steps, args.warmup, threads)
     total = sum(times)
@@ -159,15 +191,6 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repo
 # ------------------------------------------------------------------------------------------------
-def _log(msg):
-    if os.environ.get("SB_BENCH_VERBOSE"):
-        sys.stderr.write("[bench %.1fs] %s\n" % (time.perf_counter() - _T0, msg))
-        sys.stderr.flush()
-
-
-_T0 = time.perf_counter()
-
-
 def run_ours(args):
     import torch.distributed as dist
     from speech_b200 import _lib, ops
@@ -308,7 +331,7 @@ def run_ours(args):
             "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = pick_threads()
             nb = 8
             times = cpu_step_time(nb, 2, 1, threads)
             line["cpu_baseline"] = {

@@ -24,17 +24,16 @@
 // Roofline: the MMAs are tensor work but each step is bound by the all-gather + barrier latency;
 // DESIGN.md reports us/step next to the tensor-pipe share.
 #include "common.cuh"
-#include <cooperative_groups.h>
+#include <cuda.h>
 
 #include "../../include/speech_b200.h"
 
 namespace sb {
 
 static constexpr int GRU_HC = 16;           // hidden units per CTA
-static constexpr int GRU_RING = 4;          // smem ring slots for the gathered operand
-static constexpr int GRU_SLOT_BYTES = 128 * 128;  // [128 rows x 64 bf16] SWIZZLE_128B tile
-static constexpr int GRU_LOADERS = 256;     // warps 0..7 gather; warps 0..3 also run the epilogue
-static constexpr int GRU_THREADS = GRU_LOADERS + 32;  // + warp 8: MMA issuer / TMEM owner
+static constexpr int GRU_MAX_RING = 16;     // smem ring slots for the gathered operand
+static constexpr int GRU_EPI = 128;         // warps 0..3: epilogue (thread = TMEM lane = batch row)
+static constexpr int GRU_THREADS = GRU_EPI + 64;  // + warp 4: MMA issuer/TMEM owner, warp 5: TMA
 
 typedef __nv_bfloat16 bf16;
 
@@ -47,7 +46,7 @@ struct GruFwdParams {
   bf16* xnT;           // [ndir*H][(T+2)*Bp] h_t bf16 transposed, column (t+1)*Bp+b ; may be null
   float* gates;        // [T*Bp][ndir][4][H] saved r,z,n,hn for backward ; may be null
   unsigned int* barrier;  // [ndir] zero-initialised counters
-  int T, Bp, H, ndir;
+  int T, Bp, H, ndir, ring;
 };
 
 struct GruBwdParams {
@@ -62,7 +61,7 @@ struct GruBwdParams {
   float* dbih;         // [ndir*3H] += sum_{t,b} dgi
   float* dbhh;         // [ndir*3H] += sum_{t,b} dgh
   unsigned int* barrier;  // [ndir]
-  int T, Bp, H, ndir;
+  int T, Bp, H, ndir, ring;
 };
 
 // ---- per-direction grid barrier ------------------------------------------------------------
@@ -73,92 +72,63 @@ SB_DEVINL void grid_wait(const unsigned int* ctr, unsigned int target) {
     if (++spins > SB_SPIN_LIMIT) __trap();
   }
 }
-SB_DEVINL void loaders_barrier() {
-  asm volatile("bar.sync 1, %0;" ::"n"(GRU_LOADERS) : "memory");
-}
+SB_DEVINL void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GRU_EPI) : "memory"); }
 
 struct GruSmem {
   uint8_t* wtile;   // resident weight chunks
-  uint8_t* ring;    // GRU_RING slots
-  uint64_t* full;   // [GRU_RING]
-  uint64_t* empty;  // [GRU_RING]
+  uint8_t* ring;    // ring slots, stride = Bp*128 bytes (+ slack so a 128-row read stays inside)
+  uint64_t* full;   // [GRU_MAX_RING]
+  uint64_t* empty;  // [GRU_MAX_RING]
   uint64_t* accfull;
   uint32_t* tmem_slot;
   float* scratch;   // [64]
 };
 
-SB_DEVINL GruSmem carve(uint8_t* raw, int wbytes) {
+SB_DEVINL GruSmem carve(uint8_t* raw, int wbytes, int ring_bytes) {
   GruSmem s;
   s.wtile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) &
                                        ~static_cast<uintptr_t>(1023));
   s.ring = s.wtile + wbytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s.ring + GRU_RING * GRU_SLOT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.ring + ring_bytes);
   s.full = bars;
-  s.empty = bars + GRU_RING;
-  s.accfull = bars + 2 * GRU_RING;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GRU_RING + 1);
-  s.scratch = reinterpret_cast<float*>(bars + 2 * GRU_RING + 2);
+  s.empty = bars + GRU_MAX_RING;
+  s.accfull = bars + 2 * GRU_MAX_RING;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GRU_MAX_RING + 1);
+  s.scratch = reinterpret_cast<float*>(bars + 2 * GRU_MAX_RING + 2);
   return s;
 }
 
-// Gather a [Bp x Kdim] bf16 row-major operand (row stride src_ld elements) from L2 into the smem
-// ring, chunk by chunk (64 columns each), for the MMA warp.  Executed by the 256 loader threads.
-// `fill` is the running chunk counter (ring position / phase) shared with the MMA warp.
-SB_DEVINL void gather_operand(const GruSmem& s, const bf16* src, long long src_ld, int Bp, int Kdim,
-                              int nchunks, unsigned int& fill) {
-  const int tid = threadIdx.x;
-  const int pieces = Bp * 8;  // 16-byte pieces per chunk
-  for (int c0 = 0; c0 < nchunks; c0 += 2) {
-    // issue all global loads of two chunks first (MLP), then commit them to shared memory
-    uint4 v[2][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = c0 + u;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int pc = tid + q * GRU_LOADERS;
-        v[u][q] = make_uint4(0, 0, 0, 0);
-        if (c < nchunks && pc < pieces) {
-          const int row = pc >> 3, c16 = pc & 7;
-          const int k = c * 64 + c16 * 8;
-          if (k < Kdim) v[u][q] = ld_cg_u4(src + (long long)row * src_ld + k);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = c0 + u;
-      if (c >= nchunks) break;
-      const unsigned int slot = fill % GRU_RING;
-      const unsigned int par = (fill / GRU_RING) & 1u;
-      mbar_wait(&s.empty[slot], par ^ 1u);
-      uint8_t* dst = s.ring + slot * GRU_SLOT_BYTES;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int pc = tid + q * GRU_LOADERS;
-        if (pc < pieces) {
-          const int row = pc >> 3, c16 = pc & 7;
-          *reinterpret_cast<uint4*>(dst + sw128_offset(row, c16)) = v[u][q];
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&s.full[slot]);
-      ++fill;
-    }
+// ring geometry shared by host and device
+SB_DEVINL int ring_stride(int Bp) { return Bp * 128; }
+
+// TMA producer (one thread): bring `nchunks` [Bp x 64] bf16 boxes of the operand whose rows start
+// at `row0` into the ring.  `fill` is the running chunk counter shared (by construction) with
+// the MMA thread.
+SB_DEVINL void tma_gather(const GruSmem& s, const CUtensorMap* tm, int row0, int Bp, int nchunks,
+                          int ring, unsigned int& fill) {
+  const int stride = ring_stride(Bp);
+  for (int c = 0; c < nchunks; ++c) {
+    const unsigned int slot = fill % ring;
+    const unsigned int par = (fill / ring) & 1u;
+    mbar_wait(&s.empty[slot], par ^ 1u);
+    mbar_expect_tx(&s.full[slot], (uint32_t)stride);
+    tma_load_2d(s.ring + slot * stride, tm, &s.full[slot], c * 64, row0);
+    ++fill;
   }
 }
 
-// MMA warp: consume `nchunks` ring slots against the resident weight chunks (rows_w rows each).
+// MMA thread: consume `nchunks` ring slots against the resident weight chunks.
 template <int N>
 SB_DEVINL void mma_consume(const GruSmem& s, uint32_t tmem_d, int nchunks, int wchunk_bytes,
-                           unsigned int& fill) {
+                           int Bp, int ring, unsigned int& fill) {
   constexpr uint32_t idesc = umma_idesc_bf16_f32(128, N);
+  const int stride = ring_stride(Bp);
   for (int c = 0; c < nchunks; ++c) {
-    const unsigned int slot = fill % GRU_RING;
-    const unsigned int par = (fill / GRU_RING) & 1u;
+    const unsigned int slot = fill % ring;
+    const unsigned int par = (fill / ring) & 1u;
     mbar_wait(&s.full[slot], par);
     tc_fence_after_sync();
-    const uint64_t da = umma_desc_sw128_kmajor(smem_u32(s.ring + slot * GRU_SLOT_BYTES));
+    const uint64_t da = umma_desc_sw128_kmajor(smem_u32(s.ring + slot * stride));
     const uint64_t db = umma_desc_sw128_kmajor(smem_u32(s.wtile + c * wchunk_bytes));
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -173,7 +143,9 @@ SB_DEVINL void mma_consume(const GruSmem& s, uint32_t tmem_d, int nchunks, int w
 // =============================================================================================
 // forward
 // =============================================================================================
-__global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdParams p) {
+__global__ void __launch_bounds__(GRU_THREADS, 1)
+gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant__ CUtensorMap tm_d1,
+               const GruFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int H = p.H, Bp = p.Bp, T = p.T;
   const int nC = H / GRU_HC;
@@ -181,13 +153,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdPar
   const int j0 = (blockIdx.x % nC) * GRU_HC;
   const int nchunks = (H + 63) / 64;
   constexpr int WCHUNK = 48 * 128;  // 48 rows x 64 bf16
-  const GruSmem s = carve(smem_raw, nchunks * WCHUNK);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int ring_bytes = p.ring * ring_stride(Bp) + (128 - Bp) * 128;
+  const GruSmem s = carve(smem_raw, nchunks * WCHUNK, ring_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = p.ndir * H;
   const long long ldT = (long long)(T + 2) * Bp;
+  const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
 
   // ---- one-time setup: zero the ring, stage this CTA's 48 weight rows, barriers, TMEM ----
-  for (int k = tid; k < GRU_RING * GRU_SLOT_BYTES / 16; k += GRU_THREADS)
+  for (int k = tid; k < ring_bytes / 16; k += GRU_THREADS)
     reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
   {
     const int pieces_per_row = nchunks * 8;
@@ -207,14 +181,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdPar
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < GRU_RING; ++i) {
-      mbar_init(&s.full[i], GRU_LOADERS);
+    for (int i = 0; i < GRU_MAX_RING; ++i) {
+      mbar_init(&s.full[i], 1);
       mbar_init(&s.empty[i], 1);
     }
     mbar_init(s.accfull, 1);
     mbar_fence_init();
+    tma_prefetch_desc(tm);
   }
-  if (warp == 8) tmem_alloc(s.tmem_slot, 64);
+  if (warp == 4) tmem_alloc(s.tmem_slot, 64);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -222,28 +197,38 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdPar
   const uint32_t tmem_base = *s.tmem_slot;
   unsigned int* ctr = p.barrier + dir;
 
-  if (warp == 8) {
-    // ===================== MMA issuer =====================
-    if ((tid & 31) == 0) {
+  if (warp == 5) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
       unsigned int fill = 0;
-      for (int step = 1; step < T; ++step) mma_consume<48>(s, tmem_base, nchunks, WCHUNK, fill);
+      for (int step = 1; step < T; ++step) {
+        const int t = dir == 0 ? step : (T - 1 - step);
+        const int tp = dir == 0 ? t - 1 : t + 1;
+        grid_wait(ctr, (unsigned int)nC * step);   // every CTA of this direction published h_{tp}
+        fence_proxy_async_all();                    // generic-proxy writes -> async-proxy (TMA) reads
+        tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, fill);
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      unsigned int fill = 0;
+      for (int step = 1; step < T; ++step)
+        mma_consume<48>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, fill);
     }
   } else {
-    // ===================== loaders (+ epilogue on warps 0..3) =====================
-    unsigned int fill = 0;
+    // ===================== epilogue: thread = batch row =====================
     float hprev[GRU_HC];
 #pragma unroll
     for (int jj = 0; jj < GRU_HC; ++jj) hprev[jj] = 0.f;
     float bias[48];
-    if (tid < 128) {
 #pragma unroll
-      for (int r = 0; r < 48; ++r) bias[r] = s.scratch[r];
-    }
+    for (int r = 0; r < 48; ++r) bias[r] = s.scratch[r];
+    const bool active = tid < Bp;
     for (int step = 0; step < T; ++step) {
       const int t = dir == 0 ? step : (T - 1 - step);
-      // prefetch this step's input projections (independent of the recurrence)
+      // this step's input projections do not depend on the recurrence: fetch them first
       float gi[48];
-      const bool active = tid < 128 && tid < Bp;
       if (active) {
         const float* g = p.gi + ((long long)t * Bp + tid) * (p.ndir * 3 * H) + dir * 3 * H + j0;
 #pragma unroll
@@ -255,83 +240,82 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdPar
             gi[gg * 16 + q * 4 + 2] = v.z; gi[gg * 16 + q * 4 + 3] = v.w;
           }
       }
+      float acc[48];
       if (step > 0) {
-        if (tid == 0) grid_wait(ctr, (unsigned int)nC * step);
-        loaders_barrier();
-        const int tp = dir == 0 ? t - 1 : t + 1;
-        gather_operand(s, p.xn + (long long)tp * Bp * D + dir * H, D, Bp, H, nchunks, fill);
-      }
-      if (tid < 128) {
-        float acc[48];
-        if (step > 0) {
-          mbar_wait(s.accfull, (step - 1) & 1);
-          tc_fence_after_sync();
-          uint32_t v[16];
+        mbar_wait(s.accfull, (step - 1) & 1);
+        tc_fence_after_sync();
+        uint32_t v[16];
 #pragma unroll
-          for (int gg = 0; gg < 3; ++gg) {
-            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + gg * 16, v);
-            tmem_ld_wait();
+        for (int gg = 0; gg < 3; ++gg) {
+          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + gg * 16, v);
+          tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) acc[gg * 16 + jj] = __uint_as_float(v[jj]);
-          }
-          tc_fence_before_sync();
-        } else {
-#pragma unroll
-          for (int r = 0; r < 48; ++r) acc[r] = 0.f;
+          for (int jj = 0; jj < 16; ++jj) acc[gg * 16 + jj] = __uint_as_float(v[jj]);
         }
-        if (active) {
-          const long long m = (long long)t * Bp + tid;
-          float hn[GRU_HC], rr[GRU_HC], zz[GRU_HC], nn[GRU_HC];
+        tc_fence_before_sync();
+      } else {
 #pragma unroll
-          for (int jj = 0; jj < GRU_HC; ++jj) {
-            rr[jj] = sigmoidf_fast(gi[jj] + acc[jj] + bias[jj]);
-            zz[jj] = sigmoidf_fast(gi[16 + jj] + acc[16 + jj] + bias[16 + jj]);
-            hn[jj] = acc[32 + jj] + bias[32 + jj];
-            nn[jj] = tanhf_fast(gi[32 + jj] + rr[jj] * hn[jj]);
-            hprev[jj] = (1.f - zz[jj]) * nn[jj] + zz[jj] * hprev[jj];
+        for (int r = 0; r < 48; ++r) acc[r] = 0.f;
+      }
+      const long long m = (long long)t * Bp + tid;
+      float hn[GRU_HC], rr[GRU_HC], zz[GRU_HC], nn[GRU_HC];
+      if (active) {
+#pragma unroll
+        for (int jj = 0; jj < GRU_HC; ++jj) {
+          rr[jj] = sigmoidf_fast(gi[jj] + acc[jj] + bias[jj]);
+          zz[jj] = sigmoidf_fast(gi[16 + jj] + acc[16 + jj] + bias[16 + jj]);
+          hn[jj] = acc[32 + jj] + bias[32 + jj];
+          nn[jj] = tanhf_fast(gi[32 + jj] + rr[jj] * hn[jj]);
+          hprev[jj] = (1.f - zz[jj]) * nn[jj] + zz[jj] * hprev[jj];
+        }
+        // critical path: only the bf16 h_t that the other CTAs gather next step
+        uint4 pk[2];
+        uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(hprev[2 * q], hprev[2 * q + 1]);
+        uint4* xo = reinterpret_cast<uint4*>(p.xn + m * D + dir * H + j0);
+        xo[0] = pk[0];
+        xo[1] = pk[1];
+        fence_proxy_async_all();   // these generic-proxy writes are read by other CTAs' TMA
+      }
+      epi_barrier();
+      if (tid == 0) {
+        __threadfence();
+        grid_arrive(ctr);
+      }
+      // off the critical path: fp32 state, transposed copy, saved gates
+      if (active) {
+        float* yo = p.y + m * D + dir * H + j0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(yo)[q] =
+              make_float4(hprev[q * 4], hprev[q * 4 + 1], hprev[q * 4 + 2], hprev[q * 4 + 3]);
+        if (p.xnT) {
+          bf16* xt = p.xnT + (long long)(dir * H + j0) * ldT + (long long)(t + 1) * Bp + tid;
+#pragma unroll
+          for (int jj = 0; jj < GRU_HC; ++jj) xt[jj * ldT] = __float2bfloat16_rn(hprev[jj]);
+        }
+        if (p.gates) {
+          float* go = p.gates + ((m * p.ndir + dir) * 4) * H + j0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            reinterpret_cast<float4*>(go)[q] =
+                make_float4(rr[q * 4], rr[q * 4 + 1], rr[q * 4 + 2], rr[q * 4 + 3]);
+            reinterpret_cast<float4*>(go + H)[q] =
+                make_float4(zz[q * 4], zz[q * 4 + 1], zz[q * 4 + 2], zz[q * 4 + 3]);
+            reinterpret_cast<float4*>(go + 2 * H)[q] =
+                make_float4(nn[q * 4], nn[q * 4 + 1], nn[q * 4 + 2], nn[q * 4 + 3]);
+            reinterpret_cast<float4*>(go + 3 * H)[q] =
+                make_float4(hn[q * 4], hn[q * 4 + 1], hn[q * 4 + 2], hn[q * 4 + 3]);
           }
-          float* yo = p.y + m * D + dir * H + j0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            reinterpret_cast<float4*>(yo)[q] =
-                make_float4(hprev[q * 4], hprev[q * 4 + 1], hprev[q * 4 + 2], hprev[q * 4 + 3]);
-          uint4 pk[2];
-          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(hprev[2 * q], hprev[2 * q + 1]);
-          uint4* xo = reinterpret_cast<uint4*>(p.xn + m * D + dir * H + j0);
-          xo[0] = pk[0];
-          xo[1] = pk[1];
-          if (p.xnT) {
-            bf16* xt = p.xnT + (long long)(dir * H + j0) * ldT + (long long)(t + 1) * Bp + tid;
-#pragma unroll
-            for (int jj = 0; jj < GRU_HC; ++jj) xt[jj * ldT] = __float2bfloat16_rn(hprev[jj]);
-          }
-          if (p.gates) {
-            float* go = p.gates + ((m * p.ndir + dir) * 4) * H + j0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              reinterpret_cast<float4*>(go)[q] =
-                  make_float4(rr[q * 4], rr[q * 4 + 1], rr[q * 4 + 2], rr[q * 4 + 3]);
-              reinterpret_cast<float4*>(go + H)[q] =
-                  make_float4(zz[q * 4], zz[q * 4 + 1], zz[q * 4 + 2], zz[q * 4 + 3]);
-              reinterpret_cast<float4*>(go + 2 * H)[q] =
-                  make_float4(nn[q * 4], nn[q * 4 + 1], nn[q * 4 + 2], nn[q * 4 + 3]);
-              reinterpret_cast<float4*>(go + 3 * H)[q] =
-                  make_float4(hn[q * 4], hn[q * 4 + 1], hn[q * 4 + 2], hn[q * 4 + 3]);
-            }
-          }
-          __threadfence();
         }
       }
-      loaders_barrier();
-      if (tid == 0) grid_arrive(ctr);
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 64);
   }
@@ -340,7 +324,9 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdPar
 // =============================================================================================
 // backward (reverse of the forward time order of each direction)
 // =============================================================================================
-__global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdParams p) {
+__global__ void __launch_bounds__(GRU_THREADS, 1)
+gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant__ CUtensorMap tm_d1,
+               const GruBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int H = p.H, Bp = p.Bp, T = p.T;
   const int nC = H / GRU_HC;
@@ -349,12 +335,14 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdPar
   const int K3 = 3 * H;
   const int nchunks = (K3 + 63) / 64;
   constexpr int WCHUNK = 16 * 128;  // 16 rows x 64 bf16
-  const GruSmem s = carve(smem_raw, nchunks * WCHUNK);
+  const int ring_bytes = p.ring * ring_stride(Bp) + (128 - Bp) * 128;
+  const GruSmem s = carve(smem_raw, nchunks * WCHUNK, ring_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = p.ndir * H;
   const long long M = (long long)T * Bp;
+  const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
 
-  for (int k = tid; k < GRU_RING * GRU_SLOT_BYTES / 16; k += GRU_THREADS)
+  for (int k = tid; k < ring_bytes / 16; k += GRU_THREADS)
     reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
   {
     // resident operand: rows = the 16 hidden units k0..k0+15 of W_hh^T, K = 3H
@@ -369,14 +357,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdPar
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < GRU_RING; ++i) {
-      mbar_init(&s.full[i], GRU_LOADERS);
+    for (int i = 0; i < GRU_MAX_RING; ++i) {
+      mbar_init(&s.full[i], 1);
       mbar_init(&s.empty[i], 1);
     }
     mbar_init(s.accfull, 1);
     mbar_fence_init();
+    tma_prefetch_desc(tm);
   }
-  if (warp == 8) tmem_alloc(s.tmem_slot, 32);
+  if (warp == 4) tmem_alloc(s.tmem_slot, 32);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -384,15 +373,24 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdPar
   const uint32_t tmem_base = *s.tmem_slot;
   unsigned int* ctr = p.barrier + dir;
 
-  if (warp == 8) {
+  if (warp == 5) {
     if (lane == 0) {
       unsigned int fill = 0;
       // the recurrent product is needed for every step except the last one processed
-      for (int step = 0; step + 1 < T; ++step) mma_consume<16>(s, tmem_base, nchunks, WCHUNK, fill);
+      for (int step = 0; step + 1 < T; ++step) {
+        grid_wait(ctr, (unsigned int)nC * (step + 1));   // dgh of this step is complete
+        fence_proxy_async_all();
+        tma_gather(s, tm, (step & 1) * Bp, Bp, nchunks, p.ring, fill);
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      unsigned int fill = 0;
+      for (int step = 0; step + 1 < T; ++step)
+        mma_consume<16>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, fill);
     }
   } else {
-    unsigned int fill = 0;
-    const bool active = tid < 128 && tid < Bp;
+    const bool active = tid < Bp;
     float dh_rec[GRU_HC];   // dL/dh_t arriving through the recurrence (own 16 units)
     float db_i[48], db_hn[GRU_HC];
 #pragma unroll
@@ -406,12 +404,12 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdPar
       const int tp = dir == 0 ? t - 1 : t + 1;       // time index of h_{prev} in forward order
       const bool has_prev = dir == 0 ? (t > 0) : (t < T - 1);
       bf16* xb = p.xchg + ((long long)(dir * 2 + (step & 1)) * Bp) * K3;
-      float dhz[GRU_HC];
+      const long long m = (long long)t * Bp + tid;
+      // ---- saved activations of this step: independent of the recurrence, fetched first ----
+      float rr[GRU_HC], zz[GRU_HC], nn[GRU_HC], hn[GRU_HC], dh[GRU_HC], hp[GRU_HC];
       if (active) {
-        const long long m = (long long)t * Bp + tid;
         const float* go = p.gates + ((m * p.ndir + dir) * 4) * H + j0;
         const float* dyo = p.dy + m * D + dir * H + j0;
-        float rr[GRU_HC], zz[GRU_HC], nn[GRU_HC], hn[GRU_HC], dh[GRU_HC], hp[GRU_HC];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 a = __ldg(reinterpret_cast<const float4*>(go) + q);
@@ -436,7 +434,20 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdPar
 #pragma unroll
           for (int jj = 0; jj < GRU_HC; ++jj) hp[jj] = 0.f;
         }
-        float dr[GRU_HC], dz[GRU_HC], dn[GRU_HC], dnr[GRU_HC];
+      }
+      // ---- recurrent part of dL/dh_t: product issued in the previous step ----
+      if (step > 0) {
+        mbar_wait(s.accfull, (step - 1) & 1);
+        tc_fence_after_sync();
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+#pragma unroll
+        for (int jj = 0; jj < GRU_HC; ++jj) dh_rec[jj] += __uint_as_float(v[jj]);
+      }
+      float dr[GRU_HC], dz[GRU_HC], dn[GRU_HC], dnr[GRU_HC];
+      if (active) {
 #pragma unroll
         for (int jj = 0; jj < GRU_HC; ++jj) {
           const float g = dh[jj] + dh_rec[jj];
@@ -444,90 +455,79 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdPar
           dz[jj] = g * (hp[jj] - nn[jj]) * zz[jj] * (1.f - zz[jj]);
           dr[jj] = dn[jj] * hn[jj] * rr[jj] * (1.f - rr[jj]);
           dnr[jj] = dn[jj] * rr[jj];
-          dhz[jj] = g * zz[jj];
+          dh_rec[jj] = g * zz[jj];      // direct path h_{t-1} -> h_t; the W_hh path is added next step
           db_i[jj] += dr[jj];
           db_i[16 + jj] += dz[jj];
           db_i[32 + jj] += dn[jj];
           db_hn[jj] += dnr[jj];
         }
-        // dgi (bf16) row-major for the dX GEMM
-        {
-          bf16* o = p.dgi + m * (p.ndir * K3) + dir * K3 + j0;
+        // critical path: the exchange rows [dr | dz | dn*r] every CTA gathers for the product
+        if (step + 1 < T) {
           uint4 pk[2];
           uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+          bf16* x = xb + (long long)tid * K3 + j0;
 #pragma unroll
           for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dr[2 * q], dr[2 * q + 1]);
-          reinterpret_cast<uint4*>(o)[0] = pk[0]; reinterpret_cast<uint4*>(o)[1] = pk[1];
-          // exchange buffer rows are [dr | dz | dn*r]
-          bf16* x = xb + (long long)tid * K3 + j0;
           reinterpret_cast<uint4*>(x)[0] = pk[0]; reinterpret_cast<uint4*>(x)[1] = pk[1];
 #pragma unroll
           for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dz[2 * q], dz[2 * q + 1]);
-          reinterpret_cast<uint4*>(o + H)[0] = pk[0]; reinterpret_cast<uint4*>(o + H)[1] = pk[1];
           reinterpret_cast<uint4*>(x + H)[0] = pk[0]; reinterpret_cast<uint4*>(x + H)[1] = pk[1];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dn[2 * q], dn[2 * q + 1]);
-          reinterpret_cast<uint4*>(o + 2 * H)[0] = pk[0];
-          reinterpret_cast<uint4*>(o + 2 * H)[1] = pk[1];
 #pragma unroll
           for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dnr[2 * q], dnr[2 * q + 1]);
           reinterpret_cast<uint4*>(x + 2 * H)[0] = pk[0];
           reinterpret_cast<uint4*>(x + 2 * H)[1] = pk[1];
+          fence_proxy_async_all();
         }
-        // transposed copies for the weight-gradient GEMMs (column = t*Bp + b, coalesced over b)
-        {
-          bf16* gt = p.dgiT + ((long long)dir * K3 + j0) * M + m;
-          bf16* nt = p.dghnT + ((long long)dir * H + j0) * M + m;
-#pragma unroll
-          for (int jj = 0; jj < GRU_HC; ++jj) {
-            gt[(long long)jj * M] = __float2bfloat16_rn(dr[jj]);
-            gt[(long long)(H + jj) * M] = __float2bfloat16_rn(dz[jj]);
-            gt[(long long)(2 * H + jj) * M] = __float2bfloat16_rn(dn[jj]);
-            nt[(long long)jj * M] = __float2bfloat16_rn(dnr[jj]);
-          }
-        }
-        __threadfence();
       }
       if (step + 1 < T) {
-        loaders_barrier();
+        epi_barrier();
         if (tid == 0) {
+          __threadfence();
           grid_arrive(ctr);
-          grid_wait(ctr, (unsigned int)nC * (step + 1));
         }
-        loaders_barrier();
-        gather_operand(s, xb, K3, Bp, K3, nchunks, fill);
-        if (tid < 128) {
-          mbar_wait(s.accfull, step & 1);
-          tc_fence_after_sync();
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
-          tmem_ld_wait();
-          tc_fence_before_sync();
+      }
+      // ---- off the critical path: operands of the dX / dW GEMMs ----
+      if (active) {
+        bf16* o = p.dgi + m * (p.ndir * K3) + dir * K3 + j0;
+        uint4 pk[2];
+        uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
 #pragma unroll
-          for (int jj = 0; jj < GRU_HC; ++jj) dh_rec[jj] = __uint_as_float(v[jj]) + dhz[jj];
+        for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dr[2 * q], dr[2 * q + 1]);
+        reinterpret_cast<uint4*>(o)[0] = pk[0]; reinterpret_cast<uint4*>(o)[1] = pk[1];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dz[2 * q], dz[2 * q + 1]);
+        reinterpret_cast<uint4*>(o + H)[0] = pk[0]; reinterpret_cast<uint4*>(o + H)[1] = pk[1];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dn[2 * q], dn[2 * q + 1]);
+        reinterpret_cast<uint4*>(o + 2 * H)[0] = pk[0];
+        reinterpret_cast<uint4*>(o + 2 * H)[1] = pk[1];
+        bf16* gt = p.dgiT + ((long long)dir * K3 + j0) * M + m;
+        bf16* nt = p.dghnT + ((long long)dir * H + j0) * M + m;
+#pragma unroll
+        for (int jj = 0; jj < GRU_HC; ++jj) {
+          gt[(long long)jj * M] = __float2bfloat16_rn(dr[jj]);
+          gt[(long long)(H + jj) * M] = __float2bfloat16_rn(dz[jj]);
+          gt[(long long)(2 * H + jj) * M] = __float2bfloat16_rn(dn[jj]);
+          nt[(long long)jj * M] = __float2bfloat16_rn(dnr[jj]);
         }
-        // all TMEM reads of this step are done before the next step's MMAs may overwrite it:
-        // the next gather only starts after the next grid barrier, which follows this point.
       }
     }
     // ---- bias gradients: reduce the per-batch-row partial sums over the CTA ----
-    loaders_barrier();
+    epi_barrier();
     float* red = s.scratch;  // 64 floats
     if (tid < 64) red[tid] = 0.f;
-    loaders_barrier();
-    if (tid < 128) {
+    epi_barrier();
 #pragma unroll
-      for (int r = 0; r < 48; ++r) {
-        const float v = warp_sum(active ? db_i[r] : 0.f);
-        if (lane == 0) atomicAdd(&red[r], v);
-      }
-#pragma unroll
-      for (int jj = 0; jj < GRU_HC; ++jj) {
-        const float v = warp_sum(active ? db_hn[jj] : 0.f);
-        if (lane == 0) atomicAdd(&red[48 + jj], v);
-      }
+    for (int r = 0; r < 48; ++r) {
+      const float v = warp_sum(active ? db_i[r] : 0.f);
+      if (lane == 0) atomicAdd(&red[r], v);
     }
-    loaders_barrier();
+#pragma unroll
+    for (int jj = 0; jj < GRU_HC; ++jj) {
+      const float v = warp_sum(active ? db_hn[jj] : 0.f);
+      if (lane == 0) atomicAdd(&red[48 + jj], v);
+    }
+    epi_barrier();
     if (tid < 48) {
       const int g = tid / GRU_HC, jj = tid % GRU_HC;
       const int idx = dir * K3 + g * H + j0 + jj;
@@ -538,14 +538,36 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdPar
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 32);
   }
 }
 
-static size_t gru_smem_bytes(int wbytes) {
-  return (size_t)wbytes + GRU_RING * GRU_SLOT_BYTES + 1024 /*align*/ + 512 /*barriers+scratch*/;
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
+                      long long ld, int box_rows);
+
+// ring slots that fit next to the resident weights
+static int gru_ring_slots(int wbytes, int Bp, int nchunks, size_t* smem_bytes) {
+  const int stride = Bp * 128;
+  const int slack = (128 - Bp) * 128;
+  const int fixed = wbytes + slack + 1024 /*align*/ + (2 * GRU_MAX_RING + 2) * 8 + 256 /*scratch*/;
+  int ring = (227 * 1024 - fixed) / stride;
+  if (ring > GRU_MAX_RING) ring = GRU_MAX_RING;
+  if (ring > nchunks) ring = nchunks;
+  if (ring < 2) return -1;
+  *smem_bytes = (size_t)fixed + (size_t)ring * stride;
+  return ring;
+}
+
+static int gru_launch(const void* kernel, int grid, size_t smem, void** args, cudaStream_t stream) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return SB_ERR_CUDA;
+  if (cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(GRU_THREADS), args, smem, stream) !=
+      cudaSuccess)
+    return SB_ERR_CUDA;
+  return SB_OK;
 }
 
 }  // namespace sb
@@ -571,19 +593,22 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
   p.xn = reinterpret_cast<bf16*>(xn_bf16); p.xnT = reinterpret_cast<bf16*>(xnT_bf16);
   p.gates = gates; p.barrier = barrier; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
   const int nchunks = (H + 63) / 64;
-  const size_t smem = gru_smem_bytes(nchunks * 48 * 128);
-  if (smem > 227 * 1024) return SB_ERR_UNSUPPORTED;
-  if (cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem) != cudaSuccess)
-    return SB_ERR_CUDA;
+  size_t smem = 0;
+  p.ring = gru_ring_slots(nchunks * 48 * 128, Bp, nchunks, &smem);
+  if (p.ring < 0) return SB_ERR_UNSUPPORTED;
+  // one tensor map per direction over that direction's H columns of h (bf16 [T*Bp][ndir*H]):
+  // columns past H are out of bounds and read as zero
+  CUtensorMap tm[2];
+  for (int d = 0; d < 2; ++d) {
+    const int dd = d < ndir ? d : 0;
+    rc = make_tmap_bf16_2d(&tm[d], p.xn + (size_t)dd * H, (long long)T * Bp, H,
+                           (long long)ndir * H, Bp);
+    if (rc != SB_OK) return rc;
+  }
   if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * ndir, stream) != cudaSuccess)
     return SB_ERR_CUDA;
-  void* args[] = {(void*)&p};
-  const int grid = ndir * (H / GRU_HC);
-  if (cudaLaunchCooperativeKernel((void*)gru_fwd_kernel, dim3(grid), dim3(GRU_THREADS), args, smem,
-                                  stream) != cudaSuccess)
-    return SB_ERR_CUDA;
-  return SB_OK;
+  void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&p};
+  return gru_launch((const void*)gru_fwd_kernel, ndir * (H / GRU_HC), smem, args, stream);
 }
 
 extern "C" int sb_gru_bwd_workspace_size(int Bp, int H, int ndir, size_t* bytes) {
@@ -612,18 +637,20 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   p.dghnT = reinterpret_cast<bf16*>(dghnT_bf16);
   p.xchg = reinterpret_cast<bf16*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   p.dbih = dbih; p.dbhh = dbhh; p.barrier = barrier; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
-  const int nchunks = (3 * H + 63) / 64;
-  const size_t smem = gru_smem_bytes(nchunks * 16 * 128);
-  if (smem > 227 * 1024) return SB_ERR_UNSUPPORTED;
-  if (cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem) != cudaSuccess)
-    return SB_ERR_CUDA;
+  const int K3 = 3 * H;
+  const int nchunks = (K3 + 63) / 64;
+  size_t smem = 0;
+  p.ring = gru_ring_slots(nchunks * 16 * 128, Bp, nchunks, &smem);
+  if (p.ring < 0) return SB_ERR_UNSUPPORTED;
+  // per direction: the two parity buffers stacked as [2*Bp rows][3H cols]
+  CUtensorMap tm[2];
+  for (int d = 0; d < 2; ++d) {
+    const int dd = d < ndir ? d : 0;
+    rc = make_tmap_bf16_2d(&tm[d], p.xchg + (size_t)dd * 2 * Bp * K3, 2LL * Bp, K3, K3, Bp);
+    if (rc != SB_OK) return rc;
+  }
   if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * ndir, stream) != cudaSuccess)
     return SB_ERR_CUDA;
-  void* args[] = {(void*)&p};
-  const int grid = ndir * (H / GRU_HC);
-  if (cudaLaunchCooperativeKernel((void*)gru_bwd_kernel, dim3(grid), dim3(GRU_THREADS), args, smem,
-                                  stream) != cudaSuccess)
-    return SB_ERR_CUDA;
-  return SB_OK;
+  void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&p};
+  return gru_launch((const void*)gru_bwd_kernel, ndir * (H / GRU_HC), smem, args, stream);
 }
