@@ -120,6 +120,10 @@ int sb_ctc_prefix_beam(const float* logp, const int* lens, int B, int T, int S, 
                        int blank, int* out_labels, int* out_lens, double* out_scores,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Developer hook (not part of the drop-in surface): device buffer of >= 64*16 uint64 receiving a
+ * globaltimer timeline of CTA 0 for the next sb_gru_fwd launches; NULL disables. */
+int sb_debug_gru_timeline(void* dev_buffer);
+
 #ifdef __cplusplus
 }
 #endif

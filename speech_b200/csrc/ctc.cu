@@ -16,7 +16,7 @@
 //   The (T x V) log-softmax of the utterance is staged ONCE in shared memory with coalesced
 //   reads of the logits (116 KB at T=1000, V=29); lattice rows ping-pong in shared memory.
 //
-// Precision: every row is stored relative to the maximum of the previous row (per-warp maxima are
+// Precision: the lattice recursion runs in float64 (see lse3d) and every row is stored relative to the maximum of the previous row (per-warp maxima are
 // published before the step barrier, so this costs no extra synchronisation); the subtracted
 // amounts accumulate in a per-side double.  fp32 log-space values therefore stay O(1) for any T
 // and the 1e-4 parity bar holds for long utterances.
@@ -60,13 +60,26 @@ SB_DEVINL float lse3(float a, float b, float c) {
   return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
+// log(exp(a)+exp(b)+exp(c)) in float64: the largest term contributes exp(0) = 1 exactly, so
+// only the two smaller terms are exponentiated.  float32 here accumulates ~1e-4 relative
+// gradient error over a T=1000 lattice (measured, and reproduced in numpy), float64 gives 2e-7.
+SB_DEVINL double lse3d(double a, double b, double c) {
+  const double hi = fmax(a, b), lo = fmin(a, b);
+  const double m = fmax(hi, c);
+  if (m == -INFINITY) return -INFINITY;
+  const double o1 = (c > hi) ? hi : lo;
+  const double o2 = (c > hi) ? lo : c;
+  return m + log1p(exp(o1 - m) + exp(o2 - m));
+}
+
 SB_DEVINL void side_barrier(int side) {
   asm volatile("bar.sync %0, %1;" ::"r"(side + 1), "r"(CTC_SIDE) : "memory");
 }
 
 template <int NS, bool STAGED>
 __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcParams p) {
-  extern __shared__ float smem[];
+  extern __shared__ double smem_d[];
+  float* smem = reinterpret_cast<float*>(smem_d);
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int side = tid / CTC_SIDE;  // 0: alpha, 1: beta
@@ -83,14 +96,14 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
 
   // ---- shared memory carve-up ----
   constexpr int SP = NS * CTC_SIDE + 4;        // padded lattice row (2 pads each end)
-  float* row_buf = smem;                        // [2 sides][2][SP]
-  float* occ = row_buf + 4 * SP;                // [2 sides][2][V]
+  double* row_buf = reinterpret_cast<double*>(smem);   // [2 sides][2][SP]  float64 lattice rows
+  float* occ = reinterpret_cast<float*>(row_buf + 4 * SP);  // [2 sides][2][V]
   float* red = occ + 4 * V;                     // [48] reduction scratch
   float* nred = red + 32;                       // [2 sides][2][8] per-warp row maxima
   float* lse_t = red + 64;                      // [T] (only !STAGED)
   float* lp = STAGED ? (red + 64) : nullptr;    // [T*V] (only STAGED)
 
-  for (int k = tid; k < 4 * SP; k += 2 * CTC_SIDE) row_buf[k] = CTC_NEG_INF;
+  for (int k = tid; k < 4 * SP; k += 2 * CTC_SIDE) row_buf[k] = -INFINITY;
   for (int k = tid; k < 4 * V; k += 2 * CTC_SIDE) occ[k] = 0.f;
 
   // zero the gradient rows beyond this utterance's length
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
     }
   }
 
-  float* my_rows = row_buf + side * 2 * SP + 2;  // +2: leading pad so [s-2] is addressable
+  double* my_rows = row_buf + side * 2 * SP + 2;  // +2: leading pad so [s-2] is addressable
   float* my_occ = occ + side * 2 * V;
   float* my_nred = nred + side * 16;             // [2][8] warp maxima of the last two rows
   const int Th = T / 2;
@@ -166,9 +179,9 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
   // (gathered from per-warp maxima published before the previous barrier) is subtracted, so
   // stored values stay O(1); the subtracted amounts accumulate in C (double).  One barrier per
   // row, issued by the caller.
-  auto step_row = [&](int n, int t, float (&vals)[NS]) {
-    float* cur = my_rows + (n & 1) * SP;
-    const float* prev = my_rows + ((n & 1) ^ 1) * SP;
+  auto step_row = [&](int n, int t, double (&vals)[NS]) {
+    double* cur = my_rows + (n & 1) * SP;
+    const double* prev = my_rows + ((n & 1) ^ 1) * SP;
     float m_prev = 0.f;
     if (n > 0) {
       const float* w = my_nred + ((n - 1) & 1) * 8;
@@ -182,19 +195,19 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
       const int s = i + CTC_SIDE * q;
-      float v = CTC_NEG_INF;
+      double v = -INFINITY;
       if (valid[q]) {
         if (n == 0) {
-          if (side == 0) { if (s <= 1) v = 0.f; }
-          else { if (s >= S - 2) v = 0.f; }
+          if (side == 0) { if (s <= 1) v = 0.0; }
+          else { if (s >= S - 2) v = 0.0; }
         } else if (side == 0) {
-          v = lse3(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : CTC_NEG_INF) - m_prev;
+          v = lse3d(prev[s], prev[s - 1], skip[q] ? prev[s - 2] : -INFINITY) - (double)m_prev;
         } else {
-          v = lse3(prev[s], prev[s + 1], skip[q] ? prev[s + 2] : CTC_NEG_INF) - m_prev;
+          v = lse3d(prev[s], prev[s + 1], skip[q] ? prev[s + 2] : -INFINITY) - (double)m_prev;
         }
-        v += emit(t, cls[q]);
+        v += (double)emit(t, cls[q]);
         cur[s] = v;
-        wm = fmaxf(wm, v);
+        wm = fmaxf(wm, (float)v);
       }
       vals[q] = v;
     }
@@ -209,11 +222,11 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
     const int nsteps = side == 0 ? Th : (T - Th);
     for (int n = 0; n < nsteps; ++n) {
       const int t = side == 0 ? n : (T - 1 - n);
-      float vals[NS];
+      double vals[NS];
       step_row(n, t, vals);
 #pragma unroll
-      for (int q = 0; q < NS; ++q)
-        if (valid[q]) ws[(size_t)t * p.S_stride + i + CTC_SIDE * q] = vals[q];
+      for (int q = 0; q < NS; ++q)   // spilled once, consumed once: float32 is enough here
+        if (valid[q]) ws[(size_t)t * p.S_stride + i + CTC_SIDE * q] = (float)vals[q];
       if (i == 0) offs[t] = C;
       side_barrier(side);
     }
@@ -223,7 +236,7 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
   // ------------------------------------------------------------------------------------------
   // meet in the middle: alpha_Th (side 0) x beta_Th (spilled by side 1) -> log p(y|x)
   // ------------------------------------------------------------------------------------------
-  float a_reg[NS];
+  double a_reg[NS];
   if (side == 0) {
     step_row(Th, Th, a_reg);
     float local_max = CTC_NEG_INF;
@@ -233,7 +246,8 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
       const int s = i + CTC_SIDE * q;
       contrib[q] = CTC_NEG_INF;
       if (valid[q]) {
-        contrib[q] = a_reg[q] + ld_cg_f(ws + (size_t)Th * p.S_stride + s) - emit(Th, cls[q]);
+        contrib[q] = (float)(a_reg[q] + (double)ld_cg_f(ws + (size_t)Th * p.S_stride + s) -
+                             (double)emit(Th, cls[q]));
         local_max = fmaxf(local_max, contrib[q]);
       }
     }
@@ -302,7 +316,7 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
                                            : CTC_NEG_INF;
       }
       if (more) other_off_next = offs[tn];
-      float vals[NS];
+      double vals[NS];
       if (side == 0 && it == 0) {
 #pragma unroll
         for (int q = 0; q < NS; ++q) vals[q] = a_reg[q];   // row Th was formed at the meeting point
@@ -316,7 +330,8 @@ __global__ void __launch_bounds__(2 * CTC_SIDE, 1) ctc_fwd_bwd_kernel(const CtcP
       for (int q = 0; q < NS; ++q) {
         const int s = i + CTC_SIDE * q;
         if (valid[q]) {
-          const float g = __expf((vals[q] + other[q] - emit(t, cls[q])) + delta);
+          const float g =
+              __expf((float)(vals[q] + (double)other[q] - (double)emit(t, cls[q])) + delta);
           if (s & 1) atomicAdd(occ_t + cls[q], g);
           else blank_sum += g;
         }
@@ -396,7 +411,8 @@ extern "C" int sb_ctc_fwd_bwd(const float* acts, float* grads, const int* labels
   p.ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.offs + (size_t)B * T) + 255) & ~(uintptr_t)255);
   p.B = B; p.T = T; p.V = V; p.blank = blank; p.S_stride = ns * CTC_SIDE;
 
-  const size_t fixed = (size_t)(4 * (ns * CTC_SIDE + 4) + 4 * V + 64) * sizeof(float) + 8;
+  const size_t fixed = (size_t)(4 * (ns * CTC_SIDE + 4)) * sizeof(double) +
+                       (size_t)(4 * V + 64) * sizeof(float) + 8;
   const size_t staged_bytes = fixed + (size_t)T * V * sizeof(float);
   const size_t unstaged_bytes = fixed + (size_t)T * sizeof(float);
   const size_t limit = 220 * 1024;

@@ -46,6 +46,7 @@ struct GruFwdParams {
   bf16* xnT;           // [ndir*H][(T+2)*Bp] h_t bf16 transposed, column (t+1)*Bp+b ; may be null
   float* gates;        // [T*Bp][ndir][4][H] saved r,z,n,hn for backward ; may be null
   unsigned int* barrier;  // [ndir] zero-initialised counters
+  unsigned long long* dbg;  // optional timeline (CTA 0): [step][16] globaltimer stamps, or null
   int T, Bp, H, ndir, ring;
 };
 
@@ -63,6 +64,16 @@ struct GruBwdParams {
   unsigned int* barrier;  // [ndir]
   int T, Bp, H, ndir, ring;
 };
+
+SB_DEVINL unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define GRU_STAMP(ev)                                                          \
+  do {                                                                         \
+    if (p.dbg && blockIdx.x == 0 && step < 64) p.dbg[step * 16 + (ev)] = gtime(); \
+  } while (0)
 
 // ---- per-direction grid barrier ------------------------------------------------------------
 SB_DEVINL void grid_arrive(unsigned int* ctr) { red_release_gpu_add(ctr, 1u); }
@@ -205,16 +216,20 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         const int t = dir == 0 ? step : (T - 1 - step);
         const int tp = dir == 0 ? t - 1 : t + 1;
         grid_wait(ctr, (unsigned int)nC * step);   // every CTA of this direction published h_{tp}
+        GRU_STAMP(0);
         fence_proxy_async_all();                    // generic-proxy writes -> async-proxy (TMA) reads
         tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, fill);
+        GRU_STAMP(1);
       }
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       unsigned int fill = 0;
-      for (int step = 1; step < T; ++step)
+      for (int step = 1; step < T; ++step) {
         mma_consume<48>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, fill);
+        GRU_STAMP(2);
+      }
     }
   } else {
     // ===================== epilogue: thread = batch row =====================
@@ -243,6 +258,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       float acc[48];
       if (step > 0) {
         mbar_wait(s.accfull, (step - 1) & 1);
+        if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
         uint32_t v[16];
 #pragma unroll
@@ -253,6 +269,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
           for (int jj = 0; jj < 16; ++jj) acc[gg * 16 + jj] = __uint_as_float(v[jj]);
         }
         tc_fence_before_sync();
+        if (tid == 0) GRU_STAMP(4);
       } else {
 #pragma unroll
         for (int r = 0; r < 48; ++r) acc[r] = 0.f;
@@ -276,12 +293,17 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         uint4* xo = reinterpret_cast<uint4*>(p.xn + m * D + dir * H + j0);
         xo[0] = pk[0];
         xo[1] = pk[1];
+        if (tid == 0) GRU_STAMP(5);
         fence_proxy_async_all();   // these generic-proxy writes are read by other CTAs' TMA
+        if (tid == 0) GRU_STAMP(6);
       }
       epi_barrier();
       if (tid == 0) {
+        GRU_STAMP(7);
         __threadfence();
+        GRU_STAMP(8);
         grid_arrive(ctr);
+        GRU_STAMP(9);
       }
       // off the critical path: fp32 state, transposed copy, saved gates
       if (active) {
@@ -310,6 +332,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
           }
         }
       }
+      if (tid == 0) GRU_STAMP(10);
     }
   }
 
@@ -574,6 +597,15 @@ static int gru_launch(const void* kernel, int grid, size_t smem, void** args, cu
 
 using namespace sb;
 
+static unsigned long long* g_gru_dbg = nullptr;
+
+// developer hook: device buffer of >= 64*16 u64 that receives a per-step timeline of CTA 0 of the
+// next sb_gru_fwd launches (nullptr disables).  Not part of the drop-in surface.
+extern "C" int sb_debug_gru_timeline(void* dev_buffer) {
+  g_gru_dbg = reinterpret_cast<unsigned long long*>(dev_buffer);
+  return SB_OK;
+}
+
 static int gru_check(int T, int Bp, int H, int ndir) {
   if (T <= 0 || Bp <= 0 || H <= 0 || (ndir != 1 && ndir != 2)) return SB_ERR_INVALID;
   if (H % GRU_HC != 0 || Bp % 8 != 0 || Bp > 128) return SB_ERR_UNSUPPORTED;
@@ -592,6 +624,7 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
   p.gi = gi; p.whh = reinterpret_cast<const bf16*>(whh_bf16); p.bhh = bhh; p.y = y;
   p.xn = reinterpret_cast<bf16*>(xn_bf16); p.xnT = reinterpret_cast<bf16*>(xnT_bf16);
   p.gates = gates; p.barrier = barrier; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
+  p.dbg = g_gru_dbg;
   const int nchunks = (H + 63) / 64;
   size_t smem = 0;
   p.ring = gru_ring_slots(nchunks * 48 * 128, Bp, nchunks, &smem);

@@ -1,0 +1,27 @@
+"""Developer tool: per-step timeline (ns) of CTA 0 of the GRU forward kernel at north-star width."""
+import sys
+import numpy as np, torch
+sys.path.insert(0, ".")
+from speech_b200 import _lib, ops
+lib = _lib.load()
+torch.manual_seed(0)
+B, T, In, H = 64, 64, 2048, 1024
+rnn = torch.nn.GRU(In, H, 1, batch_first=True, bidirectional=True).cuda()
+x = torch.randn(B, T, In, device="cuda")
+dbg = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")
+with torch.no_grad():
+    ops.gru_stack(x, rnn)
+    torch.cuda.synchronize()
+    lib.sb_debug_gru_timeline(dbg.data_ptr())
+    ops.gru_stack(x, rnn)
+    torch.cuda.synchronize()
+    lib.sb_debug_gru_timeline(None)
+d = dbg.cpu().numpy().reshape(64, 16)
+names = ["P:grid_wait done", "P:tma issued", "M:all mma committed", "E:accfull", "E:tmem loaded",
+         "E:xn stored", "E:proxy fence", "E:epi barrier", "E:threadfence", "E:arrived", "E:offpath done"]
+for step in (10, 11, 12, 40):
+    base = d[step - 1][9]   # previous step's arrival by this CTA
+    print("step %d (ns since this CTA's previous arrive):" % step)
+    for i, n in enumerate(names):
+        print("   %-22s %7d" % (n, d[step][i] - base))
+print("mean step period (ns):", (d[60][9] - d[10][9]) / 50.0)
