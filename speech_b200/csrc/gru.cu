@@ -10,30 +10,37 @@
 // BOTH directions:
 //   * CTA c of direction d owns 16 hidden units j0..j0+15: its 48 rows of W_hh (r,z,n) stay
 //     resident in shared memory (bf16, UMMA K-major SWIZZLE_128B chunks) for all T steps;
-//   * per step the CTA all-gathers h_{t-1} (bf16, written by every CTA of the direction in the
-//     previous step) from L2 into a 4-slot smem ring, and one thread issues tcgen05.mma
-//     D[batch(128) x 48] += h_{t-1}[batch x 64] * Wslice[48 x 64]^T per K chunk, accumulating
-//     in TMEM; loads and MMAs are pipelined through full/empty mbarriers;
-//   * thread b (= TMEM lane = batch row) reads its 48 accumulators with tcgen05.ld, applies the
-//     gate math in fp32 (h_{t-1} of its own units lives in registers across steps) and writes
-//     h_t as fp32 (Y), bf16 (next GEMM operand) and bf16-transposed (wgrad operand);
-//   * a per-direction grid barrier (red.release / ld.acquire on a global counter) separates steps.
+//   * per step every CTA needs ALL of h_{t-1} (bf16, written by the CTAs of its direction in the
+//     previous step).  CTAs form thread-block clusters of up to 8; each CTA fetches 1/CS of the
+//     [Bp x 64] chunks with TMA and MULTICASTS them into the shared memory of all CTAs of its
+//     cluster, so L2 is read once per cluster instead of once per CTA (the un-multicast version
+//     was bound by 64 SMs hammering the same L2 lines: 4 us of a 13 us step);
+//   * one thread issues tcgen05.mma  D[batch(128) x 48] += h_{t-1}[batch x 64] * Wslice[48 x 64]^T
+//     per chunk as its mbarrier completes; accumulators live in TMEM;
+//   * 8 epilogue warps (thread = TMEM lane = batch row, 8 hidden units each) read the
+//     accumulators with tcgen05.ld, apply the gate math in fp32 (h_{t-1} of the thread's own units
+//     stays in registers across steps), publish the bf16 h_t, arrive on the per-direction grid
+//     barrier, and only then write the fp32 state / transposed copy / saved gates;
+//   * the grid barrier is one red.release.gpu + ld.acquire.gpu polling on a global counter.
 // The backward kernel has the same structure with W_hh^T resident (16 rows x 3H) and the
 // all-gather over the pre-activation gradients dgh_t (batch x 3H).
 //
-// Roofline: the MMAs are tensor work but each step is bound by the all-gather + barrier latency;
-// DESIGN.md reports us/step next to the tensor-pipe share.
+// Roofline: tensor work, but each step is bound by the all-gather + barrier latency; DESIGN.md
+// reports us/step next to the tensor-pipe share.
 #include "common.cuh"
 #include <cuda.h>
+#include <string.h>
+#include <algorithm>
 
 #include "../../include/speech_b200.h"
 
 namespace sb {
 
-static constexpr int GRU_HC = 16;           // hidden units per CTA
-static constexpr int GRU_MAX_RING = 16;     // smem ring slots for the gathered operand
-static constexpr int GRU_EPI = 128;         // warps 0..3: epilogue (thread = TMEM lane = batch row)
-static constexpr int GRU_THREADS = GRU_EPI + 64;  // + warp 4: MMA issuer/TMEM owner, warp 5: TMA
+static constexpr int GRU_HC = 16;            // hidden units per CTA
+static constexpr int GRU_UPT = 8;            // hidden units per epilogue thread
+static constexpr int GRU_MAX_RING = 16;      // smem ring slots for the gathered operand
+static constexpr int GRU_EPI = 256;          // warps 0..7: epilogue
+static constexpr int GRU_THREADS = GRU_EPI + 64;  // + warp 8: MMA issuer/TMEM owner, warp 9: TMA
 
 typedef __nv_bfloat16 bf16;
 
@@ -62,6 +69,7 @@ struct GruBwdParams {
   float* dbih;         // [ndir*3H] += sum_{t,b} dgi
   float* dbhh;         // [ndir*3H] += sum_{t,b} dgh
   unsigned int* barrier;  // [ndir]
+  unsigned long long* dbg;
   int T, Bp, H, ndir, ring;
 };
 
@@ -70,8 +78,8 @@ SB_DEVINL unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define GRU_STAMP(ev)                                                          \
-  do {                                                                         \
+#define GRU_STAMP(ev)                                                              \
+  do {                                                                             \
     if (p.dbg && blockIdx.x == 0 && step < 64) p.dbg[step * 16 + (ev)] = gtime(); \
   } while (0)
 
@@ -85,9 +93,44 @@ SB_DEVINL void grid_wait(const unsigned int* ctr, unsigned int target) {
 }
 SB_DEVINL void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GRU_EPI) : "memory"); }
 
+// ---- cluster helpers ---------------------------------------------------------------------------
+SB_DEVINL uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SB_DEVINL uint32_t cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+SB_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA box load multicast to every CTA in `mask` (same smem offset + same mbarrier offset in each)
+SB_DEVINL void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0,
+                              int32_t c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrive (when all prior MMAs of this thread retire) on the mbarrier at this offset in every CTA
+// of `mask`
+SB_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+
 struct GruSmem {
+  uint8_t* ring;    // ring slots (stride = Bp*128 bytes), placed BEFORE the weights so that the
+                    // 128-row MMA read of the last slot overruns into (finite) weight data
   uint8_t* wtile;   // resident weight chunks
-  uint8_t* ring;    // ring slots, stride = Bp*128 bytes (+ slack so a 128-row read stays inside)
   uint64_t* full;   // [GRU_MAX_RING]
   uint64_t* empty;  // [GRU_MAX_RING]
   uint64_t* accfull;
@@ -95,12 +138,12 @@ struct GruSmem {
   float* scratch;   // [64]
 };
 
-SB_DEVINL GruSmem carve(uint8_t* raw, int wbytes, int ring_bytes) {
+SB_DEVINL GruSmem carve(uint8_t* raw, int ring_bytes, int wbytes) {
   GruSmem s;
-  s.wtile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) &
-                                       ~static_cast<uintptr_t>(1023));
-  s.ring = s.wtile + wbytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s.ring + ring_bytes);
+  s.ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) &
+                                      ~static_cast<uintptr_t>(1023));
+  s.wtile = s.ring + ring_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.wtile + wbytes);
   s.full = bars;
   s.empty = bars + GRU_MAX_RING;
   s.accfull = bars + 2 * GRU_MAX_RING;
@@ -109,46 +152,85 @@ SB_DEVINL GruSmem carve(uint8_t* raw, int wbytes, int ring_bytes) {
   return s;
 }
 
-// ring geometry shared by host and device
-SB_DEVINL int ring_stride(int Bp) { return Bp * 128; }
-
-// TMA producer (one thread): bring `nchunks` [Bp x 64] bf16 boxes of the operand whose rows start
-// at `row0` into the ring.  `fill` is the running chunk counter shared (by construction) with
-// the MMA thread.
+// The gathered operand of one step is `nchunks` [Bp x 64] boxes; chunk c uses slot c % ring and
+// nchunks % ring == 0, so every slot is used upr = nchunks/ring times per step and the mbarrier
+// phase of use (k, c) is k*upr + c/ring for both the full and the empty barrier of the slot.
+//
+// TMA producer (one thread per CTA).  Every CTA arms its own full barriers; chunk c is fetched
+// by the CTA whose cluster rank is c % CS and multicast to the whole cluster.
 SB_DEVINL void tma_gather(const GruSmem& s, const CUtensorMap* tm, int row0, int Bp, int nchunks,
-                          int ring, unsigned int& fill) {
-  const int stride = ring_stride(Bp);
+                          int ring, int k, uint32_t rank, uint32_t cs) {
+  const int stride = Bp * 128;
+  const int upr = nchunks / ring;
+  const uint16_t mask = (uint16_t)((1u << cs) - 1u);
   for (int c = 0; c < nchunks; ++c) {
-    const unsigned int slot = fill % ring;
-    const unsigned int par = (fill / ring) & 1u;
-    mbar_wait(&s.empty[slot], par ^ 1u);
+    const int slot = c % ring;
+    const unsigned int P = (unsigned int)(k * upr + c / ring);
+    if (c >= ring) mbar_wait(&s.empty[slot], (P - 1u) & 1u);   // released by ALL CTAs of the cluster
     mbar_expect_tx(&s.full[slot], (uint32_t)stride);
-    tma_load_2d(s.ring + slot * stride, tm, &s.full[slot], c * 64, row0);
-    ++fill;
+    if ((uint32_t)c % cs == rank) {
+      if (cs > 1) tma_load_2d_mc(s.ring + slot * stride, tm, &s.full[slot], c * 64, row0, mask);
+      else tma_load_2d(s.ring + slot * stride, tm, &s.full[slot], c * 64, row0);
+    }
   }
 }
 
-// MMA thread: consume `nchunks` ring slots against the resident weight chunks.
+// MMA thread: consume the step's chunks against the resident weight chunks.
 template <int N>
 SB_DEVINL void mma_consume(const GruSmem& s, uint32_t tmem_d, int nchunks, int wchunk_bytes,
-                           int Bp, int ring, unsigned int& fill) {
+                           int Bp, int ring, int k, uint32_t cs) {
   constexpr uint32_t idesc = umma_idesc_bf16_f32(128, N);
-  const int stride = ring_stride(Bp);
+  const int stride = Bp * 128;
+  const int upr = nchunks / ring;
+  const uint16_t mask = (uint16_t)((1u << cs) - 1u);
   for (int c = 0; c < nchunks; ++c) {
-    const unsigned int slot = fill % ring;
-    const unsigned int par = (fill / ring) & 1u;
-    mbar_wait(&s.full[slot], par);
+    const int slot = c % ring;
+    const unsigned int P = (unsigned int)(k * upr + c / ring);
+    mbar_wait(&s.full[slot], P & 1u);
     tc_fence_after_sync();
     const uint64_t da = umma_desc_sw128_kmajor(smem_u32(s.ring + slot * stride));
     const uint64_t db = umma_desc_sw128_kmajor(smem_u32(s.wtile + c * wchunk_bytes));
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                   (c > 0 || k > 0) ? 1u : 0u);
-    umma_commit(&s.empty[slot]);
-    ++fill;
+    for (int kk = 0; kk < 4; ++kk)
+      umma_bf16_ss(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                   (c > 0 || kk > 0) ? 1u : 0u);
+    if (ring < nchunks) {
+      if (cs > 1) umma_commit_mc(&s.empty[slot], mask);
+      else umma_commit(&s.empty[slot]);
+    }
   }
   umma_commit(s.accfull);
+}
+
+SB_DEVINL float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+SB_DEVINL float fast_tanh(float x) {
+  // 1 - 2/(exp(2x)+1), clamped so exp never overflows (__fdividef(2, inf) is not guaranteed 0)
+  const float xc = fminf(fmaxf(x, -15.f), 15.f);
+  return 1.0f - __fdividef(2.0f, __expf(2.0f * xc) + 1.0f);
+}
+
+SB_DEVINL void ld8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+SB_DEVINL void st8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+SB_DEVINL uint4 pack8(const float (&v)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]);
+  r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
+  return r;
+}
+SB_DEVINL void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7])
+      : "r"(taddr)
+      : "memory");
 }
 
 // =============================================================================================
@@ -164,27 +246,31 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   const int j0 = (blockIdx.x % nC) * GRU_HC;
   const int nchunks = (H + 63) / 64;
   constexpr int WCHUNK = 48 * 128;  // 48 rows x 64 bf16
-  const int ring_bytes = p.ring * ring_stride(Bp) + (128 - Bp) * 128;
-  const GruSmem s = carve(smem_raw, nchunks * WCHUNK, ring_bytes);
+  const int ring_bytes = p.ring * Bp * 128;
+  // the 128-row A read of the last ring slot overruns by (16 KB - stride) into this region
+  const int wbytes = max(nchunks * WCHUNK, 16384 - Bp * 128);
+  const GruSmem s = carve(smem_raw, ring_bytes, wbytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = p.ndir * H;
   const long long ldT = (long long)(T + 2) * Bp;
   const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
+  const uint32_t crank = cluster_rank(), csize = cluster_size();
 
-  // ---- one-time setup: zero the ring, stage this CTA's 48 weight rows, barriers, TMEM ----
-  for (int k = tid; k < ring_bytes / 16; k += GRU_THREADS)
+  // ---- one-time setup: zero ring + weight region, stage the 48 weight rows, barriers, TMEM ----
+  for (int k = tid; k < (ring_bytes + wbytes) / 16; k += GRU_THREADS)
     reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
   {
     const int pieces_per_row = nchunks * 8;
     for (int k = tid; k < 48 * pieces_per_row; k += GRU_THREADS) {
       const int r = k / pieces_per_row, pc = k % pieces_per_row;
       const int g = r / GRU_HC, jj = r % GRU_HC;
       const int col = pc * 8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (col < H)
-        v = *reinterpret_cast<const uint4*>(p.whh + ((long long)dir * 3 * H + g * H + j0 + jj) * H +
-                                            col);
-      *reinterpret_cast<uint4*>(s.wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+      if (col < H) {
+        const uint4 v = *reinterpret_cast<const uint4*>(
+            p.whh + ((long long)dir * 3 * H + g * H + j0 + jj) * H + col);
+        *reinterpret_cast<uint4*>(s.wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+      }
     }
     if (tid < 48) {
       const int g = tid / GRU_HC, jj = tid % GRU_HC;
@@ -194,105 +280,100 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   if (tid == 0) {
     for (int i = 0; i < GRU_MAX_RING; ++i) {
       mbar_init(&s.full[i], 1);
-      mbar_init(&s.empty[i], 1);
+      mbar_init(&s.empty[i], csize);
     }
     mbar_init(s.accfull, 1);
     mbar_fence_init();
     tma_prefetch_desc(tm);
   }
-  if (warp == 4) tmem_alloc(s.tmem_slot, 64);
+  if (warp == 8) tmem_alloc(s.tmem_slot, 64);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   const uint32_t tmem_base = *s.tmem_slot;
   unsigned int* ctr = p.barrier + dir;
 
-  if (warp == 5) {
+  if (warp == 9) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      unsigned int fill = 0;
       for (int step = 1; step < T; ++step) {
         const int t = dir == 0 ? step : (T - 1 - step);
         const int tp = dir == 0 ? t - 1 : t + 1;
         grid_wait(ctr, (unsigned int)nC * step);   // every CTA of this direction published h_{tp}
         GRU_STAMP(0);
         fence_proxy_async_all();                    // generic-proxy writes -> async-proxy (TMA) reads
-        tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, fill);
+        tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, step - 1, crank, csize);
         GRU_STAMP(1);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      unsigned int fill = 0;
       for (int step = 1; step < T; ++step) {
-        mma_consume<48>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, fill);
+        mma_consume<48>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, step - 1, csize);
         GRU_STAMP(2);
       }
     }
   } else {
-    // ===================== epilogue: thread = batch row =====================
-    float hprev[GRU_HC];
+    // ===================== epilogue: thread = (batch row, half of the 16 units) ==============
+    const int row = (warp & 3) * 32 + lane;      // TMEM lane this thread may read
+    const int uh = warp >> 2;                    // which 8 of the CTA's 16 units
+    const int ju = j0 + uh * GRU_UPT;
+    float hprev[GRU_UPT];
 #pragma unroll
-    for (int jj = 0; jj < GRU_HC; ++jj) hprev[jj] = 0.f;
-    float bias[48];
+    for (int jj = 0; jj < GRU_UPT; ++jj) hprev[jj] = 0.f;
+    float bias[3][GRU_UPT];
 #pragma unroll
-    for (int r = 0; r < 48; ++r) bias[r] = s.scratch[r];
-    const bool active = tid < Bp;
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int jj = 0; jj < GRU_UPT; ++jj) bias[g][jj] = s.scratch[g * 16 + uh * GRU_UPT + jj];
+    const bool active = row < Bp;
     for (int step = 0; step < T; ++step) {
       const int t = dir == 0 ? step : (T - 1 - step);
       // this step's input projections do not depend on the recurrence: fetch them first
-      float gi[48];
+      float gi[3][GRU_UPT];
       if (active) {
-        const float* g = p.gi + ((long long)t * Bp + tid) * (p.ndir * 3 * H) + dir * 3 * H + j0;
+        const float* g = p.gi + ((long long)t * Bp + row) * (p.ndir * 3 * H) + dir * 3 * H + ju;
 #pragma unroll
-        for (int gg = 0; gg < 3; ++gg)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(g + gg * H) + q);
-            gi[gg * 16 + q * 4 + 0] = v.x; gi[gg * 16 + q * 4 + 1] = v.y;
-            gi[gg * 16 + q * 4 + 2] = v.z; gi[gg * 16 + q * 4 + 3] = v.w;
-          }
+        for (int gg = 0; gg < 3; ++gg) ld8(g + gg * H, gi[gg]);
       }
-      float acc[48];
+      float acc[3][GRU_UPT];
       if (step > 0) {
         mbar_wait(s.accfull, (step - 1) & 1);
         if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
-        uint32_t v[16];
+        uint32_t v[8];
 #pragma unroll
         for (int gg = 0; gg < 3; ++gg) {
-          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + gg * 16, v);
+          tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + gg * 16 + uh * GRU_UPT,
+                            v);
           tmem_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) acc[gg * 16 + jj] = __uint_as_float(v[jj]);
+          for (int jj = 0; jj < GRU_UPT; ++jj) acc[gg][jj] = __uint_as_float(v[jj]);
         }
         tc_fence_before_sync();
         if (tid == 0) GRU_STAMP(4);
       } else {
 #pragma unroll
-        for (int r = 0; r < 48; ++r) acc[r] = 0.f;
+        for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+          for (int jj = 0; jj < GRU_UPT; ++jj) acc[gg][jj] = 0.f;
       }
-      const long long m = (long long)t * Bp + tid;
-      float hn[GRU_HC], rr[GRU_HC], zz[GRU_HC], nn[GRU_HC];
+      const long long m = (long long)t * Bp + row;
+      float hn[GRU_UPT], rr[GRU_UPT], zz[GRU_UPT], nn[GRU_UPT];
       if (active) {
 #pragma unroll
-        for (int jj = 0; jj < GRU_HC; ++jj) {
-          rr[jj] = sigmoidf_fast(gi[jj] + acc[jj] + bias[jj]);
-          zz[jj] = sigmoidf_fast(gi[16 + jj] + acc[16 + jj] + bias[16 + jj]);
-          hn[jj] = acc[32 + jj] + bias[32 + jj];
-          nn[jj] = tanhf_fast(gi[32 + jj] + rr[jj] * hn[jj]);
+        for (int jj = 0; jj < GRU_UPT; ++jj) {
+          rr[jj] = fast_sigmoid(gi[0][jj] + acc[0][jj] + bias[0][jj]);
+          zz[jj] = fast_sigmoid(gi[1][jj] + acc[1][jj] + bias[1][jj]);
+          hn[jj] = acc[2][jj] + bias[2][jj];
+          nn[jj] = fast_tanh(gi[2][jj] + rr[jj] * hn[jj]);
           hprev[jj] = (1.f - zz[jj]) * nn[jj] + zz[jj] * hprev[jj];
         }
         // critical path: only the bf16 h_t that the other CTAs gather next step
-        uint4 pk[2];
-        uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(hprev[2 * q], hprev[2 * q + 1]);
-        uint4* xo = reinterpret_cast<uint4*>(p.xn + m * D + dir * H + j0);
-        xo[0] = pk[0];
-        xo[1] = pk[1];
+        *reinterpret_cast<uint4*>(p.xn + m * D + dir * H + ju) = pack8(hprev);
         if (tid == 0) GRU_STAMP(5);
         fence_proxy_async_all();   // these generic-proxy writes are read by other CTAs' TMA
         if (tid == 0) GRU_STAMP(6);
@@ -300,36 +381,23 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       epi_barrier();
       if (tid == 0) {
         GRU_STAMP(7);
-        __threadfence();
-        GRU_STAMP(8);
-        grid_arrive(ctr);
+        grid_arrive(ctr);          // release: cumulative over the CTA's writes ordered by bar.sync
         GRU_STAMP(9);
       }
       // off the critical path: fp32 state, transposed copy, saved gates
       if (active) {
-        float* yo = p.y + m * D + dir * H + j0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          reinterpret_cast<float4*>(yo)[q] =
-              make_float4(hprev[q * 4], hprev[q * 4 + 1], hprev[q * 4 + 2], hprev[q * 4 + 3]);
+        st8(p.y + m * D + dir * H + ju, hprev);
         if (p.xnT) {
-          bf16* xt = p.xnT + (long long)(dir * H + j0) * ldT + (long long)(t + 1) * Bp + tid;
+          bf16* xt = p.xnT + (long long)(dir * H + ju) * ldT + (long long)(t + 1) * Bp + row;
 #pragma unroll
-          for (int jj = 0; jj < GRU_HC; ++jj) xt[jj * ldT] = __float2bfloat16_rn(hprev[jj]);
+          for (int jj = 0; jj < GRU_UPT; ++jj) xt[jj * ldT] = __float2bfloat16_rn(hprev[jj]);
         }
         if (p.gates) {
-          float* go = p.gates + ((m * p.ndir + dir) * 4) * H + j0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            reinterpret_cast<float4*>(go)[q] =
-                make_float4(rr[q * 4], rr[q * 4 + 1], rr[q * 4 + 2], rr[q * 4 + 3]);
-            reinterpret_cast<float4*>(go + H)[q] =
-                make_float4(zz[q * 4], zz[q * 4 + 1], zz[q * 4 + 2], zz[q * 4 + 3]);
-            reinterpret_cast<float4*>(go + 2 * H)[q] =
-                make_float4(nn[q * 4], nn[q * 4 + 1], nn[q * 4 + 2], nn[q * 4 + 3]);
-            reinterpret_cast<float4*>(go + 3 * H)[q] =
-                make_float4(hn[q * 4], hn[q * 4 + 1], hn[q * 4 + 2], hn[q * 4 + 3]);
-          }
+          float* go = p.gates + ((m * p.ndir + dir) * 4) * H + ju;
+          st8(go, rr);
+          st8(go + H, zz);
+          st8(go + 2 * H, nn);
+          st8(go + 3 * H, hn);
         }
       }
       if (tid == 0) GRU_STAMP(10);
@@ -338,7 +406,8 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  cluster_sync_all();   // no CTA leaves while peers may still signal its barriers
+  if (warp == 8) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 64);
   }
@@ -358,68 +427,74 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   const int K3 = 3 * H;
   const int nchunks = (K3 + 63) / 64;
   constexpr int WCHUNK = 16 * 128;  // 16 rows x 64 bf16
-  const int ring_bytes = p.ring * ring_stride(Bp) + (128 - Bp) * 128;
-  const GruSmem s = carve(smem_raw, nchunks * WCHUNK, ring_bytes);
+  const int ring_bytes = p.ring * Bp * 128;
+  const int wbytes = max(nchunks * WCHUNK, 16384 - Bp * 128);
+  const GruSmem s = carve(smem_raw, ring_bytes, wbytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = p.ndir * H;
   const long long M = (long long)T * Bp;
   const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
+  const uint32_t crank = cluster_rank(), csize = cluster_size();
 
-  for (int k = tid; k < ring_bytes / 16; k += GRU_THREADS)
+  for (int k = tid; k < (ring_bytes + wbytes) / 16; k += GRU_THREADS)
     reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
   {
     // resident operand: rows = the 16 hidden units k0..k0+15 of W_hh^T, K = 3H
     const int pieces_per_row = nchunks * 8;
     for (int k = tid; k < 16 * pieces_per_row; k += GRU_THREADS) {
       const int r = k / pieces_per_row, pc = k % pieces_per_row;
       const int col = pc * 8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (col < K3)
-        v = *reinterpret_cast<const uint4*>(p.whhT + ((long long)dir * H + j0 + r) * K3 + col);
-      *reinterpret_cast<uint4*>(s.wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+      if (col < K3) {
+        const uint4 v =
+            *reinterpret_cast<const uint4*>(p.whhT + ((long long)dir * H + j0 + r) * K3 + col);
+        *reinterpret_cast<uint4*>(s.wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+      }
     }
   }
   if (tid == 0) {
     for (int i = 0; i < GRU_MAX_RING; ++i) {
       mbar_init(&s.full[i], 1);
-      mbar_init(&s.empty[i], 1);
+      mbar_init(&s.empty[i], csize);
     }
     mbar_init(s.accfull, 1);
     mbar_fence_init();
     tma_prefetch_desc(tm);
   }
-  if (warp == 4) tmem_alloc(s.tmem_slot, 32);
+  if (warp == 8) tmem_alloc(s.tmem_slot, 32);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  cluster_sync_all();
   const uint32_t tmem_base = *s.tmem_slot;
   unsigned int* ctr = p.barrier + dir;
 
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
-      unsigned int fill = 0;
       // the recurrent product is needed for every step except the last one processed
       for (int step = 0; step + 1 < T; ++step) {
         grid_wait(ctr, (unsigned int)nC * (step + 1));   // dgh of this step is complete
         fence_proxy_async_all();
-        tma_gather(s, tm, (step & 1) * Bp, Bp, nchunks, p.ring, fill);
+        tma_gather(s, tm, (step & 1) * Bp, Bp, nchunks, p.ring, step, crank, csize);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     if (lane == 0) {
-      unsigned int fill = 0;
       for (int step = 0; step + 1 < T; ++step)
-        mma_consume<16>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, fill);
+        mma_consume<16>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, step, csize);
     }
   } else {
-    const bool active = tid < Bp;
-    float dh_rec[GRU_HC];   // dL/dh_t arriving through the recurrence (own 16 units)
-    float db_i[48], db_hn[GRU_HC];
+    const int row = (warp & 3) * 32 + lane;
+    const int uh = warp >> 2;
+    const int ju = j0 + uh * GRU_UPT;
+    const bool active = row < Bp;
+    float dh_rec[GRU_UPT];   // dL/dh_t arriving through the recurrence (own units)
+    float db_r[GRU_UPT], db_z[GRU_UPT], db_n[GRU_UPT], db_hn[GRU_UPT];
 #pragma unroll
-    for (int jj = 0; jj < GRU_HC; ++jj) { dh_rec[jj] = 0.f; db_hn[jj] = 0.f; }
-#pragma unroll
-    for (int r = 0; r < 48; ++r) db_i[r] = 0.f;
+    for (int jj = 0; jj < GRU_UPT; ++jj) {
+      dh_rec[jj] = 0.f; db_r[jj] = 0.f; db_z[jj] = 0.f; db_n[jj] = 0.f; db_hn[jj] = 0.f;
+    }
 
     for (int step = 0; step < T; ++step) {
       // forward order of dir 0 is t=0..T-1, so its backward order is T-1..0; dir 1 mirrored
@@ -427,107 +502,72 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       const int tp = dir == 0 ? t - 1 : t + 1;       // time index of h_{prev} in forward order
       const bool has_prev = dir == 0 ? (t > 0) : (t < T - 1);
       bf16* xb = p.xchg + ((long long)(dir * 2 + (step & 1)) * Bp) * K3;
-      const long long m = (long long)t * Bp + tid;
+      const long long m = (long long)t * Bp + row;
       // ---- saved activations of this step: independent of the recurrence, fetched first ----
-      float rr[GRU_HC], zz[GRU_HC], nn[GRU_HC], hn[GRU_HC], dh[GRU_HC], hp[GRU_HC];
+      float rr[GRU_UPT], zz[GRU_UPT], nn[GRU_UPT], hn[GRU_UPT], dh[GRU_UPT], hp[GRU_UPT];
       if (active) {
-        const float* go = p.gates + ((m * p.ndir + dir) * 4) * H + j0;
-        const float* dyo = p.dy + m * D + dir * H + j0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(go) + q);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(go + H) + q);
-          const float4 c = __ldg(reinterpret_cast<const float4*>(go + 2 * H) + q);
-          const float4 d = __ldg(reinterpret_cast<const float4*>(go + 3 * H) + q);
-          const float4 e = __ldg(reinterpret_cast<const float4*>(dyo) + q);
-          rr[q * 4] = a.x; rr[q * 4 + 1] = a.y; rr[q * 4 + 2] = a.z; rr[q * 4 + 3] = a.w;
-          zz[q * 4] = b.x; zz[q * 4 + 1] = b.y; zz[q * 4 + 2] = b.z; zz[q * 4 + 3] = b.w;
-          nn[q * 4] = c.x; nn[q * 4 + 1] = c.y; nn[q * 4 + 2] = c.z; nn[q * 4 + 3] = c.w;
-          hn[q * 4] = d.x; hn[q * 4 + 1] = d.y; hn[q * 4 + 2] = d.z; hn[q * 4 + 3] = d.w;
-          dh[q * 4] = e.x; dh[q * 4 + 1] = e.y; dh[q * 4 + 2] = e.z; dh[q * 4 + 3] = e.w;
-        }
+        const float* go = p.gates + ((m * p.ndir + dir) * 4) * H + ju;
+        ld8(go, rr);
+        ld8(go + H, zz);
+        ld8(go + 2 * H, nn);
+        ld8(go + 3 * H, hn);
+        ld8(p.dy + m * D + dir * H + ju, dh);
         if (has_prev) {
-          const float* yo = p.y + ((long long)tp * Bp + tid) * D + dir * H + j0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(yo) + q);
-            hp[q * 4] = a.x; hp[q * 4 + 1] = a.y; hp[q * 4 + 2] = a.z; hp[q * 4 + 3] = a.w;
-          }
+          ld8(p.y + ((long long)tp * Bp + row) * D + dir * H + ju, hp);
         } else {
 #pragma unroll
-          for (int jj = 0; jj < GRU_HC; ++jj) hp[jj] = 0.f;
+          for (int jj = 0; jj < GRU_UPT; ++jj) hp[jj] = 0.f;
         }
       }
       // ---- recurrent part of dL/dh_t: product issued in the previous step ----
       if (step > 0) {
         mbar_wait(s.accfull, (step - 1) & 1);
         tc_fence_after_sync();
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+        uint32_t v[8];
+        tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + uh * GRU_UPT, v);
         tmem_ld_wait();
         tc_fence_before_sync();
 #pragma unroll
-        for (int jj = 0; jj < GRU_HC; ++jj) dh_rec[jj] += __uint_as_float(v[jj]);
+        for (int jj = 0; jj < GRU_UPT; ++jj) dh_rec[jj] += __uint_as_float(v[jj]);
       }
-      float dr[GRU_HC], dz[GRU_HC], dn[GRU_HC], dnr[GRU_HC];
+      float dr[GRU_UPT], dz[GRU_UPT], dn[GRU_UPT], dnr[GRU_UPT];
       if (active) {
 #pragma unroll
-        for (int jj = 0; jj < GRU_HC; ++jj) {
+        for (int jj = 0; jj < GRU_UPT; ++jj) {
           const float g = dh[jj] + dh_rec[jj];
           dn[jj] = g * (1.f - zz[jj]) * (1.f - nn[jj] * nn[jj]);
           dz[jj] = g * (hp[jj] - nn[jj]) * zz[jj] * (1.f - zz[jj]);
           dr[jj] = dn[jj] * hn[jj] * rr[jj] * (1.f - rr[jj]);
           dnr[jj] = dn[jj] * rr[jj];
           dh_rec[jj] = g * zz[jj];      // direct path h_{t-1} -> h_t; the W_hh path is added next step
-          db_i[jj] += dr[jj];
-          db_i[16 + jj] += dz[jj];
-          db_i[32 + jj] += dn[jj];
+          db_r[jj] += dr[jj];
+          db_z[jj] += dz[jj];
+          db_n[jj] += dn[jj];
           db_hn[jj] += dnr[jj];
         }
         // critical path: the exchange rows [dr | dz | dn*r] every CTA gathers for the product
         if (step + 1 < T) {
-          uint4 pk[2];
-          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
-          bf16* x = xb + (long long)tid * K3 + j0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dr[2 * q], dr[2 * q + 1]);
-          reinterpret_cast<uint4*>(x)[0] = pk[0]; reinterpret_cast<uint4*>(x)[1] = pk[1];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dz[2 * q], dz[2 * q + 1]);
-          reinterpret_cast<uint4*>(x + H)[0] = pk[0]; reinterpret_cast<uint4*>(x + H)[1] = pk[1];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dnr[2 * q], dnr[2 * q + 1]);
-          reinterpret_cast<uint4*>(x + 2 * H)[0] = pk[0];
-          reinterpret_cast<uint4*>(x + 2 * H)[1] = pk[1];
+          bf16* x = xb + (long long)row * K3 + ju;
+          *reinterpret_cast<uint4*>(x) = pack8(dr);
+          *reinterpret_cast<uint4*>(x + H) = pack8(dz);
+          *reinterpret_cast<uint4*>(x + 2 * H) = pack8(dnr);
           fence_proxy_async_all();
         }
       }
       if (step + 1 < T) {
         epi_barrier();
-        if (tid == 0) {
-          __threadfence();
-          grid_arrive(ctr);
-        }
+        if (tid == 0) grid_arrive(ctr);
       }
       // ---- off the critical path: operands of the dX / dW GEMMs ----
       if (active) {
-        bf16* o = p.dgi + m * (p.ndir * K3) + dir * K3 + j0;
-        uint4 pk[2];
-        uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+        bf16* o = p.dgi + m * (p.ndir * K3) + dir * K3 + ju;
+        *reinterpret_cast<uint4*>(o) = pack8(dr);
+        *reinterpret_cast<uint4*>(o + H) = pack8(dz);
+        *reinterpret_cast<uint4*>(o + 2 * H) = pack8(dn);
+        bf16* gt = p.dgiT + ((long long)dir * K3 + ju) * M + m;
+        bf16* nt = p.dghnT + ((long long)dir * H + ju) * M + m;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dr[2 * q], dr[2 * q + 1]);
-        reinterpret_cast<uint4*>(o)[0] = pk[0]; reinterpret_cast<uint4*>(o)[1] = pk[1];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dz[2 * q], dz[2 * q + 1]);
-        reinterpret_cast<uint4*>(o + H)[0] = pk[0]; reinterpret_cast<uint4*>(o + H)[1] = pk[1];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) pw[q] = pack_bf16x2(dn[2 * q], dn[2 * q + 1]);
-        reinterpret_cast<uint4*>(o + 2 * H)[0] = pk[0];
-        reinterpret_cast<uint4*>(o + 2 * H)[1] = pk[1];
-        bf16* gt = p.dgiT + ((long long)dir * K3 + j0) * M + m;
-        bf16* nt = p.dghnT + ((long long)dir * H + j0) * M + m;
-#pragma unroll
-        for (int jj = 0; jj < GRU_HC; ++jj) {
+        for (int jj = 0; jj < GRU_UPT; ++jj) {
           gt[(long long)jj * M] = __float2bfloat16_rn(dr[jj]);
           gt[(long long)(H + jj) * M] = __float2bfloat16_rn(dz[jj]);
           gt[(long long)(2 * H + jj) * M] = __float2bfloat16_rn(dn[jj]);
@@ -537,18 +577,21 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
     }
     // ---- bias gradients: reduce the per-batch-row partial sums over the CTA ----
     epi_barrier();
-    float* red = s.scratch;  // 64 floats
+    float* red = s.scratch;  // [64]: r(16) z(16) n(16) hn(16)
     if (tid < 64) red[tid] = 0.f;
     epi_barrier();
 #pragma unroll
-    for (int r = 0; r < 48; ++r) {
-      const float v = warp_sum(active ? db_i[r] : 0.f);
-      if (lane == 0) atomicAdd(&red[r], v);
-    }
-#pragma unroll
-    for (int jj = 0; jj < GRU_HC; ++jj) {
-      const float v = warp_sum(active ? db_hn[jj] : 0.f);
-      if (lane == 0) atomicAdd(&red[48 + jj], v);
+    for (int jj = 0; jj < GRU_UPT; ++jj) {
+      const float a = warp_sum(active ? db_r[jj] : 0.f);
+      const float b = warp_sum(active ? db_z[jj] : 0.f);
+      const float c = warp_sum(active ? db_n[jj] : 0.f);
+      const float d = warp_sum(active ? db_hn[jj] : 0.f);
+      if (lane == 0) {
+        atomicAdd(&red[uh * GRU_UPT + jj], a);
+        atomicAdd(&red[16 + uh * GRU_UPT + jj], b);
+        atomicAdd(&red[32 + uh * GRU_UPT + jj], c);
+        atomicAdd(&red[48 + uh * GRU_UPT + jj], d);
+      }
     }
     epi_barrier();
     if (tid < 48) {
@@ -561,7 +604,8 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  cluster_sync_all();
+  if (warp == 8) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 32);
   }
@@ -570,39 +614,83 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
                       long long ld, int box_rows);
 
-// ring slots that fit next to the resident weights
+// ring = largest divisor of nchunks (<= GRU_MAX_RING) whose slots fit next to the resident weights
 static int gru_ring_slots(int wbytes, int Bp, int nchunks, size_t* smem_bytes) {
   const int stride = Bp * 128;
-  const int slack = (128 - Bp) * 128;
-  const int fixed = wbytes + slack + 1024 /*align*/ + (2 * GRU_MAX_RING + 2) * 8 + 256 /*scratch*/;
-  int ring = (227 * 1024 - fixed) / stride;
-  if (ring > GRU_MAX_RING) ring = GRU_MAX_RING;
-  if (ring > nchunks) ring = nchunks;
-  if (ring < 2) return -1;
+  const int fixed = wbytes + 1024 /*align*/ + (2 * GRU_MAX_RING + 2) * 8 + 256 /*scratch*/ + 64;
+  int fit = (227 * 1024 - fixed) / stride;
+  if (fit > GRU_MAX_RING) fit = GRU_MAX_RING;
+  int ring = -1;
+  for (int r = fit; r >= 1; --r)
+    if (nchunks % r == 0) { ring = r; break; }
+  if (ring < 1) return -1;
   *smem_bytes = (size_t)fixed + (size_t)ring * stride;
   return ring;
 }
 
-static int gru_launch(const void* kernel, int grid, size_t smem, void** args, cudaStream_t stream) {
+static int g_gru_cluster = 8;   // preferred cluster size (developer knob: sb_debug_gru_cluster)
+
+static int gru_cluster_size(int nC) {
+  int cs = g_gru_cluster;
+  while (cs > 1 && (nC % cs) != 0) cs >>= 1;
+  return cs < 1 ? 1 : cs;
+}
+
+static int gru_launch(const void* kernel, int grid, int cs, size_t smem, void** args,
+                      cudaStream_t stream) {
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return SB_ERR_CUDA;
-  if (cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(GRU_THREADS), args, smem, stream) !=
-      cudaSuccess)
-    return SB_ERR_CUDA;
-  return SB_OK;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GRU_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = cs;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  // all CTAs must be co-resident (grid barrier): shrink the cluster until the grid fits
+  if (cs > 1 &&
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 0) != cudaSuccess)
+    cudaGetLastError();
+  for (; cs >= 1; cs >>= 1) {
+    attrs[1].val.clusterDim.x = cs;
+    int nclusters = 0;
+    if (cs > 1) {
+      if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      if (nclusters * cs < grid) continue;
+    }
+    if (cudaLaunchKernelExC(&cfg, kernel, args) == cudaSuccess) return SB_OK;
+    cudaGetLastError();
+  }
+  return SB_ERR_CUDA;
 }
+
+static unsigned long long* g_gru_dbg = nullptr;
 
 }  // namespace sb
 
 using namespace sb;
 
-static unsigned long long* g_gru_dbg = nullptr;
-
-// developer hook: device buffer of >= 64*16 u64 that receives a per-step timeline of CTA 0 of the
-// next sb_gru_fwd launches (nullptr disables).  Not part of the drop-in surface.
+// developer hooks (not part of the drop-in surface)
 extern "C" int sb_debug_gru_timeline(void* dev_buffer) {
-  g_gru_dbg = reinterpret_cast<unsigned long long*>(dev_buffer);
+  sb::g_gru_dbg = reinterpret_cast<unsigned long long*>(dev_buffer);
+  return SB_OK;
+}
+extern "C" int sb_debug_gru_cluster(int cluster_size) {
+  if (cluster_size != 1 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8)
+    return SB_ERR_INVALID;
+  sb::g_gru_cluster = cluster_size;
   return SB_OK;
 }
 
@@ -627,7 +715,7 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
   p.dbg = g_gru_dbg;
   const int nchunks = (H + 63) / 64;
   size_t smem = 0;
-  p.ring = gru_ring_slots(nchunks * 48 * 128, Bp, nchunks, &smem);
+  p.ring = gru_ring_slots(std::max(nchunks * 48 * 128, 16384 - Bp * 128), Bp, nchunks, &smem);
   if (p.ring < 0) return SB_ERR_UNSUPPORTED;
   // one tensor map per direction over that direction's H columns of h (bf16 [T*Bp][ndir*H]):
   // columns past H are out of bounds and read as zero
@@ -641,7 +729,9 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
   if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * ndir, stream) != cudaSuccess)
     return SB_ERR_CUDA;
   void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&p};
-  return gru_launch((const void*)gru_fwd_kernel, ndir * (H / GRU_HC), smem, args, stream);
+  const int nC = H / GRU_HC;
+  return gru_launch((const void*)gru_fwd_kernel, ndir * nC, gru_cluster_size(nC), smem, args,
+                    stream);
 }
 
 extern "C" int sb_gru_bwd_workspace_size(int Bp, int H, int ndir, size_t* bytes) {
@@ -670,10 +760,11 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   p.dghnT = reinterpret_cast<bf16*>(dghnT_bf16);
   p.xchg = reinterpret_cast<bf16*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   p.dbih = dbih; p.dbhh = dbhh; p.barrier = barrier; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
+  p.dbg = g_gru_dbg;
   const int K3 = 3 * H;
   const int nchunks = (K3 + 63) / 64;
   size_t smem = 0;
-  p.ring = gru_ring_slots(nchunks * 16 * 128, Bp, nchunks, &smem);
+  p.ring = gru_ring_slots(std::max(nchunks * 16 * 128, 16384 - Bp * 128), Bp, nchunks, &smem);
   if (p.ring < 0) return SB_ERR_UNSUPPORTED;
   // per direction: the two parity buffers stacked as [2*Bp rows][3H cols]
   CUtensorMap tm[2];
@@ -685,5 +776,7 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * ndir, stream) != cudaSuccess)
     return SB_ERR_CUDA;
   void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&p};
-  return gru_launch((const void*)gru_bwd_kernel, ndir * (H / GRU_HC), smem, args, stream);
+  const int nC = H / GRU_HC;
+  return gru_launch((const void*)gru_bwd_kernel, ndir * nC, gru_cluster_size(nC), smem, args,
+                    stream);
 }

@@ -4,6 +4,9 @@ import numpy as np, torch
 sys.path.insert(0, ".")
 from speech_b200 import _lib, ops
 lib = _lib.load()
+if len(sys.argv) > 1:
+    lib.sb_debug_gru_cluster(int(sys.argv[1]))
+    print("cluster size preference:", sys.argv[1])
 torch.manual_seed(0)
 B, T, In, H = 64, 64, 2048, 1024
 rnn = torch.nn.GRU(In, H, 1, batch_first=True, bidirectional=True).cuda()
@@ -18,10 +21,12 @@ with torch.no_grad():
     lib.sb_debug_gru_timeline(None)
 d = dbg.cpu().numpy().reshape(64, 16)
 names = ["P:grid_wait done", "P:tma issued", "M:all mma committed", "E:accfull", "E:tmem loaded",
-         "E:xn stored", "E:proxy fence", "E:epi barrier", "E:threadfence", "E:arrived", "E:offpath done"]
+         "E:xn stored", "E:proxy fence", "E:epi barrier", None, "E:arrived", "E:offpath done"]
 for step in (10, 11, 12, 40):
     base = d[step - 1][9]   # previous step's arrival by this CTA
     print("step %d (ns since this CTA's previous arrive):" % step)
     for i, n in enumerate(names):
+        if n is None:
+            continue
         print("   %-22s %7d" % (n, d[step][i] - base))
 print("mean step period (ns):", (d[60][9] - d[10][9]) / 50.0)
