@@ -54,7 +54,7 @@ struct GruFwdParams {
   float* gates;        // [T*Bp][ndir][4][H] saved r,z,n,hn for backward ; may be null
   unsigned int* barrier;  // [ndir] zero-initialised counters
   unsigned long long* dbg;  // optional timeline (CTA 0): [step][16] globaltimer stamps, or null
-  int T, Bp, H, ndir, ring;
+  int T, Bp, H, ndir, ring, gc;   // ring: slots (groups of gc chunks) in shared memory
 };
 
 struct GruBwdParams {
@@ -70,7 +70,7 @@ struct GruBwdParams {
   float* dbhh;         // [ndir*3H] += sum_{t,b} dgh
   unsigned int* barrier;  // [ndir]
   unsigned long long* dbg;
-  int T, Bp, H, ndir, ring;
+  int T, Bp, H, ndir, ring, gc;
 };
 
 SB_DEVINL unsigned long long gtime() {
@@ -152,25 +152,31 @@ SB_DEVINL GruSmem carve(uint8_t* raw, int ring_bytes, int wbytes) {
   return s;
 }
 
-// The gathered operand of one step is `nchunks` [Bp x 64] boxes; chunk c uses slot c % ring and
-// nchunks % ring == 0, so every slot is used upr = nchunks/ring times per step and the mbarrier
-// phase of use (k, c) is k*upr + c/ring for both the full and the empty barrier of the slot.
+// The gathered operand of one step is `nchunks` [Bp x 64] boxes, handled in groups of `gc` chunks
+// that share ONE full/empty mbarrier pair (an mbarrier wait costs ~100 ns even when it is already
+// complete, so per-chunk barriers were 3 us of a 10 us step).  Group g uses ring slot g % ring and
+// ngroups % ring == 0, so every slot is used upr = ngroups/ring times per step and the mbarrier
+// phase of use (k, g) is k*upr + g/ring for both barriers of the slot.
 //
 // TMA producer (one thread per CTA).  Every CTA arms its own full barriers; chunk c is fetched
 // by the CTA whose cluster rank is c % CS and multicast to the whole cluster.
 SB_DEVINL void tma_gather(const GruSmem& s, const CUtensorMap* tm, int row0, int Bp, int nchunks,
-                          int ring, int k, uint32_t rank, uint32_t cs) {
+                          int ring, int gc, int k, uint32_t rank, uint32_t cs) {
   const int stride = Bp * 128;
-  const int upr = nchunks / ring;
+  const int ngroups = nchunks / gc;
+  const int upr = ngroups / ring;
   const uint16_t mask = (uint16_t)((1u << cs) - 1u);
-  for (int c = 0; c < nchunks; ++c) {
-    const int slot = c % ring;
-    const unsigned int P = (unsigned int)(k * upr + c / ring);
-    if (c >= ring) mbar_wait(&s.empty[slot], (P - 1u) & 1u);   // released by ALL CTAs of the cluster
-    mbar_expect_tx(&s.full[slot], (uint32_t)stride);
-    if ((uint32_t)c % cs == rank) {
-      if (cs > 1) tma_load_2d_mc(s.ring + slot * stride, tm, &s.full[slot], c * 64, row0, mask);
-      else tma_load_2d(s.ring + slot * stride, tm, &s.full[slot], c * 64, row0);
+  for (int g = 0; g < ngroups; ++g) {
+    const int slot = g % ring;
+    const unsigned int P = (unsigned int)(k * upr + g / ring);
+    if (g >= ring) mbar_wait(&s.empty[slot], (P - 1u) & 1u);   // released by ALL CTAs of the cluster
+    mbar_expect_tx(&s.full[slot], (uint32_t)(stride * gc));
+    for (int i = 0; i < gc; ++i) {
+      const int c = g * gc + i;
+      if ((uint32_t)c % cs != rank) continue;
+      uint8_t* dst = s.ring + (slot * gc + i) * stride;
+      if (cs > 1) tma_load_2d_mc(dst, tm, &s.full[slot], c * 64, row0, mask);
+      else tma_load_2d(dst, tm, &s.full[slot], c * 64, row0);
     }
   }
 }
@@ -178,23 +184,27 @@ SB_DEVINL void tma_gather(const GruSmem& s, const CUtensorMap* tm, int row0, int
 // MMA thread: consume the step's chunks against the resident weight chunks.
 template <int N>
 SB_DEVINL void mma_consume(const GruSmem& s, uint32_t tmem_d, int nchunks, int wchunk_bytes,
-                           int Bp, int ring, int k, uint32_t cs) {
+                           int Bp, int ring, int gc, int k, uint32_t cs) {
   constexpr uint32_t idesc = umma_idesc_bf16_f32(128, N);
   const int stride = Bp * 128;
-  const int upr = nchunks / ring;
+  const int ngroups = nchunks / gc;
+  const int upr = ngroups / ring;
   const uint16_t mask = (uint16_t)((1u << cs) - 1u);
-  for (int c = 0; c < nchunks; ++c) {
-    const int slot = c % ring;
-    const unsigned int P = (unsigned int)(k * upr + c / ring);
+  for (int g = 0; g < ngroups; ++g) {
+    const int slot = g % ring;
+    const unsigned int P = (unsigned int)(k * upr + g / ring);
     mbar_wait(&s.full[slot], P & 1u);
     tc_fence_after_sync();
-    const uint64_t da = umma_desc_sw128_kmajor(smem_u32(s.ring + slot * stride));
-    const uint64_t db = umma_desc_sw128_kmajor(smem_u32(s.wtile + c * wchunk_bytes));
+    for (int i = 0; i < gc; ++i) {
+      const int c = g * gc + i;
+      const uint64_t da = umma_desc_sw128_kmajor(smem_u32(s.ring + (slot * gc + i) * stride));
+      const uint64_t db = umma_desc_sw128_kmajor(smem_u32(s.wtile + c * wchunk_bytes));
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-      umma_bf16_ss(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                   (c > 0 || kk > 0) ? 1u : 0u);
-    if (ring < nchunks) {
+      for (int kk = 0; kk < 4; ++kk)
+        umma_bf16_ss(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                     (c > 0 || kk > 0) ? 1u : 0u);
+    }
+    if (ring < ngroups) {
       if (cs > 1) umma_commit_mc(&s.empty[slot], mask);
       else umma_commit(&s.empty[slot]);
     }
@@ -246,7 +256,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   const int j0 = (blockIdx.x % nC) * GRU_HC;
   const int nchunks = (H + 63) / 64;
   constexpr int WCHUNK = 48 * 128;  // 48 rows x 64 bf16
-  const int ring_bytes = p.ring * Bp * 128;
+  const int ring_bytes = p.ring * p.gc * Bp * 128;
   // the 128-row A read of the last ring slot overruns by (16 KB - stride) into this region
   const int wbytes = max(nchunks * WCHUNK, 16384 - Bp * 128);
   const GruSmem s = carve(smem_raw, ring_bytes, wbytes);
@@ -303,8 +313,8 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         const int tp = dir == 0 ? t - 1 : t + 1;
         grid_wait(ctr, (unsigned int)nC * step);   // every CTA of this direction published h_{tp}
         GRU_STAMP(0);
-        fence_proxy_async_all();                    // generic-proxy writes -> async-proxy (TMA) reads
-        tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, step - 1, crank, csize);
+        // (the writers ran fence.proxy.async before their release; no reader-side proxy fence)
+        tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, p.gc, step - 1, crank, csize);
         GRU_STAMP(1);
       }
     }
@@ -312,7 +322,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       for (int step = 1; step < T; ++step) {
-        mma_consume<48>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, step - 1, csize);
+        mma_consume<48>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, p.gc, step - 1, csize);
         GRU_STAMP(2);
       }
     }
@@ -427,7 +437,7 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   const int K3 = 3 * H;
   const int nchunks = (K3 + 63) / 64;
   constexpr int WCHUNK = 16 * 128;  // 16 rows x 64 bf16
-  const int ring_bytes = p.ring * Bp * 128;
+  const int ring_bytes = p.ring * p.gc * Bp * 128;
   const int wbytes = max(nchunks * WCHUNK, 16384 - Bp * 128);
   const GruSmem s = carve(smem_raw, ring_bytes, wbytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -475,14 +485,17 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       // the recurrent product is needed for every step except the last one processed
       for (int step = 0; step + 1 < T; ++step) {
         grid_wait(ctr, (unsigned int)nC * (step + 1));   // dgh of this step is complete
-        fence_proxy_async_all();
-        tma_gather(s, tm, (step & 1) * Bp, Bp, nchunks, p.ring, step, crank, csize);
+        GRU_STAMP(0);
+        tma_gather(s, tm, (step & 1) * Bp, Bp, nchunks, p.ring, p.gc, step, crank, csize);
+        GRU_STAMP(1);
       }
     }
   } else if (warp == 8) {
     if (lane == 0) {
-      for (int step = 0; step + 1 < T; ++step)
-        mma_consume<16>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, step, csize);
+      for (int step = 0; step + 1 < T; ++step) {
+        mma_consume<16>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, p.gc, step, csize);
+        GRU_STAMP(2);
+      }
     }
   } else {
     const int row = (warp & 3) * 32 + lane;
@@ -522,11 +535,13 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       // ---- recurrent part of dL/dh_t: product issued in the previous step ----
       if (step > 0) {
         mbar_wait(s.accfull, (step - 1) & 1);
+        if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
         uint32_t v[8];
         tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + uh * GRU_UPT, v);
         tmem_ld_wait();
         tc_fence_before_sync();
+        if (tid == 0) GRU_STAMP(4);
 #pragma unroll
         for (int jj = 0; jj < GRU_UPT; ++jj) dh_rec[jj] += __uint_as_float(v[jj]);
       }
@@ -551,12 +566,18 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
           *reinterpret_cast<uint4*>(x) = pack8(dr);
           *reinterpret_cast<uint4*>(x + H) = pack8(dz);
           *reinterpret_cast<uint4*>(x + 2 * H) = pack8(dnr);
+          if (tid == 0) GRU_STAMP(5);
           fence_proxy_async_all();
+          if (tid == 0) GRU_STAMP(6);
         }
       }
       if (step + 1 < T) {
         epi_barrier();
-        if (tid == 0) grid_arrive(ctr);
+        if (tid == 0) {
+          GRU_STAMP(7);
+          grid_arrive(ctr);
+          GRU_STAMP(9);
+        }
       }
       // ---- off the critical path: operands of the dX / dW GEMMs ----
       if (active) {
@@ -574,6 +595,7 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
           nt[(long long)jj * M] = __float2bfloat16_rn(dnr[jj]);
         }
       }
+      if (tid == 0) GRU_STAMP(10);
     }
     // ---- bias gradients: reduce the per-batch-row partial sums over the CTA ----
     epi_barrier();
@@ -614,21 +636,37 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
                       long long ld, int box_rows);
 
-// ring = largest divisor of nchunks (<= GRU_MAX_RING) whose slots fit next to the resident weights
-static int gru_ring_slots(int wbytes, int Bp, int nchunks, size_t* smem_bytes) {
-  const int stride = Bp * 128;
+// chunks are grouped gc per mbarrier pair (gc = largest of 4,3,2,1 dividing nchunks); ring = the
+// largest divisor of ngroups (<= GRU_MAX_RING) whose slots fit next to the resident weights
+static int gru_ring_slots(int wbytes, int Bp, int nchunks, int* gc_out, size_t* smem_bytes) {
+  int gc = 1;
+  for (int g = 4; g >= 1; --g)
+    if (nchunks % g == 0) { gc = g; break; }
+  const int ngroups = nchunks / gc;
+  const int slot = gc * Bp * 128;
   const int fixed = wbytes + 1024 /*align*/ + (2 * GRU_MAX_RING + 2) * 8 + 256 /*scratch*/ + 64;
-  int fit = (227 * 1024 - fixed) / stride;
+  int fit = (227 * 1024 - fixed) / slot;
   if (fit > GRU_MAX_RING) fit = GRU_MAX_RING;
   int ring = -1;
   for (int r = fit; r >= 1; --r)
-    if (nchunks % r == 0) { ring = r; break; }
-  if (ring < 1) return -1;
-  *smem_bytes = (size_t)fixed + (size_t)ring * stride;
+    if (ngroups % r == 0) { ring = r; break; }
+  if (ring < 1) {
+    if (gc == 1) return -1;
+    // fall back to single-chunk groups
+    gc = 1;
+    fit = (227 * 1024 - fixed) / (Bp * 128);
+    if (fit > GRU_MAX_RING) fit = GRU_MAX_RING;
+    for (int r = fit; r >= 1; --r)
+      if (nchunks % r == 0) { ring = r; break; }
+    if (ring < 1) return -1;
+  }
+  *gc_out = gc;
+  *smem_bytes = (size_t)fixed + (size_t)ring * gc * Bp * 128;
   return ring;
 }
 
 static int g_gru_cluster = 8;   // preferred cluster size (developer knob: sb_debug_gru_cluster)
+static int g_gru_last_cluster = 0;
 
 static int gru_cluster_size(int nC) {
   int cs = g_gru_cluster;
@@ -670,7 +708,10 @@ static int gru_launch(const void* kernel, int grid, int cs, size_t smem, void** 
       }
       if (nclusters * cs < grid) continue;
     }
-    if (cudaLaunchKernelExC(&cfg, kernel, args) == cudaSuccess) return SB_OK;
+    if (cudaLaunchKernelExC(&cfg, kernel, args) == cudaSuccess) {
+      g_gru_last_cluster = cs;
+      return SB_OK;
+    }
     cudaGetLastError();
   }
   return SB_ERR_CUDA;
@@ -688,10 +729,12 @@ extern "C" int sb_debug_gru_timeline(void* dev_buffer) {
   return SB_OK;
 }
 extern "C" int sb_debug_gru_cluster(int cluster_size) {
+  // cluster_size 0 queries: returns the cluster size the last GRU launch actually used
+  if (cluster_size == 0) return sb::g_gru_last_cluster;
   if (cluster_size != 1 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8)
-    return SB_ERR_INVALID;
+    return -1;
   sb::g_gru_cluster = cluster_size;
-  return SB_OK;
+  return sb::g_gru_last_cluster;
 }
 
 static int gru_check(int T, int Bp, int H, int ndir) {
@@ -715,7 +758,7 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
   p.dbg = g_gru_dbg;
   const int nchunks = (H + 63) / 64;
   size_t smem = 0;
-  p.ring = gru_ring_slots(std::max(nchunks * 48 * 128, 16384 - Bp * 128), Bp, nchunks, &smem);
+  p.ring = gru_ring_slots(std::max(nchunks * 48 * 128, 16384 - Bp * 128), Bp, nchunks, &p.gc, &smem);
   if (p.ring < 0) return SB_ERR_UNSUPPORTED;
   // one tensor map per direction over that direction's H columns of h (bf16 [T*Bp][ndir*H]):
   // columns past H are out of bounds and read as zero
@@ -764,7 +807,7 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   const int K3 = 3 * H;
   const int nchunks = (K3 + 63) / 64;
   size_t smem = 0;
-  p.ring = gru_ring_slots(std::max(nchunks * 16 * 128, 16384 - Bp * 128), Bp, nchunks, &smem);
+  p.ring = gru_ring_slots(std::max(nchunks * 16 * 128, 16384 - Bp * 128), Bp, nchunks, &p.gc, &smem);
   if (p.ring < 0) return SB_ERR_UNSUPPORTED;
   // per direction: the two parity buffers stacked as [2*Bp rows][3H cols]
   CUtensorMap tm[2];

@@ -12,21 +12,35 @@ B, T, In, H = 64, 64, 2048, 1024
 rnn = torch.nn.GRU(In, H, 1, batch_first=True, bidirectional=True).cuda()
 x = torch.randn(B, T, In, device="cuda")
 dbg = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")
-with torch.no_grad():
-    ops.gru_stack(x, rnn)
+MODE = sys.argv[2] if len(sys.argv) > 2 else "fwd"
+if MODE == "fwd":
+    with torch.no_grad():
+        ops.gru_stack(x, rnn)
+        torch.cuda.synchronize()
+        lib.sb_debug_gru_timeline(dbg.data_ptr())
+        ops.gru_stack(x, rnn)
+        torch.cuda.synchronize()
+        lib.sb_debug_gru_timeline(None)
+else:
+    xr = x.clone().requires_grad_(True)
+    y = ops.gru_stack(xr, rnn)
+    y.sum().backward()
+    y = ops.gru_stack(xr, rnn)
     torch.cuda.synchronize()
     lib.sb_debug_gru_timeline(dbg.data_ptr())
-    ops.gru_stack(x, rnn)
+    y.sum().backward()
     torch.cuda.synchronize()
     lib.sb_debug_gru_timeline(None)
+print("mode:", MODE)
 d = dbg.cpu().numpy().reshape(64, 16)
 names = ["P:grid_wait done", "P:tma issued", "M:all mma committed", "E:accfull", "E:tmem loaded",
          "E:xn stored", "E:proxy fence", "E:epi barrier", None, "E:arrived", "E:offpath done"]
-for step in (10, 11, 12, 40):
+for step in (11, 40):
     base = d[step - 1][9]   # previous step's arrival by this CTA
     print("step %d (ns since this CTA's previous arrive):" % step)
     for i, n in enumerate(names):
         if n is None:
             continue
         print("   %-22s %7d" % (n, d[step][i] - base))
+print("cluster size used:", lib.sb_debug_gru_cluster(0))
 print("mean step period (ns):", (d[60][9] - d[10][9]) / 50.0)
