@@ -153,13 +153,15 @@ def pick_threads():
         ncpu = min(ncpu, len(os.sched_getaffinity(0)))
     except Exception:
         pass
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    cands = sorted({c for c in (8, 16, 32, 64) if c <= ncpu} or {ncpu})
     best, best_t = cands[0], None
     for c in cands:
         t = sum(cpu_step_time(4, 1, 1, c, layers=1))
         _log("cpu probe: %d threads -> %.2f s" % (c, t))
         if best_t is None or t < best_t:
             best, best_t = c, t
+        elif t > 1.5 * best_t:
+            break      # oversubscription only gets worse (128 threads measured 400x slower)
     return best
 
 
@@ -261,6 +263,18 @@ def run_ours(args):
             ms = t.item()
         return ms
 
+    if args.profile:
+        for _ in range(max(1, args.warmup)):
+            step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(args.steps):
+            step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile_run": True, "steps": args.steps}))
+        return
+
     # ---- device-resident value, with per-kernel CUDA events and clock sampling ----
     _log("model built; warm-up")
     for i in range(args.warmup):
@@ -351,8 +365,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run (ncu): 1 warm-up + --steps device steps, nothing else; "
+                         "prints no benchmark value")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
+    if args.warmup < 3 and args.impl == "ours" and not args.profile:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
