@@ -120,6 +120,28 @@ int sb_ctc_prefix_beam(const float* logp, const int* lens, int B, int T, int S, 
                        int blank, int* out_labels, int* out_lens, double* out_scores,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Beam expand/prune of Seq2Seq.beam_search (speech/models/seq2seq.py:200-212): indices and values
+ * of the k best of n float64 scores, ordered by (score descending, index ascending) - the order of
+ * the reference's stable sort over (beam, vocab) candidates. */
+int sb_beam_topk(const double* scores, int n, int k, int* out_idx, double* out_val, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * RNN-Transducer loss + gradient w.r.t. the log-probabilities.
+ * Replaces: transducer.functions.transducer.TransducerLoss()(log_probs, labels, x_lens, y_lens)
+ *           (libs/transducer, un-vendored, Makefile:10-12; call site
+ *            speech/models/transducer_model.py:46-52).
+ *   log_probs (B, T, U1, V) float32 log-softmax over V (U1 = max label length + 1)
+ *   grads     same shape, out (zero-filled here, then the 2 non-zero entries per cell); may be NULL
+ *   labels    flat int32; label_offsets exclusive prefix sum; label_lens (B); act_lens (B)
+ *   blank     blank class index (reference: V-1, transducer_model.py:28)
+ *   costs     (B) float32 out
+ * ------------------------------------------------------------------------------------- */
+int sb_rnnt_workspace_size(int B, int T, int U1, size_t* bytes);
+int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
+                    const int* label_offsets, const int* label_lens, const int* act_lens, int B,
+                    int T, int U1, int V, int blank, float* costs, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* Developer hook (not part of the drop-in surface): device buffer of >= 64*16 uint64 receiving a
  * globaltimer timeline of CTA 0 for the next sb_gru_fwd launches; NULL disables. */
 int sb_debug_gru_timeline(void* dev_buffer);

@@ -316,3 +316,63 @@ extern "C" int sb_ctc_prefix_beam(const float* logp, const int* lens, int B, int
   ctc_prefix_beam_kernel<<<B, DEC_THREADS, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
+
+// ------------------------------------------------------------------------------------------------
+// sb_beam_topk: the expand/prune step of Seq2Seq.beam_search (speech/models/seq2seq.py:200-212):
+// the reference sorts ALL beam x vocab candidates with a stable descending sort and keeps a
+// prefix, so ties keep (beam index, vocab index) order = ascending flat index.  One CTA selects
+// the top k of n float64 scores by k rounds of block arg-max on (score desc, index asc).
+// ------------------------------------------------------------------------------------------------
+namespace sb {
+__global__ void __launch_bounds__(256) beam_topk_kernel(const double* __restrict__ scores, int n,
+                                                        int k, int* out_idx, double* out_val) {
+  extern __shared__ unsigned char topk_smem[];
+  double* sc = reinterpret_cast<double*>(topk_smem);
+  __shared__ double rs[8];
+  __shared__ int ri[8];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += 256) sc[i] = scores[i];
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    double bs = 0.0;
+    int bi = -1;
+    for (int i = tid; i < n; i += 256) {
+      const double v = sc[i];
+      if (isnan(v)) continue;                      // NaN marks "already taken"
+      if (bi < 0 || v > bs) { bs = v; bi = i; }    // ascending i: first index wins ties
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
+    }
+    if ((tid & 31) == 0) { rs[tid >> 5] = bs; ri[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (ri[w] >= 0 && (bi < 0 || rs[w] > bs || (rs[w] == bs && ri[w] < bi))) {
+          bs = rs[w]; bi = ri[w];
+        }
+      out_idx[r] = bi;
+      out_val[r] = bs;
+      if (bi >= 0) sc[bi] = nan("");
+    }
+    __syncthreads();
+  }
+}
+}  // namespace sb
+
+extern "C" int sb_beam_topk(const double* scores, int n, int k, int* out_idx, double* out_val,
+                            void* stream_) {
+  if (!scores || !out_idx || !out_val || n <= 0 || k <= 0 || k > n) return SB_ERR_INVALID;
+  const size_t smem = (size_t)n * sizeof(double);
+  if (smem > 200 * 1024) return SB_ERR_UNSUPPORTED;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (smem > 40 * 1024 &&
+      cudaFuncSetAttribute(sb::beam_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem) != cudaSuccess)
+    return SB_ERR_CUDA;
+  sb::beam_topk_kernel<<<1, 256, smem, stream>>>(scores, n, k, out_idx, out_val);
+  return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}

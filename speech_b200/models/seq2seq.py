@@ -1,0 +1,213 @@
+"""Attention sequence-to-sequence model - host-side mirror of speech/models/seq2seq.py:14-248
+(Seq2Seq) and :331-360 (NNAttention, the only attention module the reference instantiates).
+
+The encoder runs on the sm_100a kernels (ops.conv_stack / ops.gru_stack).  The per-token decoder
+(embedding + GRUCell + NNAttention + fc, seq2seq.py:92-108,114-137) keeps the reference's module
+structure and state_dict names; in round 1 its small per-step ops are torch calls, the beam
+expand/prune runs on the device (ops.beam_topk) with the reference's tie order.
+Reference quirks kept on purpose: end-padding is part of the loss (:58-63), `hx` starts at zero,
+scheduled sampling draws from Python's `random` (:94), `beam_search` handles one utterance (:197)
+and needs the py3 fix list(filter(...)) (:211) - applied here.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import model
+
+
+class Seq2Seq(model.Model):
+
+    def __init__(self, freq_dim, vocab_size, config):
+        super().__init__(freq_dim, config)
+        dec = config["decoder"]
+        rnn_dim = self.encoder_dim
+        self.embedding = nn.Embedding(vocab_size, dec["embedding_dim"])
+        self.dec_rnn = nn.GRUCell(input_size=dec["embedding_dim"], hidden_size=rnn_dim)
+        self.attend = NNAttention(rnn_dim, log_t=dec.get("log_t", False))
+        self.sample_prob = dec.get("sample_prob", 0)
+        self.scheduled_sampling = (self.sample_prob != 0)
+        # the start-of-sequence token is never predicted: vocab_size - 1 classes (:32-34)
+        self.fc = model.LinearND(rnn_dim, vocab_size - 1)
+
+    def set_eval(self):
+        self.eval()
+        self.volatile = True
+        self.scheduled_sampling = False
+
+    def set_train(self):
+        self.train()
+        self.volatile = False
+        self.scheduled_sampling = (self.sample_prob != 0)
+
+    def _to_dev(self, x, y):
+        if self.is_cuda:
+            x = x.cuda(non_blocking=True)
+            y = y.cuda(non_blocking=True)
+        return x, y
+
+    def loss(self, batch):
+        x, y = self.collate(*batch)
+        x, y = self._to_dev(x, y)
+        with self._grad_ctx():
+            out, _ = self.forward_impl(x, y)
+            bsz, _, out_dim = out.shape
+            ce = nn.functional.cross_entropy(out.reshape(-1, out_dim), y[:, 1:].reshape(-1),
+                                             reduction="sum")
+            # (1,)-shaped so that train.py:33 `loss.data[0]` works on current torch
+            return (ce / bsz).reshape(1)
+
+    def forward_impl(self, x, y):
+        x = self.encode(x)
+        return self.decode(x, y)
+
+    def forward(self, batch):
+        x, y = self.collate(*batch)
+        x, y = self._to_dev(x, y)
+        with self._grad_ctx():
+            return self.forward_impl(x, y)[0]
+
+    def decode(self, x, y):
+        """Teacher-forced decode (:78-112).  x (B, T', H); y (B, U) -> logits (B, U-1, V-1)."""
+        inputs = self.embedding(y[:, :-1])
+        out, aligns = [], []
+        hx = torch.zeros((x.shape[0], x.shape[2]), device=x.device, dtype=x.dtype)
+        ax = sx = None
+        for t in range(y.shape[1] - 1):
+            if out and self.scheduled_sampling and random.random() < self.sample_prob:
+                ix = self.embedding(torch.max(out[-1], dim=2)[1])
+            else:
+                ix = inputs[:, t:t + 1, :]
+            if sx is not None:
+                ix = ix + sx
+            hx = self.dec_rnn(ix.squeeze(dim=1), hx)
+            ox = hx.unsqueeze(dim=1)
+            sx, ax = self.attend(x, ox, ax)
+            aligns.append(ax)
+            out.append(self.fc(ox + sx))
+        return torch.cat(out, dim=1), torch.stack(aligns, dim=1)
+
+    def decode_step(self, x, y, state=None, softmax=False):
+        """One decoder step (:114-137).  y (B, 1) -> (logits (B, V-1), (hx, ax, sx))."""
+        if state is None:
+            hx = torch.zeros((x.shape[0], x.shape[2]), device=x.device, dtype=x.dtype)
+            ax = sx = None
+        else:
+            hx, ax, sx = state
+        ix = self.embedding(y)
+        if sx is not None:
+            ix = ix + sx
+        hx = self.dec_rnn(ix.squeeze(dim=1), hx)
+        ox = hx.unsqueeze(dim=1)
+        sx, ax = self.attend(x, ox, ax=ax)
+        out = self.fc((ox + sx).squeeze(dim=1))
+        if softmax:
+            out = nn.functional.log_softmax(out, dim=1)
+        return out, (hx, ax, sx)
+
+    def predict(self, batch):
+        probs = self(batch)
+        return [seq.tolist() for seq in torch.max(probs, dim=2)[1].cpu().numpy()]
+
+    def infer_decode(self, x, y, end_tok, max_len):
+        probs, argmaxs, state = [], [y], None
+        for _ in range(max_len):
+            out, state = self.decode_step(x, y, state=state)
+            probs.append(out)
+            y = torch.max(out, dim=1)[1].unsqueeze(dim=1)
+            argmaxs.append(y)
+            if bool((y == end_tok).all()):
+                break
+        return torch.cat(probs), torch.cat(argmaxs, dim=1)
+
+    def infer(self, batch, max_len=200):
+        """Greedy decode (:162-178): the start token, then arg-max until every row emitted end."""
+        x, y = self.collate(*batch)
+        end_tok = int(y[0, -1])
+        x, y = self._to_dev(x, y)
+        with torch.no_grad():
+            x = self.encode(x)
+            _, argmaxs = self.infer_decode(x, y[:, 0:1], end_tok, max_len)
+        return [seq.tolist() for seq in argmaxs.cpu().numpy()]
+
+    def beam_search(self, batch, beam_size=10, max_len=200):
+        """Beam search for ONE utterance (:180-227).  Hypothesis scores are sums of
+        log-softmax; pruning is the reference's stable descending sort, i.e. ties keep
+        (beam index, then vocabulary index) order - reproduced on the device by ops.beam_topk."""
+        from .. import ops
+        x, y = self.collate(*batch)
+        start_tok, end_tok = int(y[0, 0]), int(y[0, -1])
+        x, y = self._to_dev(x, y)
+        with torch.no_grad():
+            x = self.encode(x)
+            y = y[:, 0:1].clone()
+            beam = [((start_tok,), 0.0, None)]
+            complete = []
+            for _ in range(max_len):
+                rows, scores = [], []
+                states = []
+                for hyp, score, state in beam:
+                    y[0] = hyp[-1]
+                    out, state = self.decode_step(x, y, state=state, softmax=True)
+                    rows.append(out.reshape(-1).double() + score)
+                    states.append(state)
+                cand = torch.stack(rows)                     # (beam, V-1) float64 like the ref
+                nv = cand.shape[1]
+                k = min(cand.numel(), 2 * beam_size)         # enough to fill the live beam
+                idx, val = ops.beam_topk(cand, k)
+                new_beam = [(beam[i // nv][0] + (i % nv,), v, states[i // nv])
+                            for i, v in zip(idx, val)]
+                for c in new_beam[:beam_size]:
+                    if c[0][-1] == end_tok:
+                        complete.append(c)
+                beam = [c for c in new_beam if c[0][-1] != end_tok][:beam_size]
+                if len(beam) == 0:
+                    break
+                if sum(c[1] > beam[0][1] for c in complete) >= beam_size:
+                    break
+            complete = sorted(complete, key=lambda c: c[1], reverse=True)
+            if len(complete) == 0:
+                complete = beam
+            return [complete[0][0]]
+
+    def collate(self, inputs, labels):
+        x = model.zero_pad_concat_pinned(inputs) if self.is_cuda else \
+            torch.from_numpy(model.zero_pad_concat(inputs))
+        return x, torch.from_numpy(end_pad_concat(labels))
+
+
+def end_pad_concat(labels):
+    """(B, max U) int64, padded with the first example's last token (the end token) (:239-248)."""
+    end_tok = labels[0][-1]
+    max_len = max(len(l) for l in labels)
+    cat = np.full((len(labels), max_len), fill_value=end_tok, dtype=np.int64)
+    for e, l in enumerate(labels):
+        cat[e, :len(l)] = l
+    return cat
+
+
+class NNAttention(nn.Module):
+    """Additive attention with a location feature (seq2seq.py:331-360): score_t =
+    w . relu(eh_t + dhx + conv1d(prev alignment)_t) + b, optional log(T) sharpening, softmax over
+    time, context = sum_t a_t eh_t."""
+
+    def __init__(self, n_channels, kernel_size=15, log_t=False):
+        super().__init__()
+        assert kernel_size % 2 == 1, "Kernel size should be odd for 'same' conv."
+        self.conv = nn.Conv1d(1, n_channels, kernel_size, padding=(kernel_size - 1) // 2)
+        self.nn = nn.Sequential(nn.ReLU(), model.LinearND(n_channels, 1))
+        self.log_t = log_t
+
+    def forward(self, eh, dhx, ax=None):
+        pax = eh + dhx
+        if ax is not None:
+            pax = pax + self.conv(ax.unsqueeze(dim=1)).transpose(1, 2)
+        pax = self.nn(pax).squeeze(dim=2)
+        if self.log_t:
+            pax = math.log(pax.shape[1]) * pax
+        ax = nn.functional.softmax(pax, dim=1)
+        sx = torch.sum(eh * ax.unsqueeze(2), dim=1, keepdim=True)
+        return sx, ax

@@ -256,3 +256,18 @@ def conv_stack(x, conv, training):
     y = conv(x.unsqueeze(1))
     b, c, t, f = y.shape
     return y.transpose(1, 2).reshape(b, t, c * f)
+
+
+def beam_topk(scores, k):
+    """Top-k of a float64 CUDA score matrix in the reference's stable-sort order (score
+    descending, flat index ascending).  Returns (list of flat indices, list of scores)."""
+    _lib.require_cuda(scores, "scores")
+    lib = _lib.load()
+    sc = scores.detach().double().contiguous().reshape(-1)
+    n = sc.numel()
+    idx = torch.empty(k, dtype=torch.int32, device=sc.device)
+    val = torch.empty(k, dtype=torch.float64, device=sc.device)
+    sp = _lib.stream_ptr()
+    _launch("beam_topk", 0.0,
+            lambda: lib.sb_beam_topk(sc.data_ptr(), n, k, idx.data_ptr(), val.data_ptr(), sp))
+    return idx.cpu().tolist(), val.cpu().tolist()

@@ -121,3 +121,22 @@ def test_c_oracle_matches_numpy_oracle():
     c2, g2 = ob.ctc(acts, flat, llen, alen, V - 1)
     np.testing.assert_allclose(c2, c1, rtol=1e-12)
     assert np.abs(g2 - g1).max() < 1e-6
+
+
+def test_rnnt_oracle_matches_brute_force_enumeration():
+    from oracle import rnnt_ref
+    rng = np.random.RandomState(0)
+    for T, U, V in [(1, 0, 3), (3, 2, 4), (4, 3, 3), (5, 1, 5)]:
+        x = rng.randn(T, U + 1, V)
+        lp = x - np.log(np.exp(x).sum(-1, keepdims=True))
+        labels = [int(v) for v in rng.randint(0, V - 1, size=U)]
+        c, g = rnnt_ref.rnnt_single(lp, labels, V - 1)
+        assert abs(c - rnnt_ref.brute_force_nll(lp, labels, V - 1)) < 1e-10
+        # gradient vs central finite differences of the brute-force definition
+        eps = 1e-6
+        for idx in [(0, 0, V - 1), (T - 1, U, V - 1)] + ([(0, 0, labels[0])] if U else []):
+            lp2 = lp.copy(); lp2[idx] += eps
+            lp3 = lp.copy(); lp3[idx] -= eps
+            fd = (rnnt_ref.brute_force_nll(lp2, labels, V - 1) -
+                  rnnt_ref.brute_force_nll(lp3, labels, V - 1)) / (2 * eps)
+            assert abs(fd - g[idx]) < 1e-6
