@@ -81,9 +81,8 @@ int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, 
  *   xnT    [ndir*H][(T+2)*Bp] bf16 h_t transposed, column (t+1)*Bp+b; columns of t=-1 and t=T
  *          must be zero on entry (out; may be NULL)
  *   gates  [T*Bp][ndir][4][H] f32 saved r,z,n,(W_hn h + b_hn) for backward (out; may be NULL)
- *   barrier [4] u32 scratch for the per-(direction, stream) grid barriers
- * Constraints: H % 16 == 0; Bp % 8 == 0 and Bp <= 32, or Bp % 16 == 0 and Bp <= 64;
- *              ndir*H/16 <= number of SMs.
+ *   barrier [ndir] u32 scratch for the per-direction grid barrier
+ * Constraints: H % 16 == 0, Bp % 8 == 0, Bp <= 128, ndir*H/16 <= number of SMs.
  * ------------------------------------------------------------------------------------- */
 int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bhh, float* y, void* xn_bf16,
                void* xnT_bf16, float* gates, unsigned int* barrier, int T, int Bp, int H, int ndir,

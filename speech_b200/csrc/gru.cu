@@ -21,12 +21,7 @@
 //     accumulators with tcgen05.ld, apply the gate math in fp32 (h_{t-1} of the thread's own units
 //     stays in registers across steps), publish the bf16 h_t, arrive on the per-direction grid
 //     barrier, and only then write the fp32 state / transposed copy / saved gates;
-//   * the grid barrier is one red.release.gpu + ld.acquire.gpu polling on a global counter;
-//   * the batch is split into NSTR independent STREAMS of <= 32 rows.  Stream s lives on TMEM lane
-//     quadrant s (its rows sit at row offset 32*s of the 128-row MMA tile), has its own epilogue
-//     warps {s, s+4}, its own MMA-issuing warp, TMA warp, mbarriers, accumulator columns and grid
-//     barrier counter - so while one stream waits for its all-gather the other one computes (each
-//     step is latency-, not throughput-bound: ncu shows 15 % active warps, 5-10 % tensor pipe).
+//   * the grid barrier is one red.release.gpu + ld.acquire.gpu polling on a global counter.
 // The backward kernel has the same structure with W_hh^T resident (16 rows x 3H) and the
 // all-gather over the pre-activation gradients dgh_t (batch x 3H).
 //
@@ -44,8 +39,8 @@ namespace sb {
 static constexpr int GRU_HC = 16;            // hidden units per CTA
 static constexpr int GRU_UPT = 8;            // hidden units per epilogue thread
 static constexpr int GRU_MAX_RING = 16;      // smem ring slots for the gathered operand
-static constexpr int GRU_MAX_STREAMS = 2;
-static constexpr int GRU_THREADS = 256;      // 8 warps: (w&3)<2 epilogue of stream w&3; 2,3 MMA; 6,7 TMA
+static constexpr int GRU_EPI = 256;          // warps 0..7: epilogue
+static constexpr int GRU_THREADS = GRU_EPI + 64;  // + warp 8: MMA issuer/TMEM owner, warp 9: TMA
 
 typedef __nv_bfloat16 bf16;
 
@@ -59,8 +54,7 @@ struct GruFwdParams {
   float* gates;        // [T*Bp][ndir][4][H] saved r,z,n,hn for backward ; may be null
   unsigned int* barrier;  // [ndir] zero-initialised counters
   unsigned long long* dbg;  // optional timeline (CTA 0): [step][16] globaltimer stamps, or null
-  int T, Bp, H, ndir, ring, gc;   // ring: slots (groups of gc chunks) in shared memory, per stream
-  int nstr, Bs;                   // streams and batch rows per stream (Bp = nstr*Bs, Bs <= 32)
+  int T, Bp, H, ndir, ring, gc;   // ring: slots (groups of gc chunks) in shared memory
 };
 
 struct GruBwdParams {
@@ -77,7 +71,6 @@ struct GruBwdParams {
   unsigned int* barrier;  // [ndir]
   unsigned long long* dbg;
   int T, Bp, H, ndir, ring, gc;
-  int nstr, Bs;
 };
 
 SB_DEVINL unsigned long long gtime() {
@@ -98,9 +91,7 @@ SB_DEVINL void grid_wait(const unsigned int* ctr, unsigned int target) {
     if (++spins > SB_SPIN_LIMIT) __trap();
   }
 }
-SB_DEVINL void epi_barrier(int stream) {   // the two epilogue warps of one stream
-  asm volatile("bar.sync %0, 64;" ::"r"(stream + 1) : "memory");
-}
+SB_DEVINL void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GRU_EPI) : "memory"); }
 
 // ---- cluster helpers ---------------------------------------------------------------------------
 SB_DEVINL uint32_t cluster_rank() {
@@ -137,30 +128,27 @@ SB_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 
 struct GruSmem {
-  uint8_t* ring;    // per stream: ring*gc data blocks of Bs*128 bytes.  The MMA tile of stream s
-                    // starts 4096*s bytes BEFORE its block (rows 32*s.. of the tile = the stream's
-                    // rows; for s = 1 that is inside stream 0's blocks) and the weights follow the
-                    // ring, so the 128-row read overruns into finite data only.
+  uint8_t* ring;    // ring slots (stride = Bp*128 bytes), placed BEFORE the weights so that the
+                    // 128-row MMA read of the last slot overruns into (finite) weight data
   uint8_t* wtile;   // resident weight chunks
-  uint64_t* full;   // [stream][GRU_MAX_RING]
-  uint64_t* empty;  // [stream][GRU_MAX_RING]
-  uint64_t* accfull;  // [stream]
+  uint64_t* full;   // [GRU_MAX_RING]
+  uint64_t* empty;  // [GRU_MAX_RING]
+  uint64_t* accfull;
   uint32_t* tmem_slot;
   float* scratch;   // [64]
 };
 
 SB_DEVINL GruSmem carve(uint8_t* raw, int ring_bytes, int wbytes) {
   GruSmem s;
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  s.ring = base;   // stream 1's tile base (data - 4096) falls inside stream 0's blocks: no pad
+  s.ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) &
+                                      ~static_cast<uintptr_t>(1023));
   s.wtile = s.ring + ring_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s.wtile + wbytes);
   s.full = bars;
-  s.empty = bars + GRU_MAX_STREAMS * GRU_MAX_RING;
-  s.accfull = bars + 2 * GRU_MAX_STREAMS * GRU_MAX_RING;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(s.accfull + GRU_MAX_STREAMS);
-  s.scratch = reinterpret_cast<float*>(s.accfull + GRU_MAX_STREAMS + 1);
+  s.empty = bars + GRU_MAX_RING;
+  s.accfull = bars + 2 * GRU_MAX_RING;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GRU_MAX_RING + 1);
+  s.scratch = reinterpret_cast<float*>(bars + 2 * GRU_MAX_RING + 2);
   return s;
 }
 
@@ -172,26 +160,23 @@ SB_DEVINL GruSmem carve(uint8_t* raw, int ring_bytes, int wbytes) {
 //
 // TMA producer (one thread per CTA).  Every CTA arms its own full barriers; chunk c is fetched
 // by the CTA whose cluster rank is c % CS and multicast to the whole cluster.
-SB_DEVINL void tma_gather(const GruSmem& s, const CUtensorMap* tm, int row0, int Bs, int nchunks,
-                          int ring, int gc, int k, uint32_t rank, uint32_t cs, int st) {
-  const int stride = Bs * 128;
-  uint64_t* full = s.full + st * GRU_MAX_RING;
-  uint64_t* empty = s.empty + st * GRU_MAX_RING;
-  uint8_t* blocks = s.ring + (size_t)st * ring * gc * stride;
+SB_DEVINL void tma_gather(const GruSmem& s, const CUtensorMap* tm, int row0, int Bp, int nchunks,
+                          int ring, int gc, int k, uint32_t rank, uint32_t cs) {
+  const int stride = Bp * 128;
   const int ngroups = nchunks / gc;
   const int upr = ngroups / ring;
   const uint16_t mask = (uint16_t)((1u << cs) - 1u);
   for (int g = 0; g < ngroups; ++g) {
     const int slot = g % ring;
     const unsigned int P = (unsigned int)(k * upr + g / ring);
-    if (g >= ring) mbar_wait(&empty[slot], (P - 1u) & 1u);   // released by ALL CTAs of the cluster
-    mbar_expect_tx(&full[slot], (uint32_t)(stride * gc));
+    if (g >= ring) mbar_wait(&s.empty[slot], (P - 1u) & 1u);   // released by ALL CTAs of the cluster
+    mbar_expect_tx(&s.full[slot], (uint32_t)(stride * gc));
     for (int i = 0; i < gc; ++i) {
       const int c = g * gc + i;
       if ((uint32_t)c % cs != rank) continue;
-      uint8_t* dst = blocks + (slot * gc + i) * stride;
-      if (cs > 1) tma_load_2d_mc(dst, tm, &full[slot], c * 64, row0, mask);
-      else tma_load_2d(dst, tm, &full[slot], c * 64, row0);
+      uint8_t* dst = s.ring + (slot * gc + i) * stride;
+      if (cs > 1) tma_load_2d_mc(dst, tm, &s.full[slot], c * 64, row0, mask);
+      else tma_load_2d(dst, tm, &s.full[slot], c * 64, row0);
     }
   }
 }
@@ -199,24 +184,20 @@ SB_DEVINL void tma_gather(const GruSmem& s, const CUtensorMap* tm, int row0, int
 // MMA thread: consume the step's chunks against the resident weight chunks.
 template <int N>
 SB_DEVINL void mma_consume(const GruSmem& s, uint32_t tmem_d, int nchunks, int wchunk_bytes,
-                           int Bs, int ring, int gc, int k, uint32_t cs, int st) {
+                           int Bp, int ring, int gc, int k, uint32_t cs) {
   constexpr uint32_t idesc = umma_idesc_bf16_f32(128, N);
-  const int stride = Bs * 128;
-  uint64_t* full = s.full + st * GRU_MAX_RING;
-  uint64_t* empty = s.empty + st * GRU_MAX_RING;
-  // tile base: the stream's rows are rows 32*st.. of the 128-row A tile
-  const uint8_t* blocks = s.ring + (size_t)st * ring * gc * stride - 4096 * st;
+  const int stride = Bp * 128;
   const int ngroups = nchunks / gc;
   const int upr = ngroups / ring;
   const uint16_t mask = (uint16_t)((1u << cs) - 1u);
   for (int g = 0; g < ngroups; ++g) {
     const int slot = g % ring;
     const unsigned int P = (unsigned int)(k * upr + g / ring);
-    mbar_wait(&full[slot], P & 1u);
+    mbar_wait(&s.full[slot], P & 1u);
     tc_fence_after_sync();
     for (int i = 0; i < gc; ++i) {
       const int c = g * gc + i;
-      const uint64_t da = umma_desc_sw128_kmajor(smem_u32(blocks + (slot * gc + i) * stride));
+      const uint64_t da = umma_desc_sw128_kmajor(smem_u32(s.ring + (slot * gc + i) * stride));
       const uint64_t db = umma_desc_sw128_kmajor(smem_u32(s.wtile + c * wchunk_bytes));
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
@@ -224,11 +205,11 @@ SB_DEVINL void mma_consume(const GruSmem& s, uint32_t tmem_d, int nchunks, int w
                      (c > 0 || kk > 0) ? 1u : 0u);
     }
     if (ring < ngroups) {
-      if (cs > 1) umma_commit_mc(&empty[slot], mask);
-      else umma_commit(&empty[slot]);
+      if (cs > 1) umma_commit_mc(&s.empty[slot], mask);
+      else umma_commit(&s.empty[slot]);
     }
   }
-  umma_commit(s.accfull + st);
+  umma_commit(s.accfull);
 }
 
 SB_DEVINL float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -269,15 +250,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1)
 gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant__ CUtensorMap tm_d1,
                const GruFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const int H = p.H, Bp = p.Bp, Bs = p.Bs, T = p.T;
+  const int H = p.H, Bp = p.Bp, T = p.T;
   const int nC = H / GRU_HC;
   const int dir = blockIdx.x / nC;
   const int j0 = (blockIdx.x % nC) * GRU_HC;
   const int nchunks = (H + 63) / 64;
   constexpr int WCHUNK = 48 * 128;  // 48 rows x 64 bf16
-  const int ring_bytes = p.nstr * p.ring * p.gc * Bs * 128;
-  // the 128-row A read of the last block overruns by < 16 KB into this region
-  const int wbytes = max(nchunks * WCHUNK, 16384);
+  const int ring_bytes = p.ring * p.gc * Bp * 128;
+  // the 128-row A read of the last ring slot overruns by (16 KB - stride) into this region
+  const int wbytes = max(nchunks * WCHUNK, 16384 - Bp * 128);
   const GruSmem s = carve(smem_raw, ring_bytes, wbytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = p.ndir * H;
@@ -285,13 +266,9 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
   const uint32_t crank = cluster_rank(), csize = cluster_size();
 
-  // ---- one-time setup: zero pad + ring + weight region, stage the 48 weight rows ----
-  {
-    uint8_t* z0 = s.ring;
-    const int zbytes = ring_bytes + wbytes;
-    for (int k = tid; k < zbytes / 16; k += GRU_THREADS)
-      reinterpret_cast<uint4*>(z0)[k] = make_uint4(0, 0, 0, 0);
-  }
+  // ---- one-time setup: zero ring + weight region, stage the 48 weight rows, barriers, TMEM ----
+  for (int k = tid; k < (ring_bytes + wbytes) / 16; k += GRU_THREADS)
+    reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   {
     const int pieces_per_row = nchunks * 8;
@@ -311,57 +288,49 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < GRU_MAX_STREAMS * GRU_MAX_RING; ++i) {
+    for (int i = 0; i < GRU_MAX_RING; ++i) {
       mbar_init(&s.full[i], 1);
       mbar_init(&s.empty[i], csize);
     }
-    for (int i = 0; i < GRU_MAX_STREAMS; ++i) mbar_init(&s.accfull[i], 1);
+    mbar_init(s.accfull, 1);
     mbar_fence_init();
     tma_prefetch_desc(tm);
   }
-  if (warp == 2) tmem_alloc(s.tmem_slot, 64 * GRU_MAX_STREAMS);
+  if (warp == 8) tmem_alloc(s.tmem_slot, 64);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   const uint32_t tmem_base = *s.tmem_slot;
+  unsigned int* ctr = p.barrier + dir;
 
-  const int q = warp & 3;
-  if (q >= 2) {
-    const int st = q - 2;                       // stream served by this MMA / TMA warp
-    unsigned int* ctr = p.barrier + dir * GRU_MAX_STREAMS + st;
-    if (st < p.nstr && lane == 0) {
-      if (warp >= 4) {
-        // ===================== TMA producer of stream st =====================
-        for (int step = 1; step < T; ++step) {
-          const int t = dir == 0 ? step : (T - 1 - step);
-          const int tp = dir == 0 ? t - 1 : t + 1;
-          grid_wait(ctr, (unsigned int)nC * step);   // all CTAs published this stream's h_{tp}
-          if (st == 0) GRU_STAMP(0);
-          // (the writers ran fence.proxy.async before their release; no reader-side proxy fence)
-          tma_gather(s, tm, tp * Bp + st * Bs, Bs, nchunks, p.ring, p.gc, step - 1, crank, csize,
-                     st);
-          if (st == 0) GRU_STAMP(1);
-        }
-      } else {
-        // ===================== MMA issuer of stream st =====================
-        for (int step = 1; step < T; ++step) {
-          mma_consume<48>(s, tmem_base + st * 64, nchunks, WCHUNK, Bs, p.ring, p.gc, step - 1,
-                          csize, st);
-          if (st == 0) GRU_STAMP(2);
-        }
+  if (warp == 9) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int step = 1; step < T; ++step) {
+        const int t = dir == 0 ? step : (T - 1 - step);
+        const int tp = dir == 0 ? t - 1 : t + 1;
+        grid_wait(ctr, (unsigned int)nC * step);   // every CTA of this direction published h_{tp}
+        GRU_STAMP(0);
+        // (the writers ran fence.proxy.async before their release; no reader-side proxy fence)
+        tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, p.gc, step - 1, crank, csize);
+        GRU_STAMP(1);
       }
     }
-  } else if (q < p.nstr) {
-    // ===================== epilogue of stream q: thread = (batch row, half of the units) ====
-    const int st = q;
-    unsigned int* ctr = p.barrier + dir * GRU_MAX_STREAMS + st;
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      for (int step = 1; step < T; ++step) {
+        mma_consume<48>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, p.gc, step - 1, csize);
+        GRU_STAMP(2);
+      }
+    }
+  } else {
+    // ===================== epilogue: thread = (batch row, half of the 16 units) ==============
+    const int row = (warp & 3) * 32 + lane;      // TMEM lane this thread may read
     const int uh = warp >> 2;                    // which 8 of the CTA's 16 units
     const int ju = j0 + uh * GRU_UPT;
-    const int brow = st * Bs + lane;             // batch row of this thread
-    const bool active = lane < Bs;
-    const uint32_t taddr = tmem_base + ((uint32_t)(st * 32) << 16) + st * 64 + uh * GRU_UPT;
     float hprev[GRU_UPT];
 #pragma unroll
     for (int jj = 0; jj < GRU_UPT; ++jj) hprev[jj] = 0.f;
@@ -370,24 +339,26 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
     for (int g = 0; g < 3; ++g)
 #pragma unroll
       for (int jj = 0; jj < GRU_UPT; ++jj) bias[g][jj] = s.scratch[g * 16 + uh * GRU_UPT + jj];
+    const bool active = row < Bp;
     for (int step = 0; step < T; ++step) {
       const int t = dir == 0 ? step : (T - 1 - step);
       // this step's input projections do not depend on the recurrence: fetch them first
       float gi[3][GRU_UPT];
       if (active) {
-        const float* g = p.gi + ((long long)t * Bp + brow) * (p.ndir * 3 * H) + dir * 3 * H + ju;
+        const float* g = p.gi + ((long long)t * Bp + row) * (p.ndir * 3 * H) + dir * 3 * H + ju;
 #pragma unroll
         for (int gg = 0; gg < 3; ++gg) ld8(g + gg * H, gi[gg]);
       }
       float acc[3][GRU_UPT];
       if (step > 0) {
-        mbar_wait(s.accfull + st, (step - 1) & 1);
+        mbar_wait(s.accfull, (step - 1) & 1);
         if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
         uint32_t v[8];
 #pragma unroll
         for (int gg = 0; gg < 3; ++gg) {
-          tmem_ld_32x32b_x8(taddr + gg * 16, v);
+          tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + gg * 16 + uh * GRU_UPT,
+                            v);
           tmem_ld_wait();
 #pragma unroll
           for (int jj = 0; jj < GRU_UPT; ++jj) acc[gg][jj] = __uint_as_float(v[jj]);
@@ -400,7 +371,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
 #pragma unroll
           for (int jj = 0; jj < GRU_UPT; ++jj) acc[gg][jj] = 0.f;
       }
-      const long long m = (long long)t * Bp + brow;
+      const long long m = (long long)t * Bp + row;
       float hn[GRU_UPT], rr[GRU_UPT], zz[GRU_UPT], nn[GRU_UPT];
       if (active) {
 #pragma unroll
@@ -417,17 +388,17 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         fence_proxy_async_all();   // these generic-proxy writes are read by other CTAs' TMA
         if (tid == 0) GRU_STAMP(6);
       }
-      epi_barrier(st);
-      if (warp == st && lane == 0) {
-        if (st == 0) GRU_STAMP(7);
-        grid_arrive(ctr);          // release: cumulative over the stream's writes ordered by bar.sync
-        if (st == 0) GRU_STAMP(9);
+      epi_barrier();
+      if (tid == 0) {
+        GRU_STAMP(7);
+        grid_arrive(ctr);          // release: cumulative over the CTA's writes ordered by bar.sync
+        GRU_STAMP(9);
       }
       // off the critical path: fp32 state, transposed copy, saved gates
       if (active) {
         st8(p.y + m * D + dir * H + ju, hprev);
         if (p.xnT) {
-          bf16* xt = p.xnT + (long long)(dir * H + ju) * ldT + (long long)(t + 1) * Bp + brow;
+          bf16* xt = p.xnT + (long long)(dir * H + ju) * ldT + (long long)(t + 1) * Bp + row;
 #pragma unroll
           for (int jj = 0; jj < GRU_UPT; ++jj) xt[jj * ldT] = __float2bfloat16_rn(hprev[jj]);
         }
@@ -446,9 +417,9 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();   // no CTA leaves while peers may still signal its barriers
-  if (warp == 2) {
+  if (warp == 8) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 64 * GRU_MAX_STREAMS);
+    tmem_dealloc(tmem_base, 64);
   }
 }
 
@@ -459,15 +430,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1)
 gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant__ CUtensorMap tm_d1,
                const GruBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const int H = p.H, Bp = p.Bp, Bs = p.Bs, T = p.T;
+  const int H = p.H, Bp = p.Bp, T = p.T;
   const int nC = H / GRU_HC;
   const int dir = blockIdx.x / nC;
   const int j0 = (blockIdx.x % nC) * GRU_HC;
   const int K3 = 3 * H;
   const int nchunks = (K3 + 63) / 64;
   constexpr int WCHUNK = 16 * 128;  // 16 rows x 64 bf16
-  const int ring_bytes = p.nstr * p.ring * p.gc * Bs * 128;
-  const int wbytes = max(nchunks * WCHUNK, 16384);
+  const int ring_bytes = p.ring * p.gc * Bp * 128;
+  const int wbytes = max(nchunks * WCHUNK, 16384 - Bp * 128);
   const GruSmem s = carve(smem_raw, ring_bytes, wbytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = p.ndir * H;
@@ -475,12 +446,8 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
   const uint32_t crank = cluster_rank(), csize = cluster_size();
 
-  {
-    uint8_t* z0 = s.ring;
-    const int zbytes = ring_bytes + wbytes;
-    for (int k = tid; k < zbytes / 16; k += GRU_THREADS)
-      reinterpret_cast<uint4*>(z0)[k] = make_uint4(0, 0, 0, 0);
-  }
+  for (int k = tid; k < (ring_bytes + wbytes) / 16; k += GRU_THREADS)
+    reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   {
     // resident operand: rows = the 16 hidden units k0..k0+15 of W_hh^T, K = 3H
@@ -496,52 +463,45 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < GRU_MAX_STREAMS * GRU_MAX_RING; ++i) {
+    for (int i = 0; i < GRU_MAX_RING; ++i) {
       mbar_init(&s.full[i], 1);
       mbar_init(&s.empty[i], csize);
     }
-    for (int i = 0; i < GRU_MAX_STREAMS; ++i) mbar_init(&s.accfull[i], 1);
+    mbar_init(s.accfull, 1);
     mbar_fence_init();
     tma_prefetch_desc(tm);
   }
-  if (warp == 2) tmem_alloc(s.tmem_slot, 32 * GRU_MAX_STREAMS);
+  if (warp == 8) tmem_alloc(s.tmem_slot, 32);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   cluster_sync_all();
   const uint32_t tmem_base = *s.tmem_slot;
+  unsigned int* ctr = p.barrier + dir;
 
-  const int q = warp & 3;
-  if (q >= 2) {
-    const int st = q - 2;
-    unsigned int* ctr = p.barrier + dir * GRU_MAX_STREAMS + st;
-    if (st < p.nstr && lane == 0) {
-      if (warp >= 4) {
-        // the recurrent product is needed for every step except the last one processed
-        for (int step = 0; step + 1 < T; ++step) {
-          grid_wait(ctr, (unsigned int)nC * (step + 1));   // this stream's dgh_t is complete
-          if (st == 0) GRU_STAMP(0);
-          tma_gather(s, tm, (step & 1) * Bp + st * Bs, Bs, nchunks, p.ring, p.gc, step, crank,
-                     csize, st);
-          if (st == 0) GRU_STAMP(1);
-        }
-      } else {
-        for (int step = 0; step + 1 < T; ++step) {
-          mma_consume<16>(s, tmem_base + st * 32, nchunks, WCHUNK, Bs, p.ring, p.gc, step, csize,
-                          st);
-          if (st == 0) GRU_STAMP(2);
-        }
+  if (warp == 9) {
+    if (lane == 0) {
+      // the recurrent product is needed for every step except the last one processed
+      for (int step = 0; step + 1 < T; ++step) {
+        grid_wait(ctr, (unsigned int)nC * (step + 1));   // dgh of this step is complete
+        GRU_STAMP(0);
+        tma_gather(s, tm, (step & 1) * Bp, Bp, nchunks, p.ring, p.gc, step, crank, csize);
+        GRU_STAMP(1);
       }
     }
-  } else if (q < p.nstr) {
-    const int st = q;
-    unsigned int* ctr = p.barrier + dir * GRU_MAX_STREAMS + st;
+  } else if (warp == 8) {
+    if (lane == 0) {
+      for (int step = 0; step + 1 < T; ++step) {
+        mma_consume<16>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, p.gc, step, csize);
+        GRU_STAMP(2);
+      }
+    }
+  } else {
+    const int row = (warp & 3) * 32 + lane;
     const int uh = warp >> 2;
     const int ju = j0 + uh * GRU_UPT;
-    const int brow = st * Bs + lane;
-    const bool active = lane < Bs;
-    const uint32_t taddr = tmem_base + ((uint32_t)(st * 32) << 16) + st * 32 + uh * GRU_UPT;
+    const bool active = row < Bp;
     float dh_rec[GRU_UPT];   // dL/dh_t arriving through the recurrence (own units)
     float db_r[GRU_UPT], db_z[GRU_UPT], db_n[GRU_UPT], db_hn[GRU_UPT];
 #pragma unroll
@@ -555,7 +515,7 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       const int tp = dir == 0 ? t - 1 : t + 1;       // time index of h_{prev} in forward order
       const bool has_prev = dir == 0 ? (t > 0) : (t < T - 1);
       bf16* xb = p.xchg + ((long long)(dir * 2 + (step & 1)) * Bp) * K3;
-      const long long m = (long long)t * Bp + brow;
+      const long long m = (long long)t * Bp + row;
       // ---- saved activations of this step: independent of the recurrence, fetched first ----
       float rr[GRU_UPT], zz[GRU_UPT], nn[GRU_UPT], hn[GRU_UPT], dh[GRU_UPT], hp[GRU_UPT];
       if (active) {
@@ -566,7 +526,7 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         ld8(go + 3 * H, hn);
         ld8(p.dy + m * D + dir * H + ju, dh);
         if (has_prev) {
-          ld8(p.y + ((long long)tp * Bp + brow) * D + dir * H + ju, hp);
+          ld8(p.y + ((long long)tp * Bp + row) * D + dir * H + ju, hp);
         } else {
 #pragma unroll
           for (int jj = 0; jj < GRU_UPT; ++jj) hp[jj] = 0.f;
@@ -574,11 +534,11 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       }
       // ---- recurrent part of dL/dh_t: product issued in the previous step ----
       if (step > 0) {
-        mbar_wait(s.accfull + st, (step - 1) & 1);
+        mbar_wait(s.accfull, (step - 1) & 1);
         if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
         uint32_t v[8];
-        tmem_ld_32x32b_x8(taddr, v);
+        tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + uh * GRU_UPT, v);
         tmem_ld_wait();
         tc_fence_before_sync();
         if (tid == 0) GRU_STAMP(4);
@@ -602,7 +562,7 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         }
         // critical path: the exchange rows [dr | dz | dn*r] every CTA gathers for the product
         if (step + 1 < T) {
-          bf16* x = xb + (long long)brow * K3 + ju;
+          bf16* x = xb + (long long)row * K3 + ju;
           *reinterpret_cast<uint4*>(x) = pack8(dr);
           *reinterpret_cast<uint4*>(x + H) = pack8(dz);
           *reinterpret_cast<uint4*>(x + 2 * H) = pack8(dnr);
@@ -612,11 +572,11 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         }
       }
       if (step + 1 < T) {
-        epi_barrier(st);
-        if (warp == st && lane == 0) {
-          if (st == 0) GRU_STAMP(7);
+        epi_barrier();
+        if (tid == 0) {
+          GRU_STAMP(7);
           grid_arrive(ctr);
-          if (st == 0) GRU_STAMP(9);
+          GRU_STAMP(9);
         }
       }
       // ---- off the critical path: operands of the dX / dW GEMMs ----
@@ -637,7 +597,11 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       }
       if (tid == 0) GRU_STAMP(10);
     }
-    // ---- bias gradients: per-warp sums straight to global (once per launch) ----
+    // ---- bias gradients: reduce the per-batch-row partial sums over the CTA ----
+    epi_barrier();
+    float* red = s.scratch;  // [64]: r(16) z(16) n(16) hn(16)
+    if (tid < 64) red[tid] = 0.f;
+    epi_barrier();
 #pragma unroll
     for (int jj = 0; jj < GRU_UPT; ++jj) {
       const float a = warp_sum(active ? db_r[jj] : 0.f);
@@ -645,58 +609,60 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       const float c = warp_sum(active ? db_n[jj] : 0.f);
       const float d = warp_sum(active ? db_hn[jj] : 0.f);
       if (lane == 0) {
-        const int base = dir * K3 + ju + jj;
-        atomicAdd(p.dbih + base, a);
-        atomicAdd(p.dbih + base + H, b);
-        atomicAdd(p.dbih + base + 2 * H, c);
-        atomicAdd(p.dbhh + base, a);
-        atomicAdd(p.dbhh + base + H, b);
-        atomicAdd(p.dbhh + base + 2 * H, d);
+        atomicAdd(&red[uh * GRU_UPT + jj], a);
+        atomicAdd(&red[16 + uh * GRU_UPT + jj], b);
+        atomicAdd(&red[32 + uh * GRU_UPT + jj], c);
+        atomicAdd(&red[48 + uh * GRU_UPT + jj], d);
       }
+    }
+    epi_barrier();
+    if (tid < 48) {
+      const int g = tid / GRU_HC, jj = tid % GRU_HC;
+      const int idx = dir * K3 + g * H + j0 + jj;
+      atomicAdd(p.dbih + idx, red[tid]);
+      atomicAdd(p.dbhh + idx, g < 2 ? red[tid] : red[48 + jj]);
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 2) {
+  if (warp == 8) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 32 * GRU_MAX_STREAMS);
+    tmem_dealloc(tmem_base, 32);
   }
 }
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
                       long long ld, int box_rows);
 
-// chunks are grouped gc per mbarrier pair (gc = largest of 4,3,2,1 dividing nchunks); per stream
-// ring = the largest divisor of ngroups (<= GRU_MAX_RING) such that all streams' blocks fit next
-// to the resident weights
-static int gru_ring_slots(int wbytes, int Bs, int nstr, int nchunks, int* gc_out,
-                          size_t* smem_bytes) {
-  const int fixed = wbytes + 1024 /*align*/ +
-                    (2 * GRU_MAX_STREAMS * GRU_MAX_RING + GRU_MAX_STREAMS + 2) * 8 + 256 + 64;
-  for (int gc = 4; gc >= 1; --gc) {
-    if (nchunks % gc != 0) continue;
-    const int ngroups = nchunks / gc;
-    const int slot = gc * Bs * 128 * nstr;        // one ring position across all streams
-    int fit = (227 * 1024 - fixed) / slot;
+// chunks are grouped gc per mbarrier pair (gc = largest of 4,3,2,1 dividing nchunks); ring = the
+// largest divisor of ngroups (<= GRU_MAX_RING) whose slots fit next to the resident weights
+static int gru_ring_slots(int wbytes, int Bp, int nchunks, int* gc_out, size_t* smem_bytes) {
+  int gc = 1;
+  for (int g = 4; g >= 1; --g)
+    if (nchunks % g == 0) { gc = g; break; }
+  const int ngroups = nchunks / gc;
+  const int slot = gc * Bp * 128;
+  const int fixed = wbytes + 1024 /*align*/ + (2 * GRU_MAX_RING + 2) * 8 + 256 /*scratch*/ + 64;
+  int fit = (227 * 1024 - fixed) / slot;
+  if (fit > GRU_MAX_RING) fit = GRU_MAX_RING;
+  int ring = -1;
+  for (int r = fit; r >= 1; --r)
+    if (ngroups % r == 0) { ring = r; break; }
+  if (ring < 1) {
+    if (gc == 1) return -1;
+    // fall back to single-chunk groups
+    gc = 1;
+    fit = (227 * 1024 - fixed) / (Bp * 128);
     if (fit > GRU_MAX_RING) fit = GRU_MAX_RING;
-    for (int r = fit; r >= 1; --r) {
-      if (ngroups % r == 0) {
-        *gc_out = gc;
-        *smem_bytes = (size_t)fixed + (size_t)r * slot;
-        return r;
-      }
-    }
+    for (int r = fit; r >= 1; --r)
+      if (nchunks % r == 0) { ring = r; break; }
+    if (ring < 1) return -1;
   }
-  return -1;
-}
-
-// streams: batch rows are split into nstr groups of Bs <= 32 rows (one TMEM lane quadrant each)
-static int gru_streams(int Bp, int* Bs) {
-  if (Bp <= 32) { *Bs = Bp; return 1; }
-  if (Bp <= 64 && Bp % 16 == 0) { *Bs = Bp / 2; return 2; }
-  return -1;
+  *gc_out = gc;
+  *smem_bytes = (size_t)fixed + (size_t)ring * gc * Bp * 128;
+  return ring;
 }
 
 static int g_gru_cluster = 8;   // preferred cluster size (developer knob: sb_debug_gru_cluster)
@@ -773,8 +739,7 @@ extern "C" int sb_debug_gru_cluster(int cluster_size) {
 
 static int gru_check(int T, int Bp, int H, int ndir) {
   if (T <= 0 || Bp <= 0 || H <= 0 || (ndir != 1 && ndir != 2)) return SB_ERR_INVALID;
-  int bs = 0;
-  if (H % GRU_HC != 0 || Bp % 8 != 0 || gru_streams(Bp, &bs) < 0) return SB_ERR_UNSUPPORTED;
+  if (H % GRU_HC != 0 || Bp % 8 != 0 || Bp > 128) return SB_ERR_UNSUPPORTED;
   if (ndir * (H / GRU_HC) > sb::device_sm_count()) return SB_ERR_UNSUPPORTED;
   return SB_OK;
 }
@@ -793,8 +758,7 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
   p.dbg = g_gru_dbg;
   const int nchunks = (H + 63) / 64;
   size_t smem = 0;
-  p.nstr = gru_streams(Bp, &p.Bs);
-  p.ring = gru_ring_slots(std::max(nchunks * 48 * 128, 16384), p.Bs, p.nstr, nchunks, &p.gc, &smem);
+  p.ring = gru_ring_slots(std::max(nchunks * 48 * 128, 16384 - Bp * 128), Bp, nchunks, &p.gc, &smem);
   if (p.ring < 0) return SB_ERR_UNSUPPORTED;
   // one tensor map per direction over that direction's H columns of h (bf16 [T*Bp][ndir*H]):
   // columns past H are out of bounds and read as zero
@@ -802,11 +766,10 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
   for (int d = 0; d < 2; ++d) {
     const int dd = d < ndir ? d : 0;
     rc = make_tmap_bf16_2d(&tm[d], p.xn + (size_t)dd * H, (long long)T * Bp, H,
-                           (long long)ndir * H, p.Bs);
+                           (long long)ndir * H, Bp);
     if (rc != SB_OK) return rc;
   }
-  if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * 2 * GRU_MAX_STREAMS, stream) !=
-      cudaSuccess)
+  if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * ndir, stream) != cudaSuccess)
     return SB_ERR_CUDA;
   void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&p};
   const int nC = H / GRU_HC;
@@ -844,18 +807,16 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   const int K3 = 3 * H;
   const int nchunks = (K3 + 63) / 64;
   size_t smem = 0;
-  p.nstr = gru_streams(Bp, &p.Bs);
-  p.ring = gru_ring_slots(std::max(nchunks * 16 * 128, 16384), p.Bs, p.nstr, nchunks, &p.gc, &smem);
+  p.ring = gru_ring_slots(std::max(nchunks * 16 * 128, 16384 - Bp * 128), Bp, nchunks, &p.gc, &smem);
   if (p.ring < 0) return SB_ERR_UNSUPPORTED;
   // per direction: the two parity buffers stacked as [2*Bp rows][3H cols]
   CUtensorMap tm[2];
   for (int d = 0; d < 2; ++d) {
     const int dd = d < ndir ? d : 0;
-    rc = make_tmap_bf16_2d(&tm[d], p.xchg + (size_t)dd * 2 * Bp * K3, 2LL * Bp, K3, K3, p.Bs);
+    rc = make_tmap_bf16_2d(&tm[d], p.xchg + (size_t)dd * 2 * Bp * K3, 2LL * Bp, K3, K3, Bp);
     if (rc != SB_OK) return rc;
   }
-  if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * 2 * GRU_MAX_STREAMS, stream) !=
-      cudaSuccess)
+  if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * ndir, stream) != cudaSuccess)
     return SB_ERR_CUDA;
   void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&p};
   const int nC = H / GRU_HC;

@@ -108,9 +108,9 @@ class GRUStackFunction(torch.autograd.Function):
         B, T, In = x.shape
         dev = x.device
         L = len(weights) // (4 * ndir)
-        Bp = _round_up(B, 8) if B <= 32 else _round_up(B, 16)
-        if Bp > 64:
-            raise _lib.SpeechB200Error("per-GPU batch > 64 not supported by the GRU kernel yet")
+        Bp = _round_up(B, 8)
+        if Bp > 128:
+            raise _lib.SpeechB200Error("per-GPU batch > 128 not supported by the GRU kernel yet")
         M = T * Bp
         D = ndir * H
         need_grad = any(w.requires_grad for w in weights) or x.requires_grad
@@ -120,7 +120,7 @@ class GRUStackFunction(torch.autograd.Function):
         X = torch.zeros(T, Bp, Inp, dtype=torch.bfloat16, device=dev)
         X[:, :B, :In] = x.transpose(0, 1)
         X = X.view(M, Inp)
-        barrier = torch.zeros(4, dtype=torch.int32, device=dev)
+        barrier = torch.zeros(2, dtype=torch.int32, device=dev)
         saved = []
         y = None
         for l in range(L):
@@ -174,7 +174,7 @@ class GRUStackFunction(torch.autograd.Function):
         dY = torch.zeros(T, Bp, D, dtype=torch.float32, device=dev)
         dY[:, :B] = dout.transpose(0, 1)
         dY = dY.view(M, D)
-        barrier = torch.zeros(4, dtype=torch.int32, device=dev)
+        barrier = torch.zeros(2, dtype=torch.int32, device=dev)
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.sb_gru_bwd_workspace_size(Bp, H, ndir, ctypes.byref(nbytes)), "ws")
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
