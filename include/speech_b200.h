@@ -145,6 +145,8 @@ int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
 /* Developer hook (not part of the drop-in surface): device buffer of >= 64*16 uint64 receiving a
  * globaltimer timeline of CTA 0 for the next sb_gru_fwd launches; NULL disables. */
 int sb_debug_gru_timeline(void* dev_buffer);
+/* Developer hook: enable (1, default) / disable (0) the K-split backward GRU kernel. */
+int sb_debug_gru_ksplit(int enable);
 /* Developer hook: set the preferred thread-block-cluster size (1, 2, 4 or 8) of the GRU kernels;
  * returns the cluster size the last GRU launch actually used (0 = query only, -1 = bad value). */
 int sb_debug_gru_cluster(int cluster_size);

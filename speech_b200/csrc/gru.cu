@@ -633,6 +633,308 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   }
 }
 
+// =============================================================================================
+// backward, K-split variant: the 4 CTAs of a cluster jointly own 64 hidden units.
+//
+// The plain backward kernel makes every CTA gather ALL of dgh_t (Bp x 3H bf16 = 384 KB at the
+// north-star size) every step; with 96 KB of weights resident only 128 KB can be in flight, so
+// the gather alone costs ~9 us of the 15.8 us step.  Here CTA r of a cluster contracts only the
+// r-th QUARTER of the K = 3H dimension, for all 64 units of its cluster:
+//     D_r[batch x 64] = dgh_t[:, quarter r] * W_hh[quarter r, 64 units]          (96 KB gathered)
+// and the four partial products are reduce-scattered through distributed shared memory: each
+// epilogue thread pushes the three 8-float slices that belong to peer CTAs with st.shared::cluster
+// and arrives (release.cluster) on the peer's mbarrier; the owner adds the three slices it received
+// to its own.  12 KB of DSMEM traffic replaces 288 KB of L2 reads per CTA per step.
+// Requires cluster size 4, H % 256 == 0.
+// =============================================================================================
+static constexpr int KS = 4;
+
+SB_DEVINL uint32_t mapa_shared(uint32_t local_addr, uint32_t peer) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(peer));
+  return r;
+}
+SB_DEVINL void st_cluster_f4(uint32_t raddr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+SB_DEVINL void mbar_arrive_remote_release(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr)
+               : "memory");
+}
+SB_DEVINL void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > SB_SPIN_LIMIT) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(GRU_THREADS, 1)
+gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
+                  const __grid_constant__ CUtensorMap tm_d1, const GruBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int H = p.H, Bp = p.Bp, T = p.T;
+  const int nC = H / GRU_HC;
+  const int dir = blockIdx.x / nC;
+  const int cta_in_dir = blockIdx.x % nC;
+  const int j0 = cta_in_dir * GRU_HC;                 // own 16 units (elementwise work)
+  const uint32_t crank = cluster_rank();              // == cta_in_dir % 4
+  const int k0c = (cta_in_dir / KS) * (KS * GRU_HC);  // first of the cluster's 64 units
+  const int K3 = 3 * H;
+  const int KQ = K3 / KS;                             // this CTA's share of the contraction
+  const int nchunks = KQ / 64;
+  constexpr int WCHUNK = 64 * 128;                    // 64 rows (units) x 64 bf16
+  const int stride = Bp * 128;
+  const int ring_bytes = nchunks * stride;            // the whole quarter is resident
+  const int wbytes = nchunks * WCHUNK;
+  // carve: ring | weights | recv | barriers
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* ring = base;
+  uint8_t* wtile = ring + ring_bytes;
+  float* recv = reinterpret_cast<float*>(wtile + wbytes);          // [KS][Bp][16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(recv + KS * Bp * 16);
+  uint64_t* full = bars;          // [4] groups
+  uint64_t* accfull = bars + 4;
+  uint64_t* recvbar = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = p.ndir * H;
+  const long long M = (long long)T * Bp;
+  const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
+  const int gc = (nchunks % 4 == 0) ? 4 : ((nchunks % 3 == 0) ? 3 : ((nchunks % 2 == 0) ? 2 : 1));
+  const int ngroups = nchunks / gc;                   // <= 4 for H <= 1024 ... checked on host
+
+  for (int k = tid; k < (ring_bytes + wbytes + KS * Bp * 64) / 16; k += GRU_THREADS)
+    reinterpret_cast<uint4*>(base)[k] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    // resident operand: rows = the cluster's 64 units of W_hh^T, columns = this CTA's K quarter
+    const int pieces_per_row = nchunks * 8;
+    for (int k = tid; k < 64 * pieces_per_row; k += GRU_THREADS) {
+      const int r = k / pieces_per_row, pc = k % pieces_per_row;
+      const uint4 v = *reinterpret_cast<const uint4*>(
+          p.whhT + ((long long)dir * H + k0c + r) * K3 + (long long)crank * KQ + pc * 8);
+      *reinterpret_cast<uint4*>(wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&full[i], 1);
+    mbar_init(accfull, 1);
+    mbar_init(recvbar, (KS - 1) * GRU_EPI);   // every epilogue thread of every peer arrives once
+    mbar_fence_init();
+    tma_prefetch_desc(tm);
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 64);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  cluster_sync_all();
+  const uint32_t tmem_base = *tmem_slot;
+  unsigned int* ctr = p.barrier + dir;
+
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int step = 0; step + 1 < T; ++step) {
+        grid_wait(ctr, (unsigned int)nC * (step + 1));   // dgh of this step is complete
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_expect_tx(&full[g], (uint32_t)(stride * gc));
+          for (int i = 0; i < gc; ++i) {
+            const int c = g * gc + i;
+            tma_load_2d(ring + c * stride, tm, &full[g], (int)crank * KQ + c * 64,
+                        (step & 1) * Bp);
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 64);
+      for (int step = 0; step + 1 < T; ++step) {
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&full[g], step & 1);
+          tc_fence_after_sync();
+          for (int i = 0; i < gc; ++i) {
+            const int c = g * gc + i;
+            const uint64_t da = umma_desc_sw128_kmajor(smem_u32(ring + c * stride));
+            const uint64_t db = umma_desc_sw128_kmajor(smem_u32(wtile + c * WCHUNK));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ss(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                           (c > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(accfull);
+      }
+    }
+  } else {
+    const int row = (warp & 3) * 32 + lane;
+    const int uh = warp >> 2;
+    const int ju = j0 + uh * GRU_UPT;
+    const bool active = row < Bp;
+    float dh_rec[GRU_UPT];
+    float db_r[GRU_UPT], db_z[GRU_UPT], db_n[GRU_UPT], db_hn[GRU_UPT];
+#pragma unroll
+    for (int jj = 0; jj < GRU_UPT; ++jj) {
+      dh_rec[jj] = 0.f; db_r[jj] = 0.f; db_z[jj] = 0.f; db_n[jj] = 0.f; db_hn[jj] = 0.f;
+    }
+    // where this thread's slices land in each peer: recv[src = my rank][row][uh*8 ..]
+    const uint32_t my_slot = smem_u32(recv + ((size_t)crank * Bp + (active ? row : 0)) * 16 +
+                                      uh * GRU_UPT);
+    const uint32_t my_bar = smem_u32(recvbar);
+
+    for (int step = 0; step < T; ++step) {
+      const int t = dir == 0 ? (T - 1 - step) : step;
+      const int tp = dir == 0 ? t - 1 : t + 1;
+      const bool has_prev = dir == 0 ? (t > 0) : (t < T - 1);
+      bf16* xb = p.xchg + ((long long)(dir * 2 + (step & 1)) * Bp) * K3;
+      const long long m = (long long)t * Bp + row;
+      float rr[GRU_UPT], zz[GRU_UPT], nn[GRU_UPT], hn[GRU_UPT], dh[GRU_UPT], hp[GRU_UPT];
+      if (active) {
+        const float* go = p.gates + ((m * p.ndir + dir) * 4) * H + ju;
+        ld8(go, rr);
+        ld8(go + H, zz);
+        ld8(go + 2 * H, nn);
+        ld8(go + 3 * H, hn);
+        ld8(p.dy + m * D + dir * H + ju, dh);
+        if (has_prev) {
+          ld8(p.y + ((long long)tp * Bp + row) * D + dir * H + ju, hp);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < GRU_UPT; ++jj) hp[jj] = 0.f;
+        }
+      }
+      // ---- recurrent part of dL/dh_t: reduce-scatter of the four partial products ----
+      if (step > 0) {
+        mbar_wait(accfull, (step - 1) & 1);
+        if (tid == 0) GRU_STAMP(3);
+        tc_fence_after_sync();
+        float own[GRU_UPT];
+#pragma unroll
+        for (int pr = 0; pr < KS; ++pr) {
+          uint32_t v[8];
+          tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + pr * 16 +
+                                uh * GRU_UPT, v);
+          tmem_ld_wait();
+          if ((uint32_t)pr == crank) {
+#pragma unroll
+            for (int jj = 0; jj < GRU_UPT; ++jj) own[jj] = __uint_as_float(v[jj]);
+          } else {
+            if (active) {
+              const uint32_t ra = mapa_shared(my_slot, (uint32_t)pr);
+              st_cluster_f4(ra, make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]),
+                                            __uint_as_float(v[2]), __uint_as_float(v[3])));
+              st_cluster_f4(ra + 16, make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]),
+                                                 __uint_as_float(v[6]), __uint_as_float(v[7])));
+            }
+            mbar_arrive_remote_release(mapa_shared(my_bar, (uint32_t)pr));
+          }
+        }
+        tc_fence_before_sync();
+        if (tid == 0) GRU_STAMP(4);
+        mbar_wait_acquire_cluster(recvbar, (step - 1) & 1);
+#pragma unroll
+        for (int jj = 0; jj < GRU_UPT; ++jj) dh_rec[jj] += own[jj];
+        if (active) {
+#pragma unroll
+          for (int src = 0; src < KS; ++src) {
+            if ((uint32_t)src == crank) continue;
+            const float4* rp = reinterpret_cast<const float4*>(
+                recv + ((size_t)src * Bp + row) * 16 + uh * GRU_UPT);
+            const float4 a = rp[0], b = rp[1];
+            dh_rec[0] += a.x; dh_rec[1] += a.y; dh_rec[2] += a.z; dh_rec[3] += a.w;
+            dh_rec[4] += b.x; dh_rec[5] += b.y; dh_rec[6] += b.z; dh_rec[7] += b.w;
+          }
+        }
+      }
+      float dr[GRU_UPT], dz[GRU_UPT], dn[GRU_UPT], dnr[GRU_UPT];
+      if (active) {
+#pragma unroll
+        for (int jj = 0; jj < GRU_UPT; ++jj) {
+          const float g = dh[jj] + dh_rec[jj];
+          dn[jj] = g * (1.f - zz[jj]) * (1.f - nn[jj] * nn[jj]);
+          dz[jj] = g * (hp[jj] - nn[jj]) * zz[jj] * (1.f - zz[jj]);
+          dr[jj] = dn[jj] * hn[jj] * rr[jj] * (1.f - rr[jj]);
+          dnr[jj] = dn[jj] * rr[jj];
+          dh_rec[jj] = g * zz[jj];
+          db_r[jj] += dr[jj];
+          db_z[jj] += dz[jj];
+          db_n[jj] += dn[jj];
+          db_hn[jj] += dnr[jj];
+        }
+        if (step + 1 < T) {
+          bf16* x = xb + (long long)row * K3 + ju;
+          *reinterpret_cast<uint4*>(x) = pack8(dr);
+          *reinterpret_cast<uint4*>(x + H) = pack8(dz);
+          *reinterpret_cast<uint4*>(x + 2 * H) = pack8(dnr);
+          if (tid == 0) GRU_STAMP(5);
+          fence_proxy_async_all();
+          if (tid == 0) GRU_STAMP(6);
+        }
+      }
+      if (step + 1 < T) {
+        epi_barrier();
+        if (tid == 0) {
+          GRU_STAMP(7);
+          grid_arrive(ctr);
+          GRU_STAMP(9);
+        }
+      }
+      if (active) {
+        bf16* o = p.dgi + m * (p.ndir * K3) + dir * K3 + ju;
+        *reinterpret_cast<uint4*>(o) = pack8(dr);
+        *reinterpret_cast<uint4*>(o + H) = pack8(dz);
+        *reinterpret_cast<uint4*>(o + 2 * H) = pack8(dn);
+        bf16* gt = p.dgiT + ((long long)dir * K3 + ju) * M + m;
+        bf16* nt = p.dghnT + ((long long)dir * H + ju) * M + m;
+#pragma unroll
+        for (int jj = 0; jj < GRU_UPT; ++jj) {
+          gt[(long long)jj * M] = __float2bfloat16_rn(dr[jj]);
+          gt[(long long)(H + jj) * M] = __float2bfloat16_rn(dz[jj]);
+          gt[(long long)(2 * H + jj) * M] = __float2bfloat16_rn(dn[jj]);
+          nt[(long long)jj * M] = __float2bfloat16_rn(dnr[jj]);
+        }
+      }
+      if (tid == 0) GRU_STAMP(10);
+    }
+#pragma unroll
+    for (int jj = 0; jj < GRU_UPT; ++jj) {
+      const float a = warp_sum(active ? db_r[jj] : 0.f);
+      const float b = warp_sum(active ? db_z[jj] : 0.f);
+      const float c = warp_sum(active ? db_n[jj] : 0.f);
+      const float d = warp_sum(active ? db_hn[jj] : 0.f);
+      if (lane == 0) {
+        const int bi = dir * K3 + ju + jj;
+        atomicAdd(p.dbih + bi, a);
+        atomicAdd(p.dbih + bi + H, b);
+        atomicAdd(p.dbih + bi + 2 * H, c);
+        atomicAdd(p.dbhh + bi, a);
+        atomicAdd(p.dbhh + bi + H, b);
+        atomicAdd(p.dbhh + bi + 2 * H, d);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
                       long long ld, int box_rows);
 
@@ -718,6 +1020,44 @@ static int gru_launch(const void* kernel, int grid, int cs, size_t smem, void** 
 }
 
 static unsigned long long* g_gru_dbg = nullptr;
+static int g_gru_ksplit = 1;   // developer knob: 0 disables the K-split backward kernel
+
+// cooperative launch with EXACTLY the given cluster size; fails if the grid is not co-resident
+static int gru_launch_exact(const void* kernel, int grid, int cs, size_t smem, void** args,
+                            cudaStream_t stream) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return SB_ERR_CUDA;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GRU_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = cs;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess ||
+      nclusters * cs < grid) {
+    cudaGetLastError();
+    return SB_ERR_UNSUPPORTED;
+  }
+  if (cudaLaunchKernelExC(&cfg, kernel, args) != cudaSuccess) {
+    cudaGetLastError();
+    return SB_ERR_CUDA;
+  }
+  g_gru_last_cluster = cs;
+  return SB_OK;
+}
 
 }  // namespace sb
 
@@ -726,6 +1066,10 @@ using namespace sb;
 // developer hooks (not part of the drop-in surface)
 extern "C" int sb_debug_gru_timeline(void* dev_buffer) {
   sb::g_gru_dbg = reinterpret_cast<unsigned long long*>(dev_buffer);
+  return SB_OK;
+}
+extern "C" int sb_debug_gru_ksplit(int enable) {
+  sb::g_gru_ksplit = enable ? 1 : 0;
   return SB_OK;
 }
 extern "C" int sb_debug_gru_cluster(int cluster_size) {
@@ -807,6 +1151,27 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   const int K3 = 3 * H;
   const int nchunks = (K3 + 63) / 64;
   size_t smem = 0;
+  const int nC_ = H / GRU_HC;
+  // ---- preferred: K-split over 4-CTA clusters ----
+  if (g_gru_ksplit && H % 256 == 0 && nC_ % KS == 0 && (K3 / KS / 64) <= 16) {
+    const int nq = K3 / KS / 64;
+    const size_t ks_smem = (size_t)nq * Bp * 128 + (size_t)nq * 64 * 128 + (size_t)KS * Bp * 64 +
+                           1024 + 256;
+    if (ks_smem <= 227 * 1024) {
+      if (cudaMemsetAsync(barrier, 0, sizeof(unsigned int) * ndir, stream) != cudaSuccess)
+        return SB_ERR_CUDA;
+      CUtensorMap tq[2];
+      for (int d = 0; d < 2; ++d) {
+        const int dd = d < ndir ? d : 0;
+        rc = make_tmap_bf16_2d(&tq[d], p.xchg + (size_t)dd * 2 * Bp * K3, 2LL * Bp, K3, K3, Bp);
+        if (rc != SB_OK) return rc;
+      }
+      p.ring = nq; p.gc = 1;
+      void* kargs[] = {(void*)&tq[0], (void*)&tq[1], (void*)&p};
+      rc = gru_launch_exact((const void*)gru_bwd_ks_kernel, ndir * nC_, KS, ks_smem, kargs, stream);
+      if (rc == SB_OK) return SB_OK;
+    }
+  }
   p.ring = gru_ring_slots(std::max(nchunks * 16 * 128, 16384 - Bp * 128), Bp, nchunks, &p.gc, &smem);
   if (p.ring < 0) return SB_ERR_UNSUPPORTED;
   // per direction: the two parity buffers stacked as [2*Bp rows][3H cols]
