@@ -22,11 +22,19 @@ class CTC(model.Model):
     def forward_impl(self, x, softmax=False):
         if self.is_cuda:
             x = x.cuda(non_blocking=True)
-        x = self.encode(x)
-        x = self.fc(x)
+        x = self.encode_logits(x)
         if softmax:
             return torch.nn.functional.softmax(x, dim=2)
         return x
+
+    def encode_logits(self, x):
+        """encode + fc with the halves-sum and the projection fused into one contraction on the
+        bf16 top-layer output (same math as model.py:75-77 followed by ctc_model.py:29)."""
+        from .. import _lib, ops
+        _lib.require_cuda(x, "forward_impl() input")
+        x = ops.conv_stack(x, self.conv, self.training)
+        p = self.rnn.dropout if self.training else 0.0
+        return ops.gru_stack_logits(x, self.rnn, self.fc.fc, dropout=p)
 
     def loss(self, batch):
         x, y, x_lens, y_lens = self.collate(*batch)

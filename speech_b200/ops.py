@@ -102,7 +102,10 @@ class GRUStackFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, ndir, H, dropout, *weights):
+    def forward(ctx, x, ndir, H, dropout, fc_w, fc_b, *weights):
+        """fc_w/fc_b (optional): fuse `LinearND(sum of direction halves)` (reference
+        model.py:75-77 + ctc_model.py:29) as ONE contraction on the bf16 top-layer output:
+        (h_f + h_b) W^T = [h_f | h_b] [W | W]^T, written batch-first by the GEMM epilogue."""
         _lib.require_cuda(x, "x")
         lib = _lib.load()
         B, T, In = x.shape
@@ -113,13 +116,16 @@ class GRUStackFunction(torch.autograd.Function):
             raise _lib.SpeechB200Error("per-GPU batch > 128 not supported by the GRU kernel yet")
         M = T * Bp
         D = ndir * H
-        need_grad = any(w.requires_grad for w in weights) or x.requires_grad
+        need_grad = any(ctx.needs_input_grad)     # all False under torch.no_grad()
 
         # layer-0 operand: time-major, batch padded, K padded to a multiple of 8, bf16
         Inp = _round_up(In, 8)
-        X = torch.zeros(T, Bp, Inp, dtype=torch.bfloat16, device=dev)
-        X[:, :B, :In] = x.transpose(0, 1)
-        X = X.view(M, Inp)
+        if B == Bp and In == Inp:
+            X = x.detach().transpose(0, 1).to(torch.bfloat16).reshape(M, Inp)
+        else:
+            X = torch.zeros(T, Bp, Inp, dtype=torch.bfloat16, device=dev)
+            X[:, :B, :In] = x.transpose(0, 1)
+            X = X.view(M, Inp)
         barrier = torch.zeros(2, dtype=torch.int32, device=dev)
         saved = []
         y = None
@@ -158,7 +164,17 @@ class GRUStackFunction(torch.autograd.Function):
         ctx.saved = saved
         ctx.weights = weights
         ctx.dims = (B, T, In, Bp, H, ndir, L)
-        ctx.top_bf16 = X  # bf16 copy of the top layer output (time-major), used by fused heads
+        ctx.fc = None
+        if fc_w is not None:
+            V = fc_w.shape[0]
+            wcat = fc_w.detach().to(torch.bfloat16)
+            if ndir == 2:
+                wcat = torch.cat([wcat, wcat], 1)
+            wcat = wcat.contiguous()
+            out = gemm_bf16_tn(X, wcat, bias=fc_b.detach().float().contiguous(),
+                               remap=(Bp, T, B)).view(B, T, V)
+            ctx.fc = (fc_w, X)
+            return out
         out = y.view(T, Bp, D)[:, :B].transpose(0, 1).contiguous()
         return out
 
@@ -171,9 +187,31 @@ class GRUStackFunction(torch.autograd.Function):
         M = T * Bp
         D = ndir * H
         K3 = 3 * H
-        dY = torch.zeros(T, Bp, D, dtype=torch.float32, device=dev)
-        dY[:, :B] = dout.transpose(0, 1)
-        dY = dY.view(M, D)
+        dfc_w = dfc_b = None
+        if ctx.fc is not None:
+            fc_w, Xtop = ctx.fc
+            V = fc_w.shape[0]
+            Vp = _round_up(V, 8)
+            dl = torch.zeros(T, Bp, Vp, dtype=torch.bfloat16, device=dev)
+            dl[:, :B, :V] = dout.transpose(0, 1)
+            dl = dl.view(M, Vp)
+            w = fc_w.detach().to(torch.bfloat16)
+            wT = torch.zeros(D, Vp, dtype=torch.bfloat16, device=dev)      # [D][Vp] = [W | W]^T
+            for d in range(ndir):
+                wT[d * H:(d + 1) * H, :V] = w.t()
+            dY = gemm_bf16_tn(dl, wT)                                         # [M][D] f32
+            top_xnT = ctx.saved[L - 1][3]
+            dw2 = torch.zeros(Vp, D, dtype=torch.float32, device=dev)
+            gemm_bf16_tn(dl.t().contiguous(), top_xnT[:, Bp:Bp + M], out=dw2, accumulate=True,
+                         split_k=_wgrad_split(Vp, D, M))
+            dfc_w = dw2[:V, :H] if ndir == 1 else dw2[:V, :H] + dw2[:V, H:]
+            dfc_b = dout.sum((0, 1))
+        elif B == Bp:
+            dY = dout.transpose(0, 1).reshape(M, D).float()
+        else:
+            dY = torch.zeros(T, Bp, D, dtype=torch.float32, device=dev)
+            dY[:, :B] = dout.transpose(0, 1)
+            dY = dY.view(M, D)
         barrier = torch.zeros(2, dtype=torch.int32, device=dev)
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.sb_gru_bwd_workspace_size(Bp, H, ndir, ctypes.byref(nbytes)), "ws")
@@ -228,7 +266,28 @@ class GRUStackFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = dY.view(T, Bp, -1)[:, :B, :In].transpose(0, 1).contiguous()
         ctx.saved = None
-        return (dx, None, None, None) + tuple(grads)
+        return (dx, None, None, None, dfc_w, dfc_b) + tuple(grads)
+
+
+def _gru_weights(rnn):
+    ndir = 2 if rnn.bidirectional else 1
+    weights = []
+    for l in range(rnn.num_layers):
+        for d in range(ndir):
+            sfx = "_l%d%s" % (l, "_reverse" if d == 1 else "")
+            if not rnn.bias:
+                raise _lib.SpeechB200Error("GRU without bias is not supported")
+            weights += [getattr(rnn, "weight_ih" + sfx), getattr(rnn, "weight_hh" + sfx),
+                        getattr(rnn, "bias_ih" + sfx), getattr(rnn, "bias_hh" + sfx)]
+    return ndir, weights
+
+
+def gru_stack_logits(x, rnn, fc, dropout=0.0):
+    """GRU stack + sum of direction halves + output projection `fc` (an nn.Linear), fused:
+    returns logits (B, T, V) - the encoder tail of CTC.forward_impl (ctc_model.py:25-32)."""
+    ndir, weights = _gru_weights(rnn)
+    return GRUStackFunction.apply(x, ndir, rnn.hidden_size, float(dropout), fc.weight, fc.bias,
+                                  *weights)
 
 
 def gru_stack(x, rnn, dropout=0.0):
@@ -242,7 +301,7 @@ def gru_stack(x, rnn, dropout=0.0):
                 raise _lib.SpeechB200Error("GRU without bias is not supported")
             weights += [getattr(rnn, "weight_ih" + sfx), getattr(rnn, "weight_hh" + sfx),
                         getattr(rnn, "bias_ih" + sfx), getattr(rnn, "bias_hh" + sfx)]
-    return GRUStackFunction.apply(x, ndir, rnn.hidden_size, float(dropout), *weights)
+    return GRUStackFunction.apply(x, ndir, rnn.hidden_size, float(dropout), None, None, *weights)
 
 
 def conv_stack(x, conv, training):
