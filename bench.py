@@ -197,7 +197,7 @@ def run_ours(args):
     import torch.distributed as dist
     from speech_b200 import _lib, ops
     from speech_b200.models import CTC
-    from speech_b200.parallel import GradSync
+    from speech_b200.optim import FlatSGD
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,8 +212,9 @@ def run_ours(args):
     torch.manual_seed(0)
     model = CTC(F_IN, VOCAB, MODEL_CFG).cuda()
     model.set_train()
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.0)
-    sync = GradSync(model, world)
+    # clip(200) + SGD(lr 1e-3, momentum 0) of train.py:32-35,95-97, fused over flat buffers;
+    # step() also performs the data-parallel gradient all-reduce (one NCCL call)
+    opt = FlatSGD(model, lr=1e-3, momentum=0.0, max_grad_norm=200.0, world_size=world)
     inputs, labels = synth_batch(GLOBAL_B)
     inputs = inputs[rank * nutt:(rank + 1) * nutt]
     labels = labels[rank * nutt:(rank + 1) * nutt]
@@ -226,8 +227,6 @@ def run_ours(args):
         out = model.forward_impl(x_dev)
         loss = model.ctc_loss(out, y, x_lens, y_lens)
         loss.backward()
-        sync.all_reduce()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 200)
         opt.step()
         return loss
 
@@ -235,8 +234,6 @@ def run_ours(args):
         opt.zero_grad(set_to_none=False)
         loss = model.loss(batch)          # host numpy in: pinned staging + H2D inside
         loss.backward()
-        sync.all_reduce()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 200)
         opt.step()
         return loss.item()                # D2H read of the step's result
 

@@ -120,6 +120,31 @@ int sb_ctc_prefix_beam(const float* logp, const int* lens, int B, int T, int S, 
                        int blank, int* out_labels, int* out_lens, double* out_scores,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Tail of the training step over flat fp32 buffers.
+ * Replaces: nn.utils.clip_grad_norm(model.parameters(), 200) + torch.optim.SGD.step()
+ *           (train.py:32-35, 95-97).
+ *   sb_sumsq          out[0] = sum(g^2)                       (one pass over the gradient)
+ *   sb_sgd_clip_step  c = min(1, max_norm/(sqrt(sumsq)+1e-6)); [m = momentum*m + c*g]; p -= lr*(m|c*g)
+ *                     the clip coefficient is read from device memory (no host sync)
+ * ------------------------------------------------------------------------------------- */
+int sb_sumsq(const float* g, long long n, float* out, void* stream);
+int sb_sgd_clip_step(float* params, const float* grads, float* momentum_buf, long long n,
+                     const float* sumsq, float lr, float momentum, float max_norm, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * One decoder step of the additive location-aware attention (forward only, decode path).
+ * Replaces: NNAttention.forward (speech/models/seq2seq.py:344-360) inside Seq2Seq.decode_step
+ *           (:114-137), i.e. infer (:162-178) and beam_search (:180-227).
+ *   eh (B,T,H) encoder states; dhx (B,H) decoder state; ax_prev (B,T) previous alignment or NULL
+ *   conv_w (H,Kc), conv_b (H): Conv1d(1,H,Kc,'same') over ax_prev; lin_w (H), lin_b: Linear(H,1)
+ *   log_t != 0: scores are multiplied by log(T) before the softmax
+ *   out: sx (B,H) = sum_t ax_t eh_t ; ax (B,T) = softmax over time
+ * ------------------------------------------------------------------------------------- */
+int sb_attn_step(const float* eh, const float* dhx, const float* ax_prev, const float* conv_w,
+                 const float* conv_b, const float* lin_w, float lin_b, int log_t, int B, int T,
+                 int H, int Kc, float* sx, float* ax, void* stream);
+
 /* Beam expand/prune of Seq2Seq.beam_search (speech/models/seq2seq.py:200-212): indices and values
  * of the k best of n float64 scores, ordered by (score descending, index ascending) - the order of
  * the reference's stable sort over (beam, vocab) candidates. */

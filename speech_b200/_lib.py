@@ -28,6 +28,10 @@ SIGNATURES = {
     "sb_ctc_prefix_beam_workspace_size": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_sz)]),
     "sb_ctc_prefix_beam": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp,
                                     _vp, _c_sz, _vp]),
+    "sb_sumsq": (_c_int, [_vp, _c_ll, _vp, _vp]),
+    "sb_sgd_clip_step": (_c_int, [_vp, _vp, _vp, _c_ll, _vp, _fl, _fl, _fl, _vp]),
+    "sb_attn_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _fl, _c_int, _c_int, _c_int, _c_int,
+                              _c_int, _vp, _vp, _vp]),
     "sb_beam_topk": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp]),
     "sb_rnnt_workspace_size": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_sz)]),
     "sb_rnnt_fwd_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,

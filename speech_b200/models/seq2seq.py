@@ -202,6 +202,10 @@ class NNAttention(nn.Module):
         self.log_t = log_t
 
     def forward(self, eh, dhx, ax=None):
+        if eh.is_cuda and not torch.is_grad_enabled():
+            # decode path: fused single-pass kernel (csrc/attn.cu)
+            from .. import ops
+            return ops.attn_step(eh, dhx, ax, self.conv, self.nn[1].fc, self.log_t)
         pax = eh + dhx
         if ax is not None:
             pax = pax + self.conv(ax.unsqueeze(dim=1)).transpose(1, 2)

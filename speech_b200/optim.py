@@ -1,0 +1,68 @@
+"""Fused tail of the training step: gradient-norm clip + SGD over flat buffers.
+
+Drop-in for the pair the reference uses (train.py:32-35,95-97):
+
+    grad_norm = nn.utils.clip_grad_norm(model.parameters(), 200)
+    optimizer.step()                       # torch.optim.SGD(lr, momentum)
+
+    opt = FlatSGD(model, lr=1e-3, momentum=0.0, max_grad_norm=200, world_size=1)
+    opt.zero_grad(); loss = model.loss(batch); loss.backward()
+    grad_norm = opt.step()                 # all-reduce (if world_size > 1) + clip + update
+
+Parameters and gradients are re-pointed to views of two contiguous fp32 buffers (state_dict names
+and values are unchanged), so zero_grad is one memset, the data-parallel all-reduce is one NCCL
+call, and clip + update are two kernels (csrc/elementwise.cu) with no host synchronisation: the
+clip coefficient stays on the device.  `step()` returns the pre-clip gradient norm as a 0-dim
+CUDA tensor (what train.py logs as grad_norm).
+"""
+import torch
+
+from . import _lib, ops
+
+
+class FlatSGD:
+    def __init__(self, model, lr, momentum=0.0, max_grad_norm=200.0, world_size=1, group=None):
+        self.lr = float(lr)
+        self.momentum = float(momentum)
+        self.max_norm = float(max_grad_norm)
+        self.world = world_size
+        self.group = group
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        _lib.require_cuda(self.params[0], "model parameters")
+        # 16-byte align every parameter inside the flat buffers
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4
+        self.n = n
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.mom = torch.zeros(n, dtype=torch.float32, device=dev) if self.momentum != 0 else None
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, offs):
+            view = self.flat_p[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_g.zero_()
+
+    def all_reduce(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+
+    def step(self):
+        lib = _lib.load()
+        self.all_reduce()
+        sp = _lib.stream_ptr()
+        ops._launch("sumsq", 0.0, lambda: lib.sb_sumsq(self.flat_g.data_ptr(), self.n,
+                                                       self.sumsq.data_ptr(), sp))
+        ops._launch("sgd_clip_step", 0.0,
+                    lambda: lib.sb_sgd_clip_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(),
+                                                 _lib.ptr(self.mom), self.n,
+                                                 self.sumsq.data_ptr(), self.lr, self.momentum,
+                                                 self.max_norm, sp))
+        return self.sumsq.sqrt().squeeze(0)
