@@ -18,6 +18,21 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+def _apply_env_knobs():
+    """Developer knobs (profiling under ncu cannot replay clustered cooperative launches):
+    SB_GRU_KSPLIT=0 disables the K-split backward kernel, SB_GRU_CLUSTER=<1|2|4|8> sets the
+    preferred cluster size of the other GRU kernels."""
+    import os
+    lib = _lib.load()
+    if os.environ.get("SB_GRU_KSPLIT") is not None:
+        lib.sb_debug_gru_ksplit(int(os.environ["SB_GRU_KSPLIT"]))
+    if os.environ.get("SB_GRU_CLUSTER") is not None:
+        lib.sb_debug_gru_cluster(int(os.environ["SB_GRU_CLUSTER"]))
+
+
+_knobs_applied = False
+
+
 # ---- optional per-kernel timing (CUDA events on the launching stream; used by bench.py) ----
 _prof = None
 
@@ -41,6 +56,10 @@ def profile_end():
 
 def _launch(name, flops, fn):
     """Run one C-ABI launch; counts it and, when profiling, brackets it with CUDA events."""
+    global _knobs_applied
+    if not _knobs_applied:
+        _knobs_applied = True
+        _apply_env_knobs()
     _lib.launch_count += 1
     if _prof is None:
         return _lib.check(fn(), name)
