@@ -1036,15 +1036,16 @@ static int gru_launch_exact(const void* kernel, int grid, int cs, size_t smem, v
   cfg.blockDim = dim3(GRU_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeCooperative;
-  attrs[0].val.cooperative = 1;
-  attrs[1].id = cudaLaunchAttributeClusterDimension;
-  attrs[1].val.clusterDim.x = cs;
-  attrs[1].val.clusterDim.y = 1;
-  attrs[1].val.clusterDim.z = 1;
+  // Clustered launches are NOT flagged cooperative: co-residency of the whole grid is established
+  // by the occupancy query below (1 CTA per SM, grid <= resident capacity), every spin-wait in
+  // the kernels is bounded, and Nsight Compute cannot replay cooperative+cluster launches.
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = cs;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = 1;
   int nclusters = 0;
   if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess ||
       nclusters * cs < grid) {
