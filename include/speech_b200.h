@@ -170,6 +170,8 @@ int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
 /* Developer hook (not part of the drop-in surface): device buffer of >= 64*16 uint64 receiving a
  * globaltimer timeline of CTA 0 for the next sb_gru_fwd launches; NULL disables. */
 int sb_debug_gru_timeline(void* dev_buffer);
+/* Developer hook: timing ablations of the forward GRU kernel (results become wrong; 0 = off). */
+int sb_debug_gru_flags(int flags);
 /* Developer hook: enable (1, default) / disable (0) the K-split backward GRU kernel. */
 int sb_debug_gru_ksplit(int enable);
 /* Developer hook: set the preferred thread-block-cluster size (1, 2, 4 or 8) of the GRU kernels;

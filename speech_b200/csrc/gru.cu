@@ -55,6 +55,7 @@ struct GruFwdParams {
   unsigned int* barrier;  // [ndir] zero-initialised counters
   unsigned long long* dbg;  // optional timeline (CTA 0): [step][16] globaltimer stamps, or null
   int T, Bp, H, ndir, ring, gc;   // ring: slots (groups of gc chunks) in shared memory
+  int ablate;          // developer timing ablations (results become WRONG): see sb_debug_gru_flags
 };
 
 struct GruBwdParams {
@@ -311,10 +312,11 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       for (int step = 1; step < T; ++step) {
         const int t = dir == 0 ? step : (T - 1 - step);
         const int tp = dir == 0 ? t - 1 : t + 1;
-        grid_wait(ctr, (unsigned int)nC * step);   // every CTA of this direction published h_{tp}
+        if (!(p.ablate & 16)) grid_wait(ctr, (unsigned int)nC * step);   // all CTAs published h_{tp}
         GRU_STAMP(0);
         // (the writers ran fence.proxy.async before their release; no reader-side proxy fence)
-        tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, p.gc, step - 1, crank, csize);
+        if (!(p.ablate & 4))
+          tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, p.gc, step - 1, crank, csize);
         GRU_STAMP(1);
       }
     }
@@ -322,6 +324,17 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       for (int step = 1; step < T; ++step) {
+        if (p.ablate & 8) continue;
+        if (p.ablate & 4) {   // no loads: issue the same MMAs on whatever is in the ring
+          constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 48);
+          for (int c = 0; c < nchunks; ++c)
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(smem_u32(s.ring)) + kk * 2,
+                           umma_desc_sw128_kmajor(smem_u32(s.wtile + c * WCHUNK)) + kk * 2, idesc,
+                           (c > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(s.accfull);
+          continue;
+        }
         mma_consume<48>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, p.gc, step - 1, csize);
         GRU_STAMP(2);
       }
@@ -351,7 +364,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       }
       float acc[3][GRU_UPT];
       if (step > 0) {
-        mbar_wait(s.accfull, (step - 1) & 1);
+        if (!(p.ablate & 8)) mbar_wait(s.accfull, (step - 1) & 1);
         if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
         uint32_t v[8];
@@ -385,7 +398,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         // critical path: only the bf16 h_t that the other CTAs gather next step
         *reinterpret_cast<uint4*>(p.xn + m * D + dir * H + ju) = pack8(hprev);
         if (tid == 0) GRU_STAMP(5);
-        fence_proxy_async_all();   // these generic-proxy writes are read by other CTAs' TMA
+        if (!(p.ablate & 1)) fence_proxy_async_all();   // generic writes -> other CTAs' TMA reads
         if (tid == 0) GRU_STAMP(6);
       }
       epi_barrier();
@@ -395,7 +408,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         GRU_STAMP(9);
       }
       // off the critical path: fp32 state, transposed copy, saved gates
-      if (active) {
+      if (active && !(p.ablate & 2)) {
         st8(p.y + m * D + dir * H + ju, hprev);
         if (p.xnT) {
           bf16* xt = p.xnT + (long long)(dir * H + ju) * ldT + (long long)(t + 1) * Bp + row;
@@ -1020,6 +1033,7 @@ static int gru_launch(const void* kernel, int grid, int cs, size_t smem, void** 
 }
 
 static unsigned long long* g_gru_dbg = nullptr;
+static int g_gru_ablate = 0;
 static int g_gru_ksplit = 1;   // developer knob: 0 disables the K-split backward kernel
 
 // cooperative launch with EXACTLY the given cluster size; fails if the grid is not co-resident
@@ -1069,6 +1083,12 @@ extern "C" int sb_debug_gru_timeline(void* dev_buffer) {
   sb::g_gru_dbg = reinterpret_cast<unsigned long long*>(dev_buffer);
   return SB_OK;
 }
+// timing ablations of gru_fwd (results become wrong): 1 no proxy fence, 2 no off-path stores,
+// 4 no TMA loads, 8 no MMA, 16 no grid-barrier wait
+extern "C" int sb_debug_gru_flags(int flags) {
+  sb::g_gru_ablate = flags;
+  return SB_OK;
+}
 extern "C" int sb_debug_gru_ksplit(int enable) {
   sb::g_gru_ksplit = enable ? 1 : 0;
   return SB_OK;
@@ -1101,6 +1121,7 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
   p.xn = reinterpret_cast<bf16*>(xn_bf16); p.xnT = reinterpret_cast<bf16*>(xnT_bf16);
   p.gates = gates; p.barrier = barrier; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
   p.dbg = g_gru_dbg;
+  p.ablate = g_gru_ablate;
   const int nchunks = (H + 63) / 64;
   size_t smem = 0;
   p.ring = gru_ring_slots(std::max(nchunks * 48 * 128, 16384 - Bp * 128), Bp, nchunks, &p.gc, &smem);
