@@ -97,6 +97,10 @@ SB_DEVINL void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 SB_DEVINL void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+SB_DEVINL void fence_proxy_async_global() {
+  // generic-proxy st.global -> async-proxy (TMA) readers of global memory
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 
 // ----------------------------------------------------------------------------------------------
 // TMA: tiled tensor loads (global -> shared), completion on an mbarrier

@@ -220,14 +220,22 @@ SB_DEVINL float fast_tanh(float x) {
   return 1.0f - __fdividef(2.0f, __expf(2.0f * xc) + 1.0f);
 }
 
+// One-touch data (gi, saved gates, dy, fp32 state, GEMM operands written for later kernels) uses
+// the streaming cache policy (.cs) so that it does not evict the latency-critical bf16 exchange
+// buffers, which every CTA re-reads from L2 each step.
 SB_DEVINL void ld8(const float* p, float (&v)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 SB_DEVINL void st8(float* p, const float (&v)[8]) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
+SB_DEVINL void st_stream_u4(void* p, uint4 v) { __stcs(reinterpret_cast<uint4*>(p), v); }
+SB_DEVINL void st_stream_bf16(bf16* p, float v) {
+  const unsigned short u = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"(u) : "memory");
 }
 SB_DEVINL uint4 pack8(const float (&v)[8]) {
   uint4 r;
@@ -398,7 +406,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         // critical path: only the bf16 h_t that the other CTAs gather next step
         *reinterpret_cast<uint4*>(p.xn + m * D + dir * H + ju) = pack8(hprev);
         if (tid == 0) GRU_STAMP(5);
-        if (!(p.ablate & 1)) fence_proxy_async_all();   // generic writes -> other CTAs' TMA reads
+        if (!(p.ablate & 1)) fence_proxy_async_global();   // generic writes -> other CTAs' TMA reads
         if (tid == 0) GRU_STAMP(6);
       }
       epi_barrier();
@@ -413,7 +421,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         if (p.xnT) {
           bf16* xt = p.xnT + (long long)(dir * H + ju) * ldT + (long long)(t + 1) * Bp + row;
 #pragma unroll
-          for (int jj = 0; jj < GRU_UPT; ++jj) xt[jj * ldT] = __float2bfloat16_rn(hprev[jj]);
+          for (int jj = 0; jj < GRU_UPT; ++jj) st_stream_bf16(xt + jj * ldT, hprev[jj]);
         }
         if (p.gates) {
           float* go = p.gates + ((m * p.ndir + dir) * 4) * H + ju;
@@ -580,7 +588,7 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
           *reinterpret_cast<uint4*>(x + H) = pack8(dz);
           *reinterpret_cast<uint4*>(x + 2 * H) = pack8(dnr);
           if (tid == 0) GRU_STAMP(5);
-          fence_proxy_async_all();
+          fence_proxy_async_global();
           if (tid == 0) GRU_STAMP(6);
         }
       }
@@ -595,17 +603,17 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       // ---- off the critical path: operands of the dX / dW GEMMs ----
       if (active) {
         bf16* o = p.dgi + m * (p.ndir * K3) + dir * K3 + ju;
-        *reinterpret_cast<uint4*>(o) = pack8(dr);
-        *reinterpret_cast<uint4*>(o + H) = pack8(dz);
-        *reinterpret_cast<uint4*>(o + 2 * H) = pack8(dn);
+        st_stream_u4(o, pack8(dr));
+        st_stream_u4(o + H, pack8(dz));
+        st_stream_u4(o + 2 * H, pack8(dn));
         bf16* gt = p.dgiT + ((long long)dir * K3 + ju) * M + m;
         bf16* nt = p.dghnT + ((long long)dir * H + ju) * M + m;
 #pragma unroll
         for (int jj = 0; jj < GRU_UPT; ++jj) {
-          gt[(long long)jj * M] = __float2bfloat16_rn(dr[jj]);
-          gt[(long long)(H + jj) * M] = __float2bfloat16_rn(dz[jj]);
-          gt[(long long)(2 * H + jj) * M] = __float2bfloat16_rn(dn[jj]);
-          nt[(long long)jj * M] = __float2bfloat16_rn(dnr[jj]);
+          st_stream_bf16(gt + (long long)jj * M, dr[jj]);
+          st_stream_bf16(gt + (long long)(H + jj) * M, dz[jj]);
+          st_stream_bf16(gt + (long long)(2 * H + jj) * M, dn[jj]);
+          st_stream_bf16(nt + (long long)jj * M, dnr[jj]);
         }
       }
       if (tid == 0) GRU_STAMP(10);
@@ -892,7 +900,7 @@ gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
           *reinterpret_cast<uint4*>(x + H) = pack8(dz);
           *reinterpret_cast<uint4*>(x + 2 * H) = pack8(dnr);
           if (tid == 0) GRU_STAMP(5);
-          fence_proxy_async_all();
+          fence_proxy_async_global();
           if (tid == 0) GRU_STAMP(6);
         }
       }
@@ -906,17 +914,17 @@ gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
       }
       if (active) {
         bf16* o = p.dgi + m * (p.ndir * K3) + dir * K3 + ju;
-        *reinterpret_cast<uint4*>(o) = pack8(dr);
-        *reinterpret_cast<uint4*>(o + H) = pack8(dz);
-        *reinterpret_cast<uint4*>(o + 2 * H) = pack8(dn);
+        st_stream_u4(o, pack8(dr));
+        st_stream_u4(o + H, pack8(dz));
+        st_stream_u4(o + 2 * H, pack8(dn));
         bf16* gt = p.dgiT + ((long long)dir * K3 + ju) * M + m;
         bf16* nt = p.dghnT + ((long long)dir * H + ju) * M + m;
 #pragma unroll
         for (int jj = 0; jj < GRU_UPT; ++jj) {
-          gt[(long long)jj * M] = __float2bfloat16_rn(dr[jj]);
-          gt[(long long)(H + jj) * M] = __float2bfloat16_rn(dz[jj]);
-          gt[(long long)(2 * H + jj) * M] = __float2bfloat16_rn(dn[jj]);
-          nt[(long long)jj * M] = __float2bfloat16_rn(dnr[jj]);
+          st_stream_bf16(gt + (long long)jj * M, dr[jj]);
+          st_stream_bf16(gt + (long long)(H + jj) * M, dz[jj]);
+          st_stream_bf16(gt + (long long)(2 * H + jj) * M, dn[jj]);
+          st_stream_bf16(nt + (long long)jj * M, dnr[jj]);
         }
       }
       if (tid == 0) GRU_STAMP(10);

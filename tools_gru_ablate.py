@@ -11,7 +11,10 @@ names = {0: "baseline", 1: "no proxy fence", 2: "no off-path stores", 3: "no fen
          4: "no TMA loads", 8: "no MMA (no accfull wait)", 12: "no TMA, no MMA",
          16: "no grid-barrier wait", 28: "no barrier wait, no TMA, no MMA",
          31: "epilogue + arrive only"}
+sel = [int(a) for a in sys.argv[1:]] or list(names)
 for flags, name in names.items():
+    if flags not in sel:
+        continue
     lib.sb_debug_gru_flags(flags)
     with torch.no_grad():
         for _ in range(2):
@@ -21,5 +24,5 @@ for flags, name in names.items():
             ops.gru_stack(x, rnn)
         prof = ops.profile_end()
     n, ms, _ = prof["gru_fwd"]
-    print("%-36s %.2f us/step" % (name, ms / n / T * 1e3))
+    print("%-36s %.2f us/step" % (name, ms / n / T * 1e3), flush=True)
 lib.sb_debug_gru_flags(0)
