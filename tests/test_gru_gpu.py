@@ -58,3 +58,13 @@ def test_gru_north_star_width_short(cuda_lib):
     for (n, p64), (_, pc) in zip(rnn64.named_parameters(), rnn_c.named_parameters()):
         ref = p64.grad
         assert (pc.grad.double().cpu() - ref).abs().max().item() < 3e-2 * ref.abs().max().item() + 1e-4, n
+
+
+@pytest.mark.parametrize("B", [8, 16, 32])
+def test_gru_north_star_width_small_batches(cuda_lib, B):
+    """per-rank batches of the 8/4/2-GPU strong-scaling runs (64/N) at H=1024."""
+    rnn64, x64, y64, rnn_c, xc, yc = _ref_and_ours(B, 5, 480, 1024, 1, True, seed=B)
+    assert (yc.double().cpu() - y64).abs().max().item() < 2e-2
+    for (n, p64), (_, pc) in zip(rnn64.named_parameters(), rnn_c.named_parameters()):
+        ref = p64.grad
+        assert (pc.grad.double().cpu() - ref).abs().max().item() < 3e-2 * ref.abs().max().item() + 1e-4, n
