@@ -121,6 +121,29 @@ int sb_ctc_prefix_beam(const float* logp, const int* lens, int B, int T, int S, 
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Conv2d(+ReLU) front-end as im2col + sb_gemm_bf16_tn.
+ * Replaces: the cuDNN convolutions behind nn.Conv2d in Model.encode
+ *           (speech/models/model.py:19-29,60-71; valid conv, kernel (kh,kw), stride s both dims).
+ * Activations are pixel-major channels-last f32 P[(b*To+t)*Fo+f][c] (= the GEMM's C matrix, ReLU
+ * applied on read); the im2col matrix is A[m][(i*kw+j)*Ci+ci] bf16 with K padded to Kp.
+ *   sb_conv_im2col       src P (or the (B,T,F) input with Ci=1) -> A
+ *   sb_conv_relu_to_bct  C of the last layer -> (B, To, Co*Fo) f32 with ReLU (model.py:66-71)
+ *   sb_conv_dtop         dY (B,To,Co*Fo) * (C>0) -> dC bf16 [M][Co]; db[c] += column sums
+ *   sb_conv_col2im_relu  dA f32 [M][ldA] -> dC of the layer below (gather, masked by Pprev>0)
+ *   sb_transpose_bf16    [R][C] -> [C][R] (weight-gradient operands)
+ * ------------------------------------------------------------------------------------- */
+int sb_conv_im2col(const float* src, void* dst_bf16, int B, int Ti, int Fi, int Ci, int kh, int kw,
+                   int stride, int Kp, int relu, void* stream);
+int sb_conv_relu_to_bct(const float* C, float* out, int B, int To, int Fo, int Co, void* stream);
+int sb_conv_dtop(const float* dY, const float* C, void* dC_bf16, float* db, int B, int To, int Fo,
+                 int Co, void* stream);
+int sb_conv_col2im_relu(const float* dA, long long ldA, const float* Pprev, void* dCprev_bf16,
+                        float* db, int B, int Ti, int Fi, int Ci, int kh, int kw, int stride,
+                        void* stream);
+int sb_transpose_bf16(const void* src, void* dst, long long R, int C, long long ld_src,
+                      long long ld_dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Tail of the training step over flat fp32 buffers.
  * Replaces: nn.utils.clip_grad_norm(model.parameters(), 200) + torch.optim.SGD.step()
  *           (train.py:32-35, 95-97).

@@ -323,54 +323,127 @@ def gru_stack(x, rnn, dropout=0.0):
     return GRUStackFunction.apply(x, ndir, rnn.hidden_size, float(dropout), None, None, *weights)
 
 
+def _transpose_bf16(src, rows_pad=8):
+    """[R][C] bf16 -> [C][Rp] bf16 (Rp = R rounded up so that rows stay 16-byte aligned)."""
+    lib = _lib.load()
+    R, C = src.shape
+    Rp = _round_up(R, rows_pad)
+    dst = torch.zeros(C, Rp, dtype=torch.bfloat16, device=src.device) if Rp != R else \
+        torch.empty(C, Rp, dtype=torch.bfloat16, device=src.device)
+    sp = _lib.stream_ptr()
+    _launch("transpose_bf16", 0.0,
+            lambda: lib.sb_transpose_bf16(src.data_ptr(), dst.data_ptr(), R, C, src.stride(0),
+                                          dst.stride(0), sp))
+    return dst[:, :R]
+
+
+class ConvStackFunction(torch.autograd.Function):
+    """Conv2d+ReLU stack as im2col + tcgen05 GEMM (csrc/conv.cu, csrc/gemm.cu).
+
+    forward(x (B,T,F) f32, specs ((kh,kw,s),...), w0, b0, w1, b1, ...) -> (B, T', C*F') f32 with
+    the reference's channel-major feature order (model.py:66-71)."""
+
+    @staticmethod
+    def forward(ctx, x, specs, *params):
+        _lib.require_cuda(x, "x")
+        lib = _lib.load()
+        dev = x.device
+        B, Ti, Fi = x.shape
+        Ci = 1
+        cur = x.detach().float().contiguous()
+        saved = []
+        need_grad = any(ctx.needs_input_grad)
+        sp = _lib.stream_ptr()
+        for l, (kh, kw, s_) in enumerate(specs):
+            w, b = params[2 * l], params[2 * l + 1]
+            Co = w.shape[0]
+            if Co % 8 != 0:
+                raise _lib.SpeechB200Error("conv out_channels must be a multiple of 8")
+            K = kh * kw * Ci
+            Kp = _round_up(K, 8)
+            To, Fo = (Ti - kh) // s_ + 1, (Fi - kw) // s_ + 1
+            M = B * To * Fo
+            A = torch.empty(M, Kp, dtype=torch.bfloat16, device=dev)
+            src = cur
+            _launch("conv_im2col", 0.0,
+                    lambda: lib.sb_conv_im2col(src.data_ptr(), A.data_ptr(), B, Ti, Fi, Ci, kh, kw,
+                                               s_, Kp, 1 if l > 0 else 0, sp))
+            Wp = torch.zeros(Co, Kp, dtype=torch.bfloat16, device=dev)
+            Wp[:, :K] = w.detach().permute(0, 2, 3, 1).reshape(Co, K)
+            C = gemm_bf16_tn(A, Wp, bias=b.detach().float().contiguous())
+            if need_grad:
+                saved.append((A, cur, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp)))
+            cur, Ti, Fi, Ci = C, To, Fo, Co
+        out = torch.empty(B, Ti, Ci * Fi, dtype=torch.float32, device=dev)
+        _launch("conv_relu_to_bct", 0.0,
+                lambda: lib.sb_conv_relu_to_bct(cur.data_ptr(), out.data_ptr(), B, Ti, Fi, Ci, sp))
+        ctx.saved = saved
+        ctx.B = B
+        ctx.nl = len(specs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dY):
+        lib = _lib.load()
+        dev = dY.device
+        B = ctx.B
+        sp = _lib.stream_ptr()
+        grads = [None] * (2 * ctx.nl)
+        dY = dY.contiguous().float()
+        dC = None
+        for l in reversed(range(ctx.nl)):
+            A, Pprev, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp) = ctx.saved[l]
+            M = B * To * Fo
+            if dC is None:
+                dC = torch.empty(M, Co, dtype=torch.bfloat16, device=dev)
+                db = torch.zeros(Co, dtype=torch.float32, device=dev)
+                dCl = dC
+                _launch("conv_dtop", 0.0,
+                        lambda: lib.sb_conv_dtop(dY.data_ptr(), C.data_ptr(), dCl.data_ptr(),
+                                                 db.data_ptr(), B, To, Fo, Co, sp))
+            grads[2 * l + 1] = db
+            # weight gradient: dWp[Co][Kp] = dC^T [Co][M] . A^T [Kp][M]^T   (K = M, split-K)
+            dCT = _transpose_bf16(dC)
+            AT = _transpose_bf16(A)
+            dWp = torch.zeros(Co, Kp, dtype=torch.float32, device=dev)
+            gemm_bf16_tn(dCT, AT, out=dWp, accumulate=True, split_k=_wgrad_split(Co, Kp, M))
+            grads[2 * l] = dWp[:, :K].reshape(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
+            if l > 0:
+                WpT = Wp.t().contiguous()                       # [Kp][Co]
+                dA = gemm_bf16_tn(dC, WpT)                      # [M][Kp] f32
+                Mp = B * Ti * Fi
+                dCp = torch.empty(Mp, Ci, dtype=torch.bfloat16, device=dev)
+                db = torch.zeros(Ci, dtype=torch.float32, device=dev)
+                _launch("conv_col2im_relu", 0.0,
+                        lambda: lib.sb_conv_col2im_relu(dA.data_ptr(), dA.stride(0),
+                                                        Pprev.data_ptr(), dCp.data_ptr(),
+                                                        db.data_ptr(), B, Ti, Fi, Ci, kh, kw, s_,
+                                                        sp))
+                dC = dCp
+        ctx.saved = None
+        return (None, None) + tuple(grads)
+
+
 def conv_stack(x, conv, training):
     """Conv2d+ReLU(+Dropout) front-end of the encoder (reference model.py:19-29,60-71).
 
     x (B, T, F) -> (B, T', C*F') with the reference's channel-major feature flattening
-    (transpose(1,2) of (B,C,T',F') then view, model.py:66-71).
-    INTERIM (round 1): runs the nn.Conv2d modules through cuDNN; <1% of the step FLOPs.
-    The hand-written implicit-GEMM conv is listed as the next kernel in DESIGN.md.
+    (transpose(1,2) of (B,C,T',F') then view, model.py:66-71).  Runs on our im2col + tcgen05
+    kernels; only a stack with ACTIVE conv dropout (training and p > 0) still goes through the
+    nn modules (cuDNN), because the dropout mask sits between ReLU and the next im2col.
     """
+    mods = list(conv.children())
+    convs = [m for m in mods if isinstance(m, torch.nn.Conv2d)]
+    drop = any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in mods) and training
+    simple = all(c.stride[0] == c.stride[1] and c.padding == (0, 0) and c.dilation == (1, 1)
+                 and c.groups == 1 and c.bias is not None and c.out_channels % 8 == 0
+                 for c in convs)
+    if convs and simple and not drop:
+        specs = tuple((c.kernel_size[0], c.kernel_size[1], c.stride[0]) for c in convs)
+        params = []
+        for c in convs:
+            params += [c.weight, c.bias]
+        return ConvStackFunction.apply(x, specs, *params)
     y = conv(x.unsqueeze(1))
     b, c, t, f = y.shape
     return y.transpose(1, 2).reshape(b, t, c * f)
-
-
-def beam_topk(scores, k):
-    """Top-k of a float64 CUDA score matrix in the reference's stable-sort order (score
-    descending, flat index ascending).  Returns (list of flat indices, list of scores)."""
-    _lib.require_cuda(scores, "scores")
-    lib = _lib.load()
-    sc = scores.detach().double().contiguous().reshape(-1)
-    n = sc.numel()
-    idx = torch.empty(k, dtype=torch.int32, device=sc.device)
-    val = torch.empty(k, dtype=torch.float64, device=sc.device)
-    sp = _lib.stream_ptr()
-    _launch("beam_topk", 0.0,
-            lambda: lib.sb_beam_topk(sc.data_ptr(), n, k, idx.data_ptr(), val.data_ptr(), sp))
-    return idx.cpu().tolist(), val.cpu().tolist()
-
-
-def attn_step(eh, dhx, ax_prev, conv, lin, log_t):
-    """Fused NNAttention forward for the decode path (no autograd).  eh (B,T,H), dhx (B,1,H) or
-    (B,H), ax_prev (B,T) or None; conv = nn.Conv1d(1,H,Kc), lin = nn.Linear(H,1).
-    Returns (sx (B,1,H), ax (B,T)) like the reference module."""
-    _lib.require_cuda(eh, "eh")
-    lib = _lib.load()
-    eh = eh.detach().float().contiguous()
-    B, T, H = eh.shape
-    d = dhx.detach().float().reshape(B, H).contiguous()
-    axp = None if ax_prev is None else ax_prev.detach().float().contiguous()
-    cw = conv.weight.detach().float().reshape(H, -1).contiguous()
-    Kc = cw.shape[1]
-    cb = conv.bias.detach().float().contiguous()
-    lw = lin.weight.detach().float().reshape(-1).contiguous()
-    lb = float(lin.bias.detach().float().item()) if lin.bias is not None else 0.0
-    sx = torch.empty(B, H, dtype=torch.float32, device=eh.device)
-    ax = torch.empty(B, T, dtype=torch.float32, device=eh.device)
-    sp = _lib.stream_ptr()
-    _launch("attn_step", 0.0,
-            lambda: lib.sb_attn_step(eh.data_ptr(), d.data_ptr(), _lib.ptr(axp), cw.data_ptr(),
-                                     cb.data_ptr(), lw.data_ptr(), lb, 1 if log_t else 0, B, T, H,
-                                     Kc, sx.data_ptr(), ax.data_ptr(), sp))
-    return sx.unsqueeze(1), ax

@@ -1,0 +1,45 @@
+"""GPU parity: im2col + tcgen05 conv stack vs torch.nn.Conv2d (fp64 on CPU).
+Operands are rounded to bf16 (fp32 accumulation), so outputs are compared at 2% of the largest
+output magnitude and gradients at 3% of the largest reference gradient entry."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(specs, in_c=1):
+    layers = []
+    for out_c, h, w, s in specs:
+        layers += [torch.nn.Conv2d(in_c, out_c, (h, w), stride=(s, s)), torch.nn.ReLU()]
+        in_c = out_c
+    return torch.nn.Sequential(*layers)
+
+
+@pytest.mark.parametrize("specs,B,T,F", [
+    ([[32, 5, 32, 2]], 4, 100, 40),                      # tests/shared.py tiny config
+    ([[8, 5, 8, 2], [8, 5, 8, 2]], 3, 61, 80),          # golden 'bi' config
+    ([[32, 5, 8, 2], [32, 5, 8, 2]], 2, 90, 80),        # north-star conv stack (WSJ)
+    ([[16, 3, 4, 1], [8, 2, 3, 3]], 2, 33, 21),          # odd geometry, stride 1 and 3
+])
+def test_conv_stack_forward_backward(cuda_lib, specs, B, T, F):
+    from speech_b200 import ops
+    torch.manual_seed(B + T + F)
+    conv = _build(specs)
+    x = torch.randn(B, T, F)
+    conv64 = _build(specs).double()
+    conv64.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
+    y64 = conv64(x.double().unsqueeze(1))
+    b, c, t, f = y64.shape
+    y64 = y64.transpose(1, 2).reshape(b, t, c * f)
+    w = torch.randn_like(y64)
+    (y64 * w).sum().backward()
+    conv_c = conv.cuda()
+    y = ops.conv_stack(x.cuda(), conv_c, True)
+    assert y.shape == y64.shape
+    (y * w.float().cuda()).sum().backward()
+    scale = y64.abs().max().item()
+    assert (y.double().cpu() - y64).abs().max().item() < 2e-2 * scale
+    for (n, p64), (_, pc) in zip(conv64.named_parameters(), conv_c.named_parameters()):
+        ref = p64.grad
+        err = (pc.grad.double().cpu() - ref).abs().max().item()
+        assert err < 3e-2 * ref.abs().max().item() + 1e-4, (n, err, ref.abs().max().item())
