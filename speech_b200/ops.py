@@ -447,3 +447,43 @@ def conv_stack(x, conv, training):
     y = conv(x.unsqueeze(1))
     b, c, t, f = y.shape
     return y.transpose(1, 2).reshape(b, t, c * f)
+
+
+def beam_topk(scores, k):
+    """Top-k of a float64 CUDA score matrix in the reference's stable-sort order (score
+    descending, flat index ascending).  Returns (list of flat indices, list of scores)."""
+    _lib.require_cuda(scores, "scores")
+    lib = _lib.load()
+    sc = scores.detach().double().contiguous().reshape(-1)
+    n = sc.numel()
+    idx = torch.empty(k, dtype=torch.int32, device=sc.device)
+    val = torch.empty(k, dtype=torch.float64, device=sc.device)
+    sp = _lib.stream_ptr()
+    _launch("beam_topk", 0.0,
+            lambda: lib.sb_beam_topk(sc.data_ptr(), n, k, idx.data_ptr(), val.data_ptr(), sp))
+    return idx.cpu().tolist(), val.cpu().tolist()
+
+
+def attn_step(eh, dhx, ax_prev, conv, lin, log_t):
+    """Fused NNAttention forward for the decode path (no autograd).  eh (B,T,H), dhx (B,1,H) or
+    (B,H), ax_prev (B,T) or None; conv = nn.Conv1d(1,H,Kc), lin = nn.Linear(H,1).
+    Returns (sx (B,1,H), ax (B,T)) like the reference module."""
+    _lib.require_cuda(eh, "eh")
+    lib = _lib.load()
+    eh = eh.detach().float().contiguous()
+    B, T, H = eh.shape
+    d = dhx.detach().float().reshape(B, H).contiguous()
+    axp = None if ax_prev is None else ax_prev.detach().float().contiguous()
+    cw = conv.weight.detach().float().reshape(H, -1).contiguous()
+    Kc = cw.shape[1]
+    cb = conv.bias.detach().float().contiguous()
+    lw = lin.weight.detach().float().reshape(-1).contiguous()
+    lb = float(lin.bias.detach().float().item()) if lin.bias is not None else 0.0
+    sx = torch.empty(B, H, dtype=torch.float32, device=eh.device)
+    ax = torch.empty(B, T, dtype=torch.float32, device=eh.device)
+    sp = _lib.stream_ptr()
+    _launch("attn_step", 0.0,
+            lambda: lib.sb_attn_step(eh.data_ptr(), d.data_ptr(), _lib.ptr(axp), cw.data_ptr(),
+                                     cb.data_ptr(), lw.data_ptr(), lb, 1 if log_t else 0, B, T, H,
+                                     Kc, sx.data_ptr(), ax.data_ptr(), sp))
+    return sx.unsqueeze(1), ax
