@@ -1,6 +1,13 @@
-"""GPU parity: im2col + tcgen05 conv stack vs torch.nn.Conv2d (fp64 on CPU).
-Operands are rounded to bf16 (fp32 accumulation), so outputs are compared at 2% of the largest
-output magnitude and gradients at 3% of the largest reference gradient entry."""
+"""GPU parity: im2col + tcgen05 conv stack vs torch conv2d in fp64 on the CPU.
+
+The kernels round the GEMM operands (inputs, weights, inter-layer activations) to bf16 and
+accumulate in fp32.  A ReLU mask is discontinuous, so a reference computed from UN-rounded operands
+flips the mask of the few pre-activations that lie within the rounding error of zero and its
+gradient then differs by O(1) on those elements (measured: ~0.3 % of elements, 6 % of the largest
+gradient entry under a white-noise upstream gradient) - that is a property of bf16 arithmetic, not
+of the kernels.  The reference here therefore applies the SAME operand rounding (straight-through
+in backward) and is otherwise exact (fp64): outputs must agree to 1e-3 of the output scale,
+gradients to 3 % of the largest reference entry (bf16 rounding of the backward operands)."""
 import pytest
 import torch
 
@@ -28,7 +35,18 @@ def test_conv_stack_forward_backward(cuda_lib, specs, B, T, F):
     x = torch.randn(B, T, F)
     conv64 = _build(specs).double()
     conv64.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
-    y64 = conv64(x.double().unsqueeze(1))
+
+    def rnd(t):   # bf16 rounding with a straight-through gradient
+        return t + (t.detach().float().bfloat16().double() - t.detach())
+
+    h = rnd(x.double().unsqueeze(1))
+    mods = [m for m in conv64 if isinstance(m, torch.nn.Conv2d)]
+    for li, m in enumerate(mods):
+        pre = torch.nn.functional.conv2d(h, rnd(m.weight), m.bias, stride=m.stride)
+        h = torch.relu(pre)
+        if li + 1 < len(mods):
+            h = rnd(h)
+    y64 = h
     b, c, t, f = y64.shape
     y64 = y64.transpose(1, 2).reshape(b, t, c * f)
     w = torch.randn_like(y64)
@@ -38,7 +56,7 @@ def test_conv_stack_forward_backward(cuda_lib, specs, B, T, F):
     assert y.shape == y64.shape
     (y * w.float().cuda()).sum().backward()
     scale = y64.abs().max().item()
-    assert (y.double().cpu() - y64).abs().max().item() < 2e-2 * scale
+    assert (y.double().cpu() - y64).abs().max().item() < 1e-3 * scale
     for (n, p64), (_, pc) in zip(conv64.named_parameters(), conv_c.named_parameters()):
         ref = p64.grad
         err = (pc.grad.double().cpu() - ref).abs().max().item()
