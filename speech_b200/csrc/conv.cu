@@ -26,30 +26,55 @@ namespace sb {
 typedef __nv_bfloat16 bf16;
 
 // ---- im2col ------------------------------------------------------------------------------------
-// src: P[(b*Ti + ti)*Fi + fi][Ci] f32 (relu on read if `relu`), dst: A[M][Kp] bf16
+// src: P[(b*Ti + ti)*Fi + fi][Ci] f32 (relu on read if `relu`), dst: A[M][Kp] bf16.
+// One thread produces 8 consecutive K entries (one 16-byte store).  For Ci % 8 == 0 these are 8
+// channels of one tap (two float4 loads); otherwise the scalar path is used per element.
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int Ti, int Fi, int Ci,
               int kh, int kw, int s, int To, int Fo, int Kp, int relu) {
-  const long long M = (long long)B * To * Fo;
   const int K = kh * kw * Ci;
-  const long long total = M * Kp;
+  const int kvec = Kp >> 3;                       // 8-wide groups per row
+  const long long M = (long long)B * To * Fo;
+  const long long total = M * kvec;
+  const bool vec = (Ci & 7) == 0;
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * 256) {
-    const long long m = idx / Kp;
-    const int k = (int)(idx - m * Kp);
-    float v = 0.f;
-    if (k < K) {
-      const int ci = k % Ci;
-      const int ij = k / Ci;
+    const long long m = idx / kvec;
+    const int k0 = (int)(idx - m * kvec) << 3;
+    const int f = (int)(m % Fo);
+    const int bt = (int)(m / Fo);
+    const int t = bt % To;
+    const int b = bt / To;
+    float v[8];
+    if (vec && k0 < K) {
+      const int ci = k0 % Ci;
+      const int ij = k0 / Ci;
       const int j = ij % kw, i = ij / kw;
-      const int f = (int)(m % Fo);
-      const long long bt = m / Fo;
-      const int t = (int)(bt % To);
-      const int b = (int)(bt / To);
-      v = __ldg(src + (((long long)b * Ti + (s * t + i)) * Fi + (s * f + j)) * Ci + ci);
-      if (relu) v = fmaxf(v, 0.f);
+      const float4* p = reinterpret_cast<const float4*>(
+          src + (((long long)b * Ti + (s * t + i)) * Fi + (s * f + j)) * Ci + ci);
+      const float4 a = __ldg(p), c = __ldg(p + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        v[e] = 0.f;
+        if (k < K) {
+          const int ci = k % Ci;
+          const int ij = k / Ci;
+          const int j = ij % kw, i = ij / kw;
+          v[e] = __ldg(src + (((long long)b * Ti + (s * t + i)) * Fi + (s * f + j)) * Ci + ci);
+        }
+      }
     }
-    dst[idx] = __float2bfloat16_rn(v);
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + m * Kp + k0) = o;
   }
 }
 
@@ -132,25 +157,107 @@ col2im_relu_kernel(const float* __restrict__ dA, long long ldA, const float* __r
     if (dbs[c] != 0.f) atomicAdd(db + c, dbs[c]);
 }
 
-// ---- bf16 matrix transpose [R][C] -> [C][Rp] (Rp >= R, leading dimension of the output) ---------
+// ---- bf16 matrix transpose [R][C] -> [C][ld_dst] ------------------------------------------------
+// 64x64 tiles, 32-bit (bf16x2) global accesses on both sides, padded shared tile.
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long long R, int C,
                       long long ld_src, long long ld_dst) {
-  __shared__ bf16 tile[64][66];
+  __shared__ unsigned short tile[64][66];
   const long long r0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
-  for (int rr = ty; rr < 64; rr += 4) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const unsigned short* s16 = reinterpret_cast<const unsigned short*>(src);
+  unsigned short* d16 = reinterpret_cast<unsigned short*>(dst);
+  const bool src_vec = ((ld_src & 1) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+  for (int rr = ty; rr < 64; rr += 8) {
     const long long r = r0 + rr;
-    const int c = c0 + tx;
-    tile[rr][tx] = (r < R && c < C) ? src[r * ld_src + c] : __float2bfloat16_rn(0.f);
+    const int c = c0 + 2 * tx;
+    unsigned short a = 0, b = 0;
+    if (r < R) {
+      if (src_vec && c + 1 < C) {
+        const unsigned int u = *reinterpret_cast<const unsigned int*>(s16 + r * ld_src + c);
+        a = (unsigned short)(u & 0xffff); b = (unsigned short)(u >> 16);
+      } else {
+        if (c < C) a = s16[r * ld_src + c];
+        if (c + 1 < C) b = s16[r * ld_src + c + 1];
+      }
+    }
+    tile[rr][2 * tx] = a;
+    tile[rr][2 * tx + 1] = b;
   }
   __syncthreads();
-  for (int cc = ty; cc < 64; cc += 4) {
+  const bool dst_vec = ((ld_dst & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0);
+  for (int cc = ty; cc < 64; cc += 8) {
     const int c = c0 + cc;
-    const long long r = r0 + tx;
-    if (c < C && r < R) dst[(long long)c * ld_dst + r] = tile[tx][cc];
+    const long long r = r0 + 2 * tx;
+    if (c >= C) continue;
+    const unsigned short a = tile[2 * tx][cc], b = tile[2 * tx + 1][cc];
+    if (dst_vec && r + 1 < R) {
+      *reinterpret_cast<unsigned int*>(d16 + (long long)c * ld_dst + r) =
+          (unsigned int)a | ((unsigned int)b << 16);
+    } else {
+      if (r < R) d16[(long long)c * ld_dst + r] = a;
+      if (r + 1 < R) d16[(long long)c * ld_dst + r + 1] = b;
+    }
   }
+}
+
+// ---- fused data gradient of a conv layer + ReLU mask of the layer below --------------------------
+// dCprev[(b,ti,fi)][ci] = [Pprev > 0] * sum_{taps (i,j) hitting the pixel} sum_co
+//                          dC[(b,t,f)][co] * W[co][(i*kw+j)*Ci + ci]
+// One warp per input pixel, lane = ci (Ci <= 32 per pass).  The dC row of a tap is read with a
+// warp-uniform address (broadcast), the weights come from shared memory (bf16, conflict-free over
+// ci).  Replaces a K = Co GEMM that would materialise the (M x kh*kw*Ci) f32 patch gradient
+// (1.2 GB at the north-star size) plus a col2im pass over it.
+__global__ void __launch_bounds__(256)
+conv_dgrad_relu_kernel(const bf16* __restrict__ dC, const bf16* __restrict__ Wp, int Kp,
+                       const float* __restrict__ Pprev, bf16* __restrict__ dCprev,
+                       float* __restrict__ db, int B, int Ti, int Fi, int Ci, int kh, int kw,
+                       int s, int To, int Fo, int Co) {
+  extern __shared__ unsigned char dg_smem[];
+  bf16* ws = reinterpret_cast<bf16*>(dg_smem);                 // [Co][kh*kw*Ci]
+  float* dbs = reinterpret_cast<float*>(ws + (size_t)Co * kh * kw * Ci);
+  const int K = kh * kw * Ci;
+  for (int k = threadIdx.x; k < Co * K; k += 256) ws[k] = Wp[(size_t)(k / K) * Kp + (k % K)];
+  for (int c = threadIdx.x; c < Ci; c += 256) dbs[c] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long npix = (long long)B * Ti * Fi;
+  for (long long px = (long long)blockIdx.x * 8 + warp; px < npix; px += (long long)gridDim.x * 8) {
+    const int fi = (int)(px % Fi);
+    const int bt = (int)(px / Fi);
+    const int ti = bt % Ti;
+    const int b = bt / Ti;
+    for (int cb = 0; cb < Ci; cb += 32) {
+      const int ci = cb + lane;
+      float g = 0.f;
+      for (int i = ti % s; i < kh; i += s) {
+        const int t = (ti - i) / s;
+        if (ti - i < 0 || t >= To) continue;
+        for (int j = fi % s; j < kw; j += s) {
+          const int f = (fi - j) / s;
+          if (fi - j < 0 || f >= Fo) continue;
+          const bf16* drow = dC + (((long long)b * To + t) * Fo + f) * Co;
+          const bf16* wtap = ws + (i * kw + j) * Ci + ci;
+          if (ci < Ci) {
+            for (int co = 0; co < Co; co += 2) {
+              const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(drow + co);
+              g += __bfloat162float(d2.x) * __bfloat162float(wtap[(size_t)co * K]);
+              g += __bfloat162float(d2.y) * __bfloat162float(wtap[(size_t)(co + 1) * K]);
+            }
+          }
+        }
+      }
+      if (ci < Ci) {
+        if (__ldg(Pprev + px * Ci + ci) <= 0.f) g = 0.f;
+        dCprev[px * Ci + ci] = __float2bfloat16_rn(g);
+        if (g != 0.f) atomicAdd(&dbs[ci], g);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Ci; c += 256)
+    if (dbs[c] != 0.f) atomicAdd(db + c, dbs[c]);
 }
 
 static int grid_for(long long total) {
@@ -217,5 +324,29 @@ extern "C" int sb_transpose_bf16(const void* src, void* dst, long long R, int C,
   transpose_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(src),
                                                   reinterpret_cast<bf16*>(dst), R, C, ld_src,
                                                   ld_dst);
+  return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+extern "C" int sb_conv_dgrad_relu(const void* dC_bf16, const void* Wp_bf16, int Kp,
+                                  const float* Pprev, void* dCprev_bf16, float* db, int B, int Ti,
+                                  int Fi, int Ci, int kh, int kw, int stride, int Co,
+                                  void* stream_) {
+  if (!dC_bf16 || !Wp_bf16 || !Pprev || !dCprev_bf16 || !db || B <= 0) return SB_ERR_INVALID;
+  const int To = (Ti - kh) / stride + 1, Fo = (Fi - kw) / stride + 1;
+  if (To <= 0 || Fo <= 0 || (Co & 1)) return SB_ERR_INVALID;
+  const size_t smem = (size_t)Co * kh * kw * Ci * sizeof(bf16) + (size_t)Ci * sizeof(float);
+  if (smem > 200 * 1024) return SB_ERR_UNSUPPORTED;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (smem > 40 * 1024 &&
+      cudaFuncSetAttribute(conv_dgrad_relu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem) != cudaSuccess)
+    return SB_ERR_CUDA;
+  const long long npix = (long long)B * Ti * Fi;
+  long long grid = (npix + 7) / 8;
+  const long long cap = (long long)device_sm_count() * 2;
+  if (grid > cap) grid = cap;
+  conv_dgrad_relu_kernel<<<(int)grid, 256, smem, stream>>>(
+      reinterpret_cast<const bf16*>(dC_bf16), reinterpret_cast<const bf16*>(Wp_bf16), Kp, Pprev,
+      reinterpret_cast<bf16*>(dCprev_bf16), db, B, Ti, Fi, Ci, kh, kw, stride, To, Fo, Co);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
