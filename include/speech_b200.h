@@ -130,8 +130,6 @@ int sb_ctc_prefix_beam(const float* logp, const int* lens, int B, int T, int S, 
  *   sb_conv_relu_to_bct  C of the last layer -> (B, To, Co*Fo) f32 with ReLU (model.py:66-71)
  *   sb_conv_dtop         dY (B,To,Co*Fo) * (C>0) -> dC bf16 [M][Co]; db[c] += column sums
  *   sb_conv_col2im_relu  dA f32 [M][ldA] -> dC of the layer below (gather, masked by Pprev>0)
- *   sb_conv_dgrad_relu   fused data gradient: dC of a layer (bf16 [M][Co]) x permuted weights ->
- *                        dC of the layer below, masked by Pprev>0 (no patch-gradient tensor)
  *   sb_transpose_bf16    [R][C] -> [C][R] (weight-gradient operands)
  * ------------------------------------------------------------------------------------- */
 int sb_conv_im2col(const float* src, void* dst_bf16, int B, int Ti, int Fi, int Ci, int kh, int kw,
@@ -142,9 +140,6 @@ int sb_conv_dtop(const float* dY, const float* C, void* dC_bf16, float* db, int 
 int sb_conv_col2im_relu(const float* dA, long long ldA, const float* Pprev, void* dCprev_bf16,
                         float* db, int B, int Ti, int Fi, int Ci, int kh, int kw, int stride,
                         void* stream);
-int sb_conv_dgrad_relu(const void* dC_bf16, const void* Wp_bf16, int Kp, const float* Pprev,
-                       void* dCprev_bf16, float* db, int B, int Ti, int Fi, int Ci, int kh, int kw,
-                       int stride, int Co, void* stream);
 int sb_transpose_bf16(const void* src, void* dst, long long R, int C, long long ld_src,
                       long long ld_dst, void* stream);
 

@@ -120,6 +120,10 @@ dconv_top_kernel(const float* __restrict__ dY, const float* __restrict__ C, bf16
 
 // ---- col2im as a gather, fused with the ReLU mask of the layer below -----------------------------
 // dA[m][(i*kw+j)*Ci + ci] f32 (ld = ldA) -> dCprev[(b*Ti+ti)*Fi+fi][ci] bf16 (masked by Pprev > 0)
+// Each input pixel receives at most ceil(kh/s)*ceil(kw/s) taps.  All tap loads of a thread are
+// issued before any is consumed (a loop with data-dependent `continue`s left ONE load in flight
+// per thread and ran at 0.9 TB/s).
+template <int MAXI, int MAXJ>
 __global__ void __launch_bounds__(256)
 col2im_relu_kernel(const float* __restrict__ dA, long long ldA, const float* __restrict__ Pprev,
                    bf16* __restrict__ dCprev, float* __restrict__ db, int B, int Ti, int Fi,
@@ -131,24 +135,33 @@ col2im_relu_kernel(const float* __restrict__ dA, long long ldA, const float* __r
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * 256) {
     const int ci = (int)(idx % Ci);
-    const long long px = idx / Ci;
-    const int fi = (int)(px % Fi);
-    const long long bt = px / Fi;
-    const int ti = (int)(bt % Ti);
-    const int b = (int)(bt / Ti);
-    float g = 0.f;
-    if (__ldg(Pprev + idx) > 0.f) {
-      for (int i = ti % s; i < kh; i += s) {
-        const int t = (ti - i) / s;
-        if (ti - i < 0 || t >= To) continue;
-        for (int j = fi % s; j < kw; j += s) {
-          const int f = (fi - j) / s;
-          if (fi - j < 0 || f >= Fo) continue;
-          const long long m = ((long long)b * To + t) * Fo + f;
-          g += __ldg(dA + m * ldA + (i * kw + j) * Ci + ci);
-        }
+    const int px = (int)(idx / Ci);
+    const int fi = px % Fi;
+    const int bt = px / Fi;
+    const int ti = bt % Ti;
+    const int b = bt / Ti;
+    const float mask = __ldg(Pprev + idx);
+    float v[MAXI * MAXJ];
+#pragma unroll
+    for (int a = 0; a < MAXI; ++a) {
+      const int i = ti % s + a * s;
+      const int t = (ti - i) / s;
+      const bool okt = (i < kh) && (ti - i >= 0) && (t < To);
+#pragma unroll
+      for (int c = 0; c < MAXJ; ++c) {
+        const int j = fi % s + c * s;
+        const int f = (fi - j) / s;
+        const bool ok = okt && (j < kw) && (fi - j >= 0) && (f < Fo);
+        v[a * MAXJ + c] = 0.f;
+        if (ok)
+          v[a * MAXJ + c] =
+              __ldcs(dA + (((long long)b * To + t) * Fo + f) * ldA + (i * kw + j) * Ci + ci);
       }
     }
+    float g = 0.f;
+#pragma unroll
+    for (int e = 0; e < MAXI * MAXJ; ++e) g += v[e];
+    if (mask <= 0.f) g = 0.f;
     dCprev[idx] = __float2bfloat16_rn(g);
     if (g != 0.f) atomicAdd(&dbs[ci], g);
   }
@@ -202,64 +215,6 @@ transpose_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long
   }
 }
 
-// ---- fused data gradient of a conv layer + ReLU mask of the layer below --------------------------
-// dCprev[(b,ti,fi)][ci] = [Pprev > 0] * sum_{taps (i,j) hitting the pixel} sum_co
-//                          dC[(b,t,f)][co] * W[co][(i*kw+j)*Ci + ci]
-// One warp per input pixel, lane = ci (Ci <= 32 per pass).  The dC row of a tap is read with a
-// warp-uniform address (broadcast), the weights come from shared memory (bf16, conflict-free over
-// ci).  Replaces a K = Co GEMM that would materialise the (M x kh*kw*Ci) f32 patch gradient
-// (1.2 GB at the north-star size) plus a col2im pass over it.
-__global__ void __launch_bounds__(256)
-conv_dgrad_relu_kernel(const bf16* __restrict__ dC, const bf16* __restrict__ Wp, int Kp,
-                       const float* __restrict__ Pprev, bf16* __restrict__ dCprev,
-                       float* __restrict__ db, int B, int Ti, int Fi, int Ci, int kh, int kw,
-                       int s, int To, int Fo, int Co) {
-  extern __shared__ unsigned char dg_smem[];
-  bf16* ws = reinterpret_cast<bf16*>(dg_smem);                 // [Co][kh*kw*Ci]
-  float* dbs = reinterpret_cast<float*>(ws + (size_t)Co * kh * kw * Ci);
-  const int K = kh * kw * Ci;
-  for (int k = threadIdx.x; k < Co * K; k += 256) ws[k] = Wp[(size_t)(k / K) * Kp + (k % K)];
-  for (int c = threadIdx.x; c < Ci; c += 256) dbs[c] = 0.f;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long npix = (long long)B * Ti * Fi;
-  for (long long px = (long long)blockIdx.x * 8 + warp; px < npix; px += (long long)gridDim.x * 8) {
-    const int fi = (int)(px % Fi);
-    const int bt = (int)(px / Fi);
-    const int ti = bt % Ti;
-    const int b = bt / Ti;
-    for (int cb = 0; cb < Ci; cb += 32) {
-      const int ci = cb + lane;
-      float g = 0.f;
-      for (int i = ti % s; i < kh; i += s) {
-        const int t = (ti - i) / s;
-        if (ti - i < 0 || t >= To) continue;
-        for (int j = fi % s; j < kw; j += s) {
-          const int f = (fi - j) / s;
-          if (fi - j < 0 || f >= Fo) continue;
-          const bf16* drow = dC + (((long long)b * To + t) * Fo + f) * Co;
-          const bf16* wtap = ws + (i * kw + j) * Ci + ci;
-          if (ci < Ci) {
-            for (int co = 0; co < Co; co += 2) {
-              const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(drow + co);
-              g += __bfloat162float(d2.x) * __bfloat162float(wtap[(size_t)co * K]);
-              g += __bfloat162float(d2.y) * __bfloat162float(wtap[(size_t)(co + 1) * K]);
-            }
-          }
-        }
-      }
-      if (ci < Ci) {
-        if (__ldg(Pprev + px * Ci + ci) <= 0.f) g = 0.f;
-        dCprev[px * Ci + ci] = __float2bfloat16_rn(g);
-        if (g != 0.f) atomicAdd(&dbs[ci], g);
-      }
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < Ci; c += 256)
-    if (dbs[c] != 0.f) atomicAdd(db + c, dbs[c]);
-}
-
 static int grid_for(long long total) {
   long long g = (total + 255) / 256;
   const long long cap = (long long)device_sm_count() * 16;
@@ -309,9 +264,19 @@ extern "C" int sb_conv_col2im_relu(const float* dA, long long ldA, const float* 
   const int To = (Ti - kh) / stride + 1, Fo = (Fi - kw) / stride + 1;
   if (To <= 0 || Fo <= 0) return SB_ERR_INVALID;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  col2im_relu_kernel<<<grid_for((long long)B * Ti * Fi * Ci), 256, Ci * sizeof(float), stream>>>(
-      dA, ldA, Pprev, reinterpret_cast<bf16*>(dCprev_bf16), db, B, Ti, Fi, Ci, kh, kw, stride, To,
-      Fo);
+  const int ni = (kh + stride - 1) / stride, nj = (kw + stride - 1) / stride;
+  const int g = grid_for((long long)B * Ti * Fi * Ci);
+  bf16* out = reinterpret_cast<bf16*>(dCprev_bf16);
+  const size_t sm = Ci * sizeof(float);
+  if ((long long)B * Ti * Fi >= (1LL << 31)) return SB_ERR_UNSUPPORTED;
+#define SB_C2I(I, J)                                                                              \
+  col2im_relu_kernel<I, J><<<g, 256, sm, stream>>>(dA, ldA, Pprev, out, db, B, Ti, Fi, Ci, kh, kw, \
+                                                   stride, To, Fo)
+  if (ni <= 2 && nj <= 2) SB_C2I(2, 2);
+  else if (ni <= 3 && nj <= 4) SB_C2I(3, 4);
+  else if (ni <= 5 && nj <= 8) SB_C2I(5, 8);
+  else return SB_ERR_UNSUPPORTED;
+#undef SB_C2I
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
@@ -324,29 +289,5 @@ extern "C" int sb_transpose_bf16(const void* src, void* dst, long long R, int C,
   transpose_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(src),
                                                   reinterpret_cast<bf16*>(dst), R, C, ld_src,
                                                   ld_dst);
-  return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
-}
-
-extern "C" int sb_conv_dgrad_relu(const void* dC_bf16, const void* Wp_bf16, int Kp,
-                                  const float* Pprev, void* dCprev_bf16, float* db, int B, int Ti,
-                                  int Fi, int Ci, int kh, int kw, int stride, int Co,
-                                  void* stream_) {
-  if (!dC_bf16 || !Wp_bf16 || !Pprev || !dCprev_bf16 || !db || B <= 0) return SB_ERR_INVALID;
-  const int To = (Ti - kh) / stride + 1, Fo = (Fi - kw) / stride + 1;
-  if (To <= 0 || Fo <= 0 || (Co & 1)) return SB_ERR_INVALID;
-  const size_t smem = (size_t)Co * kh * kw * Ci * sizeof(bf16) + (size_t)Ci * sizeof(float);
-  if (smem > 200 * 1024) return SB_ERR_UNSUPPORTED;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (smem > 40 * 1024 &&
-      cudaFuncSetAttribute(conv_dgrad_relu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem) != cudaSuccess)
-    return SB_ERR_CUDA;
-  const long long npix = (long long)B * Ti * Fi;
-  long long grid = (npix + 7) / 8;
-  const long long cap = (long long)device_sm_count() * 2;
-  if (grid > cap) grid = cap;
-  conv_dgrad_relu_kernel<<<(int)grid, 256, smem, stream>>>(
-      reinterpret_cast<const bf16*>(dC_bf16), reinterpret_cast<const bf16*>(Wp_bf16), Kp, Pprev,
-      reinterpret_cast<bf16*>(dCprev_bf16), db, B, Ti, Fi, Ci, kh, kw, stride, To, Fo, Co);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }

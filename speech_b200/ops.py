@@ -409,15 +409,16 @@ class ConvStackFunction(torch.autograd.Function):
             gemm_bf16_tn(dCT, AT, out=dWp, accumulate=True, split_k=_wgrad_split(Co, Kp, M))
             grads[2 * l] = dWp[:, :K].reshape(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
             if l > 0:
+                WpT = Wp.t().contiguous()                       # [Kp][Co]
+                dA = gemm_bf16_tn(dC, WpT)                      # [M][Kp] f32 patch gradient
                 Mp = B * Ti * Fi
                 dCp = torch.empty(Mp, Ci, dtype=torch.bfloat16, device=dev)
                 db = torch.zeros(Ci, dtype=torch.float32, device=dev)
-                dCc = dC
-                _launch("conv_dgrad_relu", 2.0 * M * Co * K,
-                        lambda: lib.sb_conv_dgrad_relu(dCc.data_ptr(), Wp.data_ptr(), Kp,
-                                                       Pprev.data_ptr(), dCp.data_ptr(),
-                                                       db.data_ptr(), B, Ti, Fi, Ci, kh, kw, s_,
-                                                       Co, sp))
+                _launch("conv_col2im_relu", 0.0,
+                        lambda: lib.sb_conv_col2im_relu(dA.data_ptr(), dA.stride(0),
+                                                        Pprev.data_ptr(), dCp.data_ptr(),
+                                                        db.data_ptr(), B, Ti, Fi, Ci, kh, kw, s_,
+                                                        sp))
                 dC = dCp
         ctx.saved = None
         return (None, None) + tuple(grads)

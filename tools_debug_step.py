@@ -25,9 +25,9 @@ x, y, xl, yl = m.collate(inputs, labels)
 x = x.cuda()
 tick("batch on gpu", t0)
 for it in range(3):
+    ops.profile_begin()
     c = ops.conv_stack(x, m.conv, True)
     tick("conv", t0)
-    ops.profile_begin()
     h = ops.gru_stack(c, m.rnn)
     tick("gru fwd", t0)
     out = m.fc(h[:, :, :1024] + h[:, :, 1024:])
