@@ -53,6 +53,12 @@ def synth_batch(nutt, seed=0):
     return inputs[:nutt], labels[:nutt]
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the committed
+# `ncu --set full` captures of this same workload (profiles/r01_summary.md; B=64 per GPU)
+NCU_TRAFFIC_BYTES = {"gru_bwd": 802.77e6 + 405.38e6, "gru_fwd": 407.09e6 + 725.50e6,
+                     "gemm_bf16_tn": 96.45e6 + 339.29e6, "ctc_fwd_bwd": 3.13e6}
+
+
 def flops_per_step(nutt):
     """Algorithmic FLOPs of one training step for `nutt` utterances (126.7 GF/utt)."""
     return 126.7e9 * nutt
@@ -318,9 +324,13 @@ def run_ours(args):
             n, ms, fl = prof[dom]
             ach = (fl / 1e12) / (ms * 1e-3)
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "traffic": NCU_TRAFFIC_BYTES.get(dom) if nutt == GLOBAL_B else None,
+                    "traffic_source": "profiles/r01_summary.md (ncu --set full, bytes per launch)",
                     "peak_source": peak_src,
-                    "avg_launch_ms": ms / n if n else None}
+                    "avg_launch_ms": ms / n if n else None,
+                    "note": "per-step latency-bound recurrence (see DESIGN.md 4.2): tensor pipe "
+                            "and HBM are both far from saturated by construction at B=64"}
         line = {
             "metric": "utterances/sec (training step, B=64,T=1000,80-feat)",
             "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
