@@ -193,6 +193,8 @@ int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
 /* Developer hook (not part of the drop-in surface): device buffer of >= 64*16 uint64 receiving a
  * globaltimer timeline of CTA 0 for the next sb_gru_fwd launches; NULL disables. */
 int sb_debug_gru_timeline(void* dev_buffer);
+/* Developer hook: 1 forces the 128-row CTA tile in sb_gemm_bf16_tn (disables the 256-row variant). */
+int sb_debug_gemm_mt1(int force);
 /* Developer hook: timing ablations of the forward GRU kernel (results become wrong; 0 = off). */
 int sb_debug_gru_flags(int flags);
 /* Developer hook: enable (1, default) / disable (0) the K-split backward GRU kernel. */

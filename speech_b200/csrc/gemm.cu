@@ -35,21 +35,28 @@ struct GemmParams {
   int m_tiles, n_tiles;
 };
 
-template <int BN>
+// MT = number of 128-row MMA sub-tiles per CTA tile.  MT = 2 (256 x BN CTA tile) re-uses every B
+// tile for two MMAs: operand traffic per FLOP drops 1.5x at BN = 256 (the 128x256 tile measured
+// 12.4 TB/s of L2->SM reads with the tensor pipe only 55 % busy), at the price of a single
+// accumulator stage (all 512 TMEM columns hold one tile), so it is used for long-K GEMMs only.
+template <int BN, int MT>
 struct GemmCfg {
-  static constexpr int kStageBytes = (BM + BN) * BK * 2;
+  static constexpr int kStageBytes = (MT * BM + BN) * BK * 2;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);  // 2 accumulator stages
+  static constexpr int kAccStages = MT == 1 ? 2 : 1;
+  static constexpr int kTmemColsRaw = kAccStages * MT * BN;
+  static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, MT>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kAcc = Cfg::kAccStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned tile ring (SWIZZLE_128B requirement)
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -103,9 +110,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
-          uint8_t* sb_ = sa + BM * BK * 2;
+          uint8_t* sb_ = sa + MT * BM * BK * 2;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * (MT * BM));
           tma_load_2d(sb_, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -126,20 +133,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (lane == 0) mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       __syncwarp();
       tc_fence_after_sync();
-      const uint32_t tmem_d = tmem_base + acc * BN;
+      const uint32_t tmem_d = tmem_base + acc * (MT * BN);
       for (int kb = kb0; kb < kb1; ++kb) {
         if (lane == 0) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
-          const uint32_t sb_ = sa + BM * BK * 2;
-          const uint64_t da = umma_desc_sw128_kmajor(sa);
+          const uint32_t sb_ = sa + MT * BM * BK * 2;
           const uint64_t db = umma_desc_sw128_kmajor(sb_);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the >>4 field
-            umma_bf16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                         (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t da = umma_desc_sw128_kmajor(sa + mt * BM * BK * 2);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the >>4 field
+              umma_bf16_ss(tmem_d + mt * BN, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                           (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
@@ -151,7 +161,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // empty K range (can only happen with an over-split K): nothing accumulated
         umma_commit(&tfull_bar[acc]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
@@ -168,7 +178,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const bool has_k = kb0 < p.k_blocks_total;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
-      const int m = m_blk * BM + sub * 32 + lane;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int m = m_blk * (MT * BM) + mt * BM + sub * 32 + lane;
       bool row_ok = m < p.M;
       long long out_row = m;
       if (p.flags & SB_GEMM_ROW_REMAP) {
@@ -182,7 +194,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * BN + c * 32;
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(sub * 32) << 16) + acc * (MT * BN) + mt * BN + c * 32;
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
         const int n0 = n_blk * BN + c * 32;
@@ -224,10 +237,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       }
+      }  // mt
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -286,13 +300,13 @@ int device_sm_count() {
   return sms;
 }
 
-template <int BN>
+template <int BN, int MT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, MT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return SB_ERR_CUDA;
@@ -302,13 +316,21 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   int grid = device_sm_count();
   if (grid > total) grid = total;
-  gemm_bf16_tn_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_tn_kernel<BN, MT><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
+
+static int g_gemm_force_mt1 = 0;
 
 }  // namespace sb
 
 using namespace sb;
+
+// developer hook: 1 disables the 256-row CTA tile variant
+extern "C" int sb_debug_gemm_mt1(int force) {
+  sb::g_gemm_force_mt1 = force;
+  return SB_OK;
+}
 
 extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, float* C,
                                long long ldc, const float* bias, int M, int N, int K, int flags,
@@ -338,15 +360,23 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
     const long long tiles256 = (long long)p.m_tiles * ((N + 255) / 256) * split_k;
     bn = (tiles256 >= sms || N > 2048) ? 256 : 128;
   }
+  // 256-row CTA tiles when the GEMM is long (K >= 1024) and still leaves >= 3 waves of tiles
+  int mt = 1;
+  if (bn == 256 && K >= 1024 && split_k == 1 && !g_gemm_force_mt1) {
+    const long long tiles2 = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
+    if (tiles2 >= 3LL * sms) mt = 2;
+  }
+  p.m_tiles = (M + mt * BM - 1) / (mt * BM);
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, BM);
+  int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, mt * BM);
   if (rc != SB_OK) return rc;
   rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, bn);
   if (rc != SB_OK) return rc;
+  if (mt == 2) return launch_gemm<256, 2>(ta, tb, p, stream);
   switch (bn) {
-    case 32: return launch_gemm<32>(ta, tb, p, stream);
-    case 64: return launch_gemm<64>(ta, tb, p, stream);
-    case 128: return launch_gemm<128>(ta, tb, p, stream);
-    default: return launch_gemm<256>(ta, tb, p, stream);
+    case 32: return launch_gemm<32, 1>(ta, tb, p, stream);
+    case 64: return launch_gemm<64, 1>(ta, tb, p, stream);
+    case 128: return launch_gemm<128, 1>(ta, tb, p, stream);
+    default: return launch_gemm<256, 1>(ta, tb, p, stream);
   }
 }

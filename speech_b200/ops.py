@@ -26,6 +26,8 @@ def _apply_env_knobs():
     lib = _lib.load()
     if os.environ.get("SB_GRU_KSPLIT") is not None:
         lib.sb_debug_gru_ksplit(int(os.environ["SB_GRU_KSPLIT"]))
+    if os.environ.get("SB_GEMM_MT1") is not None:
+        lib.sb_debug_gemm_mt1(int(os.environ["SB_GEMM_MT1"]))
     if os.environ.get("SB_GRU_CLUSTER") is not None:
         lib.sb_debug_gru_cluster(int(os.environ["SB_GRU_CLUSTER"]))
 

@@ -36,6 +36,8 @@ def _gemm(A, B, bias=None, accumulate_into=None, split_k=1, remap=None):
     (15808, 96, 480),     # layer-0 input projection shape class
     (1000, 6144, 2048),   # many tiles per CTA -> ring + TMEM double buffering wrap around
     (4096, 29, 2048),     # output projection N=29 (ldc not a multiple of 4 -> scalar stores)
+    (16000, 3072, 1024),  # long-K, many tiles -> 256-row CTA tile variant (MT=2)
+    (15808, 6144, 1088),  # same, ragged K (17 k-blocks) and ragged M (15808 = 61.75 x 256)
     (192, 48, 160),       # tests/shared.py tiny config
 ])
 def test_gemm_matches_fp32_reference(cuda_lib, M, N, K):
