@@ -33,6 +33,7 @@ struct GemmParams {
   int flags;            // SB_GEMM_ACCUMULATE | SB_GEMM_ROW_REMAP
   int remap_B, remap_T, valid_B;
   int m_tiles, n_tiles;
+  int tma_store;        // epilogue through swizzled smem + cp.async.bulk.tensor stores
 };
 
 // MT = number of 128-row MMA sub-tiles per CTA tile.  MT = 2 (256 x BN CTA tile) re-uses every B
@@ -47,13 +48,16 @@ struct GemmCfg {
   static constexpr int kAccStages = MT == 1 ? 2 : 1;
   static constexpr int kTmemColsRaw = kAccStages * MT * BN;
   static constexpr int kTmemCols = kTmemColsRaw < 32 ? 32 : kTmemColsRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStageOutBytes = 4 * 2 * 4096;   // 4 epilogue warps x 2 x [32 x 32] f32
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStageOutBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BN, int MT>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   using Cfg = GemmCfg<BN, MT>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAcc = Cfg::kAccStages;
@@ -61,7 +65,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // 1024-byte aligned tile ring (SWIZZLE_128B requirement)
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kStages * Cfg::kStageBytes);
+  uint8_t* out_stage = tiles + kStages * Cfg::kStageBytes;   // 1024-aligned (stage bytes are)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::kStageOutBytes);
   uint64_t* full_bar = bars;                  // [kStages]
   uint64_t* empty_bar = bars + kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]
@@ -74,6 +79,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_store) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -169,6 +175,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    unsigned int out_slot = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int split = w / tiles_mn;
       const int t = w - split * tiles_mn;
@@ -199,7 +206,48 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
         const int n0 = n_blk * BN + c * 32;
-        if (row_ok && has_k && n0 < p.N) {
+        if (p.tma_store) {
+          // ---- coalesced path: registers -> swizzled smem tile -> one bulk tensor store ----
+          const int m0 = m_blk * (MT * BM) + mt * BM + sub * 32;
+          if (has_k && n0 < p.N && m0 < p.M) {      // warp-uniform
+            uint8_t* buf = out_stage + ((warp - 2) * 2 + (out_slot & 1)) * 4096;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              o.x = __uint_as_float(v[j + 0]);
+              o.y = __uint_as_float(v[j + 1]);
+              o.z = __uint_as_float(v[j + 2]);
+              o.w = __uint_as_float(v[j + 3]);
+              if (add_bias) {
+                if (n0 + j + 0 < p.N) o.x += __ldg(p.bias + n0 + j + 0);
+                if (n0 + j + 1 < p.N) o.y += __ldg(p.bias + n0 + j + 1);
+                if (n0 + j + 2 < p.N) o.z += __ldg(p.bias + n0 + j + 2);
+                if (n0 + j + 3 < p.N) o.w += __ldg(p.bias + n0 + j + 3);
+              }
+              *reinterpret_cast<float4*>(buf + sw128_offset(lane, j >> 2)) = o;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.flags & SB_GEMM_ACCUMULATE)
+                asm volatile(
+                    "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group"
+                    " [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmap_c)),
+                    "r"(smem_u32(buf)), "r"(n0), "r"(m0)
+                    : "memory");
+              else
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group"
+                    " [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmap_c)),
+                    "r"(smem_u32(buf)), "r"(n0), "r"(m0)
+                    : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++out_slot;
+          }
+        } else if (row_ok && has_k && n0 < p.N) {
           if (p.flags & SB_GEMM_ACCUMULATE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -243,6 +291,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
     }
+    // all bulk stores of this thread must have completed before the CTA exits
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before_sync();
@@ -300,6 +350,23 @@ int device_sm_count() {
   return sms;
 }
 
+// f32 tensor map over C [M][N] (ld = ldc): box 32 x 32, SWIZZLE_128B; stores clip at the edges
+static int make_tmap_f32_c(CUtensorMap* map, float* base, long long rows, long long cols,
+                           long long ld) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return SB_ERR_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SB_OK : SB_ERR_CUDA;
+}
+
+static int g_gemm_tma_store = 1;
+
 template <int BN, int MT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p,
                        cudaStream_t stream) {
@@ -316,11 +383,17 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   int grid = device_sm_count();
   if (grid > total) grid = total;
-  gemm_bf16_tn_kernel<BN, MT><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  CUtensorMap tc = ta;   // placeholder when the register epilogue is used
+  p.tma_store = 0;
+  if (g_gemm_tma_store && !(p.flags & SB_GEMM_ROW_REMAP) && (p.ldc & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
+    if (make_tmap_f32_c(&tc, p.C, p.M, p.N, p.ldc) == SB_OK) p.tma_store = 1;
+  }
+  gemm_bf16_tn_kernel<BN, MT><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
-static int g_gemm_force_mt1 = 0;
+static int g_gemm_force_mt1 = 1;   // the 256-row CTA tile measured slower (epilogue not overlapped)
 
 }  // namespace sb
 
@@ -328,7 +401,10 @@ using namespace sb;
 
 // developer hook: 1 disables the 256-row CTA tile variant
 extern "C" int sb_debug_gemm_mt1(int force) {
-  sb::g_gemm_force_mt1 = force;
+  // bit 0: 1 = 128-row CTA tiles only (default), 0 = allow the 256-row variant
+  // bit 1: 1 = disable the TMA-store epilogue (register stores)
+  sb::g_gemm_force_mt1 = force & 1;
+  sb::g_gemm_tma_store = (force & 2) ? 0 : 1;
   return SB_OK;
 }
 
