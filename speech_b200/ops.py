@@ -157,8 +157,11 @@ class GRUStackFunction(torch.autograd.Function):
             b_ih = [wl[d * 4 + 2] for d in range(ndir)]
             b_hh = [wl[d * 4 + 3] for d in range(ndir)]
             Kl = X.shape[1]
-            wih_cat = torch.zeros(ndir * 3 * H, Kl, dtype=torch.bfloat16, device=dev)
-            wih_cat[:, :w_ih[0].shape[1]] = torch.cat([w.detach() for w in w_ih], 0)
+            if Kl == w_ih[0].shape[1]:
+                wih_cat = torch.cat([w.detach() for w in w_ih], 0).to(torch.bfloat16)
+            else:
+                wih_cat = torch.zeros(ndir * 3 * H, Kl, dtype=torch.bfloat16, device=dev)
+                wih_cat[:, :w_ih[0].shape[1]] = torch.cat([w.detach() for w in w_ih], 0)
             bih_cat = torch.cat([b.detach() for b in b_ih]).float().contiguous()
             whh = torch.stack([w.detach() for w in w_hh]).to(torch.bfloat16).contiguous()
             bhh = torch.stack([b.detach() for b in b_hh]).float().contiguous()
@@ -167,7 +170,9 @@ class GRUStackFunction(torch.autograd.Function):
             xn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
             xnT = gates = None
             if need_grad:
-                xnT = torch.zeros(D, (T + 2) * Bp, dtype=torch.bfloat16, device=dev)
+                xnT = torch.empty(D, (T + 2) * Bp, dtype=torch.bfloat16, device=dev)
+                xnT[:, :Bp].zero_()                     # h_{-1} = 0 (forward direction)
+                xnT[:, (T + 1) * Bp:].zero_()           # h_{T}  = 0 (backward direction)
                 gates = torch.empty(M, ndir, 4, H, dtype=torch.float32, device=dev)
             sp = _lib.stream_ptr()
             _launch("gru_fwd", 2.0 * M * 3 * H * H * ndir,
@@ -264,16 +269,22 @@ class GRUStackFunction(torch.autograd.Function):
                 XT = ctx.saved[l - 1][3][:, Bp:Bp + M]                   # [In_l][M] view
             else:
                 XT = X.t().contiguous()                                   # [Kl][M]
-            dwih = torch.zeros(ndir * K3, XT.shape[0], dtype=torch.float32, device=dev)
-            gemm_bf16_tn(dgiT, XT, out=dwih, accumulate=True,
-                         split_k=_wgrad_split(ndir * K3, XT.shape[0], M))
+            sk = _wgrad_split(ndir * K3, XT.shape[0], M)
+            if sk == 1:
+                dwih = gemm_bf16_tn(dgiT, XT)
+            else:
+                dwih = torch.zeros(ndir * K3, XT.shape[0], dtype=torch.float32, device=dev)
+                gemm_bf16_tn(dgiT, XT, out=dwih, accumulate=True, split_k=sk)
             for d in range(ndir):
                 hprevT = xnT[d * H:(d + 1) * H, (0 if d == 0 else 2 * Bp):][:, :M]
-                dwhh = torch.zeros(K3, H, dtype=torch.float32, device=dev)
                 sk = _wgrad_split(2 * H, H, M)
+                if sk == 1:
+                    dwhh = torch.empty(K3, H, dtype=torch.float32, device=dev)
+                else:
+                    dwhh = torch.zeros(K3, H, dtype=torch.float32, device=dev)
                 gemm_bf16_tn(dgiT[d * K3:d * K3 + 2 * H], hprevT, out=dwhh[:2 * H],
-                             accumulate=True, split_k=sk)
-                gemm_bf16_tn(dghnT[d], hprevT, out=dwhh[2 * H:], accumulate=True, split_k=sk)
+                             accumulate=sk > 1, split_k=sk)
+                gemm_bf16_tn(dghnT[d], hprevT, out=dwhh[2 * H:], accumulate=sk > 1, split_k=sk)
                 grads[l * 4 * ndir + d * 4 + 0] = dwih[d * K3:(d + 1) * K3, :In_l]
                 grads[l * 4 * ndir + d * 4 + 1] = dwhh
                 grads[l * 4 * ndir + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
