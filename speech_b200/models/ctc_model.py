@@ -50,8 +50,8 @@ class CTC(model.Model):
         # every utterance is scored over the full padded T' (reference ctc_model.py:43-45)
         max_t = self.conv_out_size(max(i.shape[0] for i in inputs), 0)
         x_lens = torch.IntTensor([max_t] * len(inputs))
-        x = model.zero_pad_concat_pinned(inputs) if self.is_cuda else \
-            torch.from_numpy(model.zero_pad_concat(inputs))
+        x = model.zero_pad_concat_device(inputs, next(self.parameters()).device) \
+            if self.is_cuda else torch.from_numpy(model.zero_pad_concat(inputs))
         y_lens = torch.IntTensor([len(l) for l in labels])
         y = torch.IntTensor([int(t) for label in labels for t in label])
         return [x, y, x_lens, y_lens]

@@ -114,22 +114,67 @@ def zero_pad_concat(inputs):
 
 
 _pinned = {}
+_pool = None
+
+
+def _staging(shape):
+    buf = _pinned.get(shape)
+    if buf is None:
+        buf = [torch.zeros(shape, dtype=torch.float32).pin_memory(), None]   # tensor, last H2D event
+        _pinned.clear()
+        _pinned[shape] = buf
+    return buf
 
 
 def zero_pad_concat_pinned(inputs):
-    """zero_pad_concat into a reused PINNED staging tensor so the H2D copy can be asynchronous
-    (batch assembly becomes the critical path once the step is ms-scale)."""
+    """zero_pad_concat into a reused PINNED staging tensor (host tensor; H2D is the caller's)."""
     max_t = max(inp.shape[0] for inp in inputs)
     shape = (len(inputs), max_t, inputs[0].shape[1])
-    buf = _pinned.get(shape)
-    if buf is None:
-        buf = torch.zeros(shape, dtype=torch.float32).pin_memory()
-        _pinned.clear()
-        _pinned[shape] = buf
-    arr = buf.numpy()
+    buf = _staging(shape)
+    if buf[1] is not None:
+        buf[1].synchronize()
+        buf[1] = None
+    arr = buf[0].numpy()
     for e, inp in enumerate(inputs):
         n = inp.shape[0]
         arr[e, :n, :] = inp
         if n < max_t:
             arr[e, n:, :] = 0.0
-    return buf
+    return buf[0]
+
+
+def zero_pad_concat_device(inputs, device, chunk=8, threads=4):
+    """Batch assembly straight to the GPU: utterances are written
+    into a reused pinned staging buffer by a few host threads, chunk by chunk, and every finished
+    chunk is copied to the device asynchronously while the next ones are still being filled, so
+    the host memcpy and the PCIe transfer overlap.  Returns the (B, max T, F) float32 CUDA tensor
+    zero-padded like the reference's zero_pad_concat (model.py:135-141)."""
+    global _pool
+    from concurrent.futures import ThreadPoolExecutor
+    max_t = max(inp.shape[0] for inp in inputs)
+    B, F = len(inputs), inputs[0].shape[1]
+    shape = (B, max_t, F)
+    buf = _staging(shape)
+    if buf[1] is not None:
+        buf[1].synchronize()           # the previous batch's H2D must be done before we overwrite
+    arr = buf[0].numpy()
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+
+    def fill(lo, hi):
+        for e in range(lo, hi):
+            n = inputs[e].shape[0]
+            arr[e, :n, :] = inputs[e]
+            if n < max_t:
+                arr[e, n:, :] = 0.0
+        return lo, hi
+
+    if _pool is None:
+        _pool = ThreadPoolExecutor(max_workers=threads)
+    futs = [_pool.submit(fill, lo, min(B, lo + chunk)) for lo in range(0, B, chunk)]
+    for f in futs:                      # in order: chunk k goes out while k+1.. are being filled
+        lo, hi = f.result()
+        out[lo:hi].copy_(buf[0][lo:hi], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    buf[1] = ev
+    return out

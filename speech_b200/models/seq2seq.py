@@ -174,8 +174,8 @@ class Seq2Seq(model.Model):
             return [complete[0][0]]
 
     def collate(self, inputs, labels):
-        x = model.zero_pad_concat_pinned(inputs) if self.is_cuda else \
-            torch.from_numpy(model.zero_pad_concat(inputs))
+        x = model.zero_pad_concat_device(inputs, next(self.parameters()).device) \
+            if self.is_cuda else torch.from_numpy(model.zero_pad_concat(inputs))
         return x, torch.from_numpy(end_pad_concat(labels))
 
 

@@ -62,8 +62,8 @@ class Transducer(model.Model):
     def collate(self, inputs, labels):
         max_t = self.conv_out_size(max(i.shape[0] for i in inputs), 0)
         x_lens = torch.IntTensor([max_t] * len(inputs))
-        x = model.zero_pad_concat_pinned(inputs) if self.is_cuda else \
-            torch.from_numpy(model.zero_pad_concat(inputs))
+        x = model.zero_pad_concat_device(inputs, next(self.parameters()).device) \
+            if self.is_cuda else torch.from_numpy(model.zero_pad_concat(inputs))
         y_lens = torch.IntTensor([len(l) for l in labels])
         y = torch.IntTensor([int(t) for label in labels for t in label])
         return [x, y, x_lens, y_lens]
