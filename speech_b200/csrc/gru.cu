@@ -752,7 +752,7 @@ gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&full[i], 1);
     mbar_init(accfull, 1);
-    mbar_init(recvbar, (KS - 1) * GRU_EPI);   // every epilogue thread of every peer arrives once
+    mbar_init(recvbar, (KS - 1) * (GRU_EPI / 32));   // one arrive per epilogue warp of every peer
     mbar_fence_init();
     tma_prefetch_desc(tm);
   }
@@ -842,25 +842,32 @@ gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
         if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
         float own[GRU_UPT];
+        uint32_t v[KS][8];
+#pragma unroll
+        for (int pr = 0; pr < KS; ++pr)
+          tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + pr * 16 +
+                                uh * GRU_UPT, v[pr]);
+        tmem_ld_wait();
 #pragma unroll
         for (int pr = 0; pr < KS; ++pr) {
-          uint32_t v[8];
-          tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + pr * 16 +
-                                uh * GRU_UPT, v);
-          tmem_ld_wait();
           if ((uint32_t)pr == crank) {
 #pragma unroll
-            for (int jj = 0; jj < GRU_UPT; ++jj) own[jj] = __uint_as_float(v[jj]);
-          } else {
-            if (active) {
-              const uint32_t ra = mapa_shared(my_slot, (uint32_t)pr);
-              st_cluster_f4(ra, make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]),
-                                            __uint_as_float(v[2]), __uint_as_float(v[3])));
-              st_cluster_f4(ra + 16, make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]),
-                                                 __uint_as_float(v[6]), __uint_as_float(v[7])));
-            }
-            mbar_arrive_remote_release(mapa_shared(my_bar, (uint32_t)pr));
+            for (int jj = 0; jj < GRU_UPT; ++jj) own[jj] = __uint_as_float(v[pr][jj]);
+          } else if (active) {
+            const uint32_t ra = mapa_shared(my_slot, (uint32_t)pr);
+            st_cluster_f4(ra, make_float4(__uint_as_float(v[pr][0]), __uint_as_float(v[pr][1]),
+                                          __uint_as_float(v[pr][2]), __uint_as_float(v[pr][3])));
+            st_cluster_f4(ra + 16, make_float4(__uint_as_float(v[pr][4]), __uint_as_float(v[pr][5]),
+                                               __uint_as_float(v[pr][6]), __uint_as_float(v[pr][7])));
           }
+        }
+        // one release-arrive per warp and peer: __syncwarp orders the lanes' DSMEM stores before
+        // lane 0's cumulative release
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int pr = 0; pr < KS; ++pr)
+            if ((uint32_t)pr != crank) mbar_arrive_remote_release(mapa_shared(my_bar, (uint32_t)pr));
         }
         tc_fence_before_sync();
         if (tid == 0) GRU_STAMP(4);
