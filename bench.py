@@ -351,6 +351,8 @@ def run_ours(args):
             "roofline": roof,
             "kernels": kernels,
         }
+        if world == 1 and not args.no_secondary:
+            line["secondary"] = secondary_measurements(model, batch, dev)
         if world == 1 and not args.no_cpu_baseline:
             threads = pick_threads()
             nb = 8
@@ -365,6 +367,72 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def secondary_measurements(model, batch, dev):
+    """SURVEY.md section 8d secondary numbers, N=1 only (outside the timed regions):
+       - CTC loss delta vs the reference model restated on the CPU (oracle/model_ref.py) with the
+         SAME weights and inputs (8 utterances): the effect of the bf16 tensor-core operands;
+       - CTC kernel-only delta: our kernel vs torch's CPU float64 CTC on OUR logits;
+       - standalone CTC micro-benchmark at B=64, T=1000, V=29 (algorithmic bytes / time);
+       - decode throughput: CTC.infer (prefix beam search on the GPU), beam 1 and 8."""
+    from oracle.model_ref import RefCTC
+    from speech_b200.functions.ctc import ctc_costs_and_grads
+    out = {}
+    inputs, labels = batch
+    sub = (tuple(inputs[:8]), tuple(labels[:8]))
+    # ---- loss delta, same weights ----
+    with torch.no_grad():
+        ours = float(model.loss(sub).item())
+        x, y, x_lens, y_lens = model.collate(*sub)
+        logits = model.forward_impl(x)
+    ref = RefCTC(F_IN, VOCAB, MODEL_CFG)
+    ref.load_from_dropin({k: v.detach().float().cpu() for k, v in model.state_dict().items()})
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref_loss = float(ref.loss(torch.from_numpy(np.stack(sub[0])), y, y_lens).item())
+    out["ctc_loss_ours_8utt"] = ours
+    out["ctc_loss_cpu_reference_8utt"] = ref_loss
+    out["ctc_loss_rel_delta"] = abs(ours - ref_loss) / abs(ref_loss)
+    # ---- kernel-only delta on our logits ----
+    lg = logits.detach().double().cpu()
+    lp = torch.log_softmax(lg, 2).transpose(0, 1)
+    T = lg.shape[1]
+    c64 = torch.nn.functional.ctc_loss(lp, y.long(), torch.full((8,), T, dtype=torch.long),
+                                       y_lens.long(), blank=VOCAB, reduction="sum").item()
+    out["ctc_kernel_rel_delta_vs_f64"] = abs(ours - c64) / abs(c64)
+    # ---- standalone CTC micro-benchmark ----
+    rng = np.random.RandomState(0)
+    acts = torch.from_numpy(rng.randn(GLOBAL_B, T_IN, VOCAB + 1).astype(np.float32)).to(dev)
+    llen = torch.tensor([len(l) for l in labels], dtype=torch.int32)
+    flat = torch.tensor([t for l in labels for t in l], dtype=torch.int32)
+    alen = torch.full((GLOBAL_B,), T_IN, dtype=torch.int32)
+    for _ in range(3):
+        ctc_costs_and_grads(acts, flat, alen, llen)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ctc_costs_and_grads(acts, flat, alen, llen)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    algo = 2.0 * GLOBAL_B * T_IN * (VOCAB + 1) * 4
+    out["ctc_standalone"] = {"shape": [GLOBAL_B, T_IN, VOCAB + 1], "ms": ms,
+                             "algorithmic_bytes": algo, "GB_per_s": algo / ms / 1e6,
+                             "note": "includes the host->device copy of the label arrays; bound "
+                                     "by the T-step dependency chain (float64 lattice)"}
+    # ---- decode throughput ----
+    model.set_eval()
+    for beam in (1, 8):
+        model.infer(batch, beam_size=beam)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.infer(batch, beam_size=beam)
+        torch.cuda.synchronize()
+        out["infer_beam%d_utt_per_s" % beam] = len(inputs) / (time.perf_counter() - t0)
+    model.set_train()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -372,6 +440,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the secondary measurements (loss delta vs the CPU reference model, "
+                         "standalone CTC micro-benchmark, decode throughput)")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run (ncu): 1 warm-up + --steps device steps, nothing else; "
                          "prints no benchmark value")
