@@ -106,6 +106,20 @@ def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=N
     return out
 
 
+def _grad_sink(param, rows=None):
+    """The parameter's existing .grad (optionally a row slice) if the weight-gradient GEMM can
+    accumulate straight into it (fp32, contiguous, 16-byte aligned rows), else None.  Writing
+    dW with the GEMM's reduce-add epilogue into .grad replaces a zero-filled temporary plus
+    autograd's separate `grad += dW` pass (the gradient-accumulation fusion used by large-model
+    trainers); the Function then returns None for that parameter."""
+    g = getattr(param, "grad", None)
+    if g is None or not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous():
+        return None
+    if g.dim() != 2 or (g.stride(0) % 4) != 0 or (g.data_ptr() % 16) != 0:
+        return None
+    return g if rows is None else g[rows[0]:rows[1]]
+
+
 def _wgrad_split(M, N, K):
     """split-K factor for the K = T*B weight-gradient contractions (few output tiles, long K)."""
     tiles = ((M + 127) // 128) * ((N + 255) // 256)
@@ -269,24 +283,40 @@ class GRUStackFunction(torch.autograd.Function):
                 XT = ctx.saved[l - 1][3][:, Bp:Bp + M]                   # [In_l][M] view
             else:
                 XT = X.t().contiguous()                                   # [Kl][M]
-            sk = _wgrad_split(ndir * K3, XT.shape[0], M)
-            if sk == 1:
-                dwih = gemm_bf16_tn(dgiT, XT)
+            sinks_ih = [_grad_sink(wl[d * 4]) if XT.shape[0] == In_l else None
+                        for d in range(ndir)]
+            if all(g is not None for g in sinks_ih):
+                # accumulate dW_ih of each direction straight into the parameter's .grad
+                for d in range(ndir):
+                    gemm_bf16_tn(dgiT[d * K3:(d + 1) * K3], XT, out=sinks_ih[d], accumulate=True,
+                                 split_k=_wgrad_split(K3, In_l, M))
+                dwih = None
             else:
-                dwih = torch.zeros(ndir * K3, XT.shape[0], dtype=torch.float32, device=dev)
-                gemm_bf16_tn(dgiT, XT, out=dwih, accumulate=True, split_k=sk)
+                sk = _wgrad_split(ndir * K3, XT.shape[0], M)
+                if sk == 1:
+                    dwih = gemm_bf16_tn(dgiT, XT)
+                else:
+                    dwih = torch.zeros(ndir * K3, XT.shape[0], dtype=torch.float32, device=dev)
+                    gemm_bf16_tn(dgiT, XT, out=dwih, accumulate=True, split_k=sk)
             for d in range(ndir):
                 hprevT = xnT[d * H:(d + 1) * H, (0 if d == 0 else 2 * Bp):][:, :M]
                 sk = _wgrad_split(2 * H, H, M)
-                if sk == 1:
+                sink = _grad_sink(wl[d * 4 + 1])
+                if sink is not None:
+                    dwhh = sink
+                    acc = True
+                elif sk == 1:
                     dwhh = torch.empty(K3, H, dtype=torch.float32, device=dev)
+                    acc = False
                 else:
                     dwhh = torch.zeros(K3, H, dtype=torch.float32, device=dev)
+                    acc = True
                 gemm_bf16_tn(dgiT[d * K3:d * K3 + 2 * H], hprevT, out=dwhh[:2 * H],
-                             accumulate=sk > 1, split_k=sk)
-                gemm_bf16_tn(dghnT[d], hprevT, out=dwhh[2 * H:], accumulate=sk > 1, split_k=sk)
-                grads[l * 4 * ndir + d * 4 + 0] = dwih[d * K3:(d + 1) * K3, :In_l]
-                grads[l * 4 * ndir + d * 4 + 1] = dwhh
+                             accumulate=acc, split_k=sk)
+                gemm_bf16_tn(dghnT[d], hprevT, out=dwhh[2 * H:], accumulate=acc, split_k=sk)
+                grads[l * 4 * ndir + d * 4 + 0] = None if dwih is None else \
+                    dwih[d * K3:(d + 1) * K3, :In_l]
+                grads[l * 4 * ndir + d * 4 + 1] = None if sink is not None else dwhh
                 grads[l * 4 * ndir + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
                 grads[l * 4 * ndir + d * 4 + 3] = dbhh[d * K3:(d + 1) * K3]
             # ---- gradient w.r.t. the layer input ----

@@ -78,3 +78,22 @@ def test_gru_large_per_gpu_batch(cuda_lib, B, H):
     for (n, p64), (_, pc) in zip(rnn64.named_parameters(), rnn_c.named_parameters()):
         ref = p64.grad
         assert (pc.grad.double().cpu() - ref).abs().max().item() < 3e-2 * ref.abs().max().item() + 1e-4, n
+
+
+def test_gru_wgrad_accumulates_into_existing_grad(cuda_lib):
+    """With .grad already allocated (FlatSGD / zero_grad(set_to_none=False)) the weight-gradient
+    GEMMs reduce-add straight into it; two backward passes must give exactly 2x one pass."""
+    from speech_b200.ops import gru_stack
+    torch.manual_seed(3)
+    rnn = torch.nn.GRU(64, 128, 2, batch_first=True, bidirectional=True).cuda()
+    x = torch.randn(8, 7, 64).cuda()
+    gru_stack(x, rnn).sum().backward()                    # .grad is None -> returned-gradient path
+    ref = [p.grad.clone() for p in rnn.parameters()]
+    for p in rnn.parameters():
+        p.grad.zero_()
+    gru_stack(x, rnn).sum().backward()                    # fused accumulation path
+    for p, r in zip(rnn.parameters(), ref):
+        assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-6)
+    gru_stack(x, rnn).sum().backward()
+    for p, r in zip(rnn.parameters(), ref):
+        assert torch.allclose(p.grad, 2 * r, rtol=1e-5, atol=1e-6)
