@@ -247,7 +247,8 @@ class GRUStackFunction(torch.autograd.Function):
             dfc_w = dw2[:V, :H] if ndir == 1 else dw2[:V, :H] + dw2[:V, H:]
             dfc_b = dout.sum((0, 1))
         elif B == Bp:
-            dY = dout.transpose(0, 1).reshape(M, D).float()
+            # (dout may be an expanded stride-0 tensor, e.g. from y.sum(): force a real copy)
+            dY = dout.transpose(0, 1).float().contiguous().view(M, D)
         else:
             dY = torch.zeros(T, Bp, D, dtype=torch.float32, device=dev)
             dY[:, :B] = dout.transpose(0, 1)
