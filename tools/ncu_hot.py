@@ -1,5 +1,5 @@
 """Developer tool: print the hottest SASS lines (warp-stall samples) of an ncu report's source page.
-    ncu -i rep.ncu-rep --page source --csv > src.csv ; python tools_ncu_hot.py src.csv [N]"""
+    ncu -i rep.ncu-rep --page source --csv > src.csv ; python tools/ncu_hot.py src.csv [N]"""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 20

@@ -1,5 +1,5 @@
 """Developer tool: run every kernel once at small sizes (for compute-sanitizer).
-    compute-sanitizer --tool memcheck python tools_sanitize.py"""
+    compute-sanitizer --tool memcheck python tools/sanitize.py"""
 import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
