@@ -132,14 +132,19 @@ int sb_ctc_prefix_beam(const float* logp, const int* lens, int B, int T, int S, 
  *   sb_conv_col2im_relu  dA f32 [M][ldA] -> dC of the layer below (gather, masked by Pprev>0)
  *   sb_transpose_bf16    [R][C] -> [C][R] (weight-gradient operands)
  * ------------------------------------------------------------------------------------- */
-int sb_conv_im2col(const float* src, void* dst_bf16, int B, int Ti, int Fi, int Ci, int kh, int kw,
-                   int stride, int Kp, int relu, void* stream);
-int sb_conv_relu_to_bct(const float* C, float* out, int B, int To, int Fo, int Co, void* stream);
-int sb_conv_dtop(const float* dY, const float* C, void* dC_bf16, float* db, int B, int To, int Fo,
-                 int Co, void* stream);
-int sb_conv_col2im_relu(const float* dA, long long ldA, const float* Pprev, void* dCprev_bf16,
-                        float* db, int B, int Ti, int Fi, int Ci, int kh, int kw, int stride,
-                        void* stream);
+/* `mask_u8` (may be NULL): dropout keep-bytes (1 keep, 0 drop) of the activations involved, same
+ * pixel-major channels-last layout as those activations; kept values are multiplied by `mscale`
+ * = 1/(1-p) (nn.Dropout after ReLU, model.py:25-26). */
+int sb_conv_im2col(const float* src, const void* mask_u8, float mscale, void* dst_bf16, int B,
+                   int Ti, int Fi, int Ci, int kh, int kw, int stride, int Kp, int relu,
+                   void* stream);
+int sb_conv_relu_to_bct(const float* C, const void* mask_u8, float mscale, float* out, int B,
+                        int To, int Fo, int Co, void* stream);
+int sb_conv_dtop(const float* dY, const float* C, const void* mask_u8, float mscale,
+                 void* dC_bf16, float* db, int B, int To, int Fo, int Co, void* stream);
+int sb_conv_col2im_relu(const float* dA, long long ldA, const float* Pprev,
+                        const void* maskprev_u8, float mscale, void* dCprev_bf16, float* db, int B,
+                        int Ti, int Fi, int Ci, int kh, int kw, int stride, void* stream);
 int sb_transpose_bf16(const void* src, void* dst, long long R, int C, long long ld_src,
                       long long ld_dst, void* stream);
 

@@ -28,12 +28,12 @@ SIGNATURES = {
     "sb_ctc_prefix_beam_workspace_size": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_sz)]),
     "sb_ctc_prefix_beam": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp,
                                     _vp, _c_sz, _vp]),
-    "sb_conv_im2col": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
-                                _c_int, _c_int, _vp]),
-    "sb_conv_relu_to_bct": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
-    "sb_conv_dtop": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
-    "sb_conv_col2im_relu": (_c_int, [_vp, _c_ll, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int,
-                                     _c_int, _c_int, _c_int, _vp]),
+    "sb_conv_im2col": (_c_int, [_vp, _vp, _fl, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                _c_int, _c_int, _c_int, _vp]),
+    "sb_conv_relu_to_bct": (_c_int, [_vp, _vp, _fl, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "sb_conv_dtop": (_c_int, [_vp, _vp, _vp, _fl, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "sb_conv_col2im_relu": (_c_int, [_vp, _c_ll, _vp, _vp, _fl, _vp, _vp, _c_int, _c_int, _c_int,
+                                     _c_int, _c_int, _c_int, _c_int, _vp]),
     "sb_transpose_bf16": (_c_int, [_vp, _vp, _c_ll, _c_int, _c_ll, _c_ll, _vp]),
     "sb_sumsq": (_c_int, [_vp, _c_ll, _vp, _vp]),
     "sb_sgd_clip_step": (_c_int, [_vp, _vp, _vp, _c_ll, _vp, _fl, _fl, _fl, _vp]),

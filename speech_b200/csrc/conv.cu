@@ -30,7 +30,8 @@ typedef __nv_bfloat16 bf16;
 // One thread produces 8 consecutive K entries (one 16-byte store).  For Ci % 8 == 0 these are 8
 // channels of one tap (two float4 loads); otherwise the scalar path is used per element.
 __global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int Ti, int Fi, int Ci,
+im2col_kernel(const float* __restrict__ src, const unsigned char* __restrict__ mask,
+              float mscale, bf16* __restrict__ dst, int B, int Ti, int Fi, int Ci,
               int kh, int kw, int s, int To, int Fo, int Kp, int relu) {
   const int K = kh * kw * Ci;
   const int kvec = Kp >> 3;                       // 8-wide groups per row
@@ -50,10 +51,20 @@ im2col_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int 
       const int ci = k0 % Ci;
       const int ij = k0 / Ci;
       const int j = ij % kw, i = ij / kw;
-      const float4* p = reinterpret_cast<const float4*>(
-          src + (((long long)b * Ti + (s * t + i)) * Fi + (s * f + j)) * Ci + ci);
+      const long long off = (((long long)b * Ti + (s * t + i)) * Fi + (s * f + j)) * Ci + ci;
+      const float4* p = reinterpret_cast<const float4*>(src + off);
       const float4 a = __ldg(p), c = __ldg(p + 1);
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+      if (relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+      }
+      if (mask) {   // dropout of the layer below: keep-byte per element, same layout as src
+        const uint2 mk = __ldg(reinterpret_cast<const uint2*>(mask + off));
+        const unsigned char* mb = reinterpret_cast<const unsigned char*>(&mk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = mb[e] ? v[e] * mscale : 0.f;
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -63,13 +74,12 @@ im2col_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int 
           const int ci = k % Ci;
           const int ij = k / Ci;
           const int j = ij % kw, i = ij / kw;
-          v[e] = __ldg(src + (((long long)b * Ti + (s * t + i)) * Fi + (s * f + j)) * Ci + ci);
+          const long long off = (((long long)b * Ti + (s * t + i)) * Fi + (s * f + j)) * Ci + ci;
+          v[e] = __ldg(src + off);
+          if (relu) v[e] = fmaxf(v[e], 0.f);
+          if (mask) v[e] = mask[off] ? v[e] * mscale : 0.f;
         }
       }
-    }
-    if (relu) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
     }
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -80,8 +90,8 @@ im2col_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int 
 
 // ---- final relayout: C[(b*To+t)*Fo+f][c] -> out[b][t][c*Fo + f] with ReLU ------------------------
 __global__ void __launch_bounds__(256)
-relu_to_bct_kernel(const float* __restrict__ C, float* __restrict__ out, int B, int To, int Fo,
-                   int Co) {
+relu_to_bct_kernel(const float* __restrict__ C, const unsigned char* __restrict__ mask,
+                   float mscale, float* __restrict__ out, int B, int To, int Fo, int Co) {
   const long long total = (long long)B * To * Fo * Co;
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * 256) {
@@ -90,13 +100,17 @@ relu_to_bct_kernel(const float* __restrict__ C, float* __restrict__ out, int B, 
     long long r = idx / Fo;
     const int c = (int)(r % Co);
     r /= Co;                       // r = b*To + t
-    out[idx] = fmaxf(__ldg(C + (r * Fo + f) * Co + c), 0.f);
+    const long long src = (r * Fo + f) * Co + c;
+    float v = fmaxf(__ldg(C + src), 0.f);
+    if (mask) v = mask[src] ? v * mscale : 0.f;
+    out[idx] = v;
   }
 }
 
 // ---- top of backward: dY[b][t][c*Fo+f] * (C > 0) -> dC[(b*To+t)*Fo+f][c] bf16, db[c] += ----------
 __global__ void __launch_bounds__(256)
-dconv_top_kernel(const float* __restrict__ dY, const float* __restrict__ C, bf16* __restrict__ dC,
+dconv_top_kernel(const float* __restrict__ dY, const float* __restrict__ C,
+                 const unsigned char* __restrict__ mask, float mscale, bf16* __restrict__ dC,
                  float* __restrict__ db, int B, int To, int Fo, int Co) {
   extern __shared__ float dbs[];
   for (int c = threadIdx.x; c < Co; c += 256) dbs[c] = 0.f;
@@ -110,6 +124,7 @@ dconv_top_kernel(const float* __restrict__ dY, const float* __restrict__ C, bf16
     const long long r = m / Fo;
     float g = __ldg(dY + (r * Co + c) * Fo + f);
     if (__ldg(C + idx) <= 0.f) g = 0.f;
+    else if (mask) g = mask[idx] ? g * mscale : 0.f;
     dC[idx] = __float2bfloat16_rn(g);
     if (g != 0.f) atomicAdd(&dbs[c], g);
   }
@@ -126,6 +141,7 @@ dconv_top_kernel(const float* __restrict__ dY, const float* __restrict__ C, bf16
 template <int MAXI, int MAXJ>
 __global__ void __launch_bounds__(256)
 col2im_relu_kernel(const float* __restrict__ dA, long long ldA, const float* __restrict__ Pprev,
+                   const unsigned char* __restrict__ maskprev, float mscale,
                    bf16* __restrict__ dCprev, float* __restrict__ db, int B, int Ti, int Fi,
                    int Ci, int kh, int kw, int s, int To, int Fo) {
   extern __shared__ float dbs[];
@@ -162,6 +178,7 @@ col2im_relu_kernel(const float* __restrict__ dA, long long ldA, const float* __r
 #pragma unroll
     for (int e = 0; e < MAXI * MAXJ; ++e) g += v[e];
     if (mask <= 0.f) g = 0.f;
+    else if (maskprev) g = maskprev[idx] ? g * mscale : 0.f;
     dCprev[idx] = __float2bfloat16_rn(g);
     if (g != 0.f) atomicAdd(&dbs[ci], g);
   }
@@ -225,41 +242,50 @@ static int grid_for(long long total) {
 
 using namespace sb;
 
-extern "C" int sb_conv_im2col(const float* src, void* dst_bf16, int B, int Ti, int Fi, int Ci,
-                              int kh, int kw, int stride, int Kp, int relu, void* stream_) {
+extern "C" int sb_conv_im2col(const float* src, const void* mask_u8, float mscale,
+                              void* dst_bf16, int B,
+                              int Ti, int Fi, int Ci, int kh, int kw, int stride, int Kp,
+                              int relu, void* stream_) {
   if (!src || !dst_bf16 || B <= 0 || Ci <= 0 || kh <= 0 || kw <= 0 || stride <= 0)
     return SB_ERR_INVALID;
   const int To = (Ti - kh) / stride + 1, Fo = (Fi - kw) / stride + 1;
   if (To <= 0 || Fo <= 0 || Kp < kh * kw * Ci) return SB_ERR_INVALID;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const long long total = (long long)B * To * Fo * Kp;
-  im2col_kernel<<<grid_for(total), 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst_bf16), B, Ti,
-                                                     Fi, Ci, kh, kw, stride, To, Fo, Kp, relu);
+  const long long total = (long long)B * To * Fo * (Kp / 8);
+  im2col_kernel<<<grid_for(total), 256, 0, stream>>>(
+      src, reinterpret_cast<const unsigned char*>(mask_u8), mscale,
+      reinterpret_cast<bf16*>(dst_bf16), B, Ti, Fi,
+      Ci, kh, kw, stride, To, Fo, Kp, relu);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
-extern "C" int sb_conv_relu_to_bct(const float* C, float* out, int B, int To, int Fo, int Co,
-                                   void* stream_) {
+extern "C" int sb_conv_relu_to_bct(const float* C, const void* mask_u8, float mscale,
+                                   float* out, int B,
+                                   int To, int Fo, int Co, void* stream_) {
   if (!C || !out || B <= 0 || To <= 0 || Fo <= 0 || Co <= 0) return SB_ERR_INVALID;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  relu_to_bct_kernel<<<grid_for((long long)B * To * Fo * Co), 256, 0, stream>>>(C, out, B, To, Fo,
-                                                                               Co);
+  relu_to_bct_kernel<<<grid_for((long long)B * To * Fo * Co), 256, 0, stream>>>(
+      C, reinterpret_cast<const unsigned char*>(mask_u8), mscale, out, B, To, Fo, Co);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
-extern "C" int sb_conv_dtop(const float* dY, const float* C, void* dC_bf16, float* db, int B,
-                            int To, int Fo, int Co, void* stream_) {
+extern "C" int sb_conv_dtop(const float* dY, const float* C, const void* mask_u8, float mscale,
+                            void* dC_bf16,
+                            float* db, int B, int To, int Fo, int Co, void* stream_) {
   if (!dY || !C || !dC_bf16 || !db || B <= 0 || To <= 0 || Fo <= 0 || Co <= 0)
     return SB_ERR_INVALID;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   dconv_top_kernel<<<grid_for((long long)B * To * Fo * Co), 256, Co * sizeof(float), stream>>>(
-      dY, C, reinterpret_cast<bf16*>(dC_bf16), db, B, To, Fo, Co);
+      dY, C, reinterpret_cast<const unsigned char*>(mask_u8), mscale,
+      reinterpret_cast<bf16*>(dC_bf16), db, B, To, Fo, Co);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
 extern "C" int sb_conv_col2im_relu(const float* dA, long long ldA, const float* Pprev,
-                                   void* dCprev_bf16, float* db, int B, int Ti, int Fi, int Ci,
-                                   int kh, int kw, int stride, void* stream_) {
+                                   const void* maskprev_u8, float mscale, void* dCprev_bf16,
+                                   float* db, int B,
+                                   int Ti, int Fi, int Ci, int kh, int kw, int stride,
+                                   void* stream_) {
   if (!dA || !Pprev || !dCprev_bf16 || !db || B <= 0) return SB_ERR_INVALID;
   const int To = (Ti - kh) / stride + 1, Fo = (Fi - kw) / stride + 1;
   if (To <= 0 || Fo <= 0) return SB_ERR_INVALID;
@@ -270,8 +296,10 @@ extern "C" int sb_conv_col2im_relu(const float* dA, long long ldA, const float* 
   const size_t sm = Ci * sizeof(float);
   if ((long long)B * Ti * Fi >= (1LL << 31)) return SB_ERR_UNSUPPORTED;
 #define SB_C2I(I, J)                                                                              \
-  col2im_relu_kernel<I, J><<<g, 256, sm, stream>>>(dA, ldA, Pprev, out, db, B, Ti, Fi, Ci, kh, kw, \
-                                                   stride, To, Fo)
+  col2im_relu_kernel<I, J><<<g, 256, sm, stream>>>(                                                \
+      dA, ldA, Pprev, reinterpret_cast<const unsigned char*>(maskprev_u8), mscale, out, db, B, Ti,  \
+      Fi, Ci, kh, kw,                                                                                 \
+      stride, To, Fo)
   if (ni <= 2 && nj <= 2) SB_C2I(2, 2);
   else if (ni <= 3 && nj <= 4) SB_C2I(3, 4);
   else if (ni <= 5 && nj <= 8) SB_C2I(5, 8);

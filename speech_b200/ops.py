@@ -196,7 +196,7 @@ class GRUStackFunction(torch.autograd.Function):
             mask = None
             if dropout > 0.0 and l + 1 < L:
                 # inter-layer dropout of nn.GRU(dropout=p): applied to every layer output but the last
-                mask = (torch.rand(M, D, device=dev) >= dropout).to(torch.bfloat16) / (1.0 - dropout)
+                mask = (torch.rand(M, D, device=dev) >= dropout).float() * (1.0 / (1.0 - dropout))
                 xn = xn * mask
             if need_grad:
                 saved.append((X, y, gates, xnT, mask))
@@ -345,26 +345,30 @@ def _gru_weights(rnn):
     return ndir, weights
 
 
+GRU_MAX_BATCH = 128   # rows one recurrence launch keeps resident (gru.cu)
+
+
+def _batch_chunks(x, fn):
+    """The recurrence is independent across utterances, so a minibatch larger than one launch
+    holds is run as consecutive chunks of <= GRU_MAX_BATCH rows (exact, autograd sees a cat)."""
+    if x.shape[0] <= GRU_MAX_BATCH:
+        return fn(x)
+    return torch.cat([fn(x[i:i + GRU_MAX_BATCH]) for i in range(0, x.shape[0], GRU_MAX_BATCH)], 0)
+
+
 def gru_stack_logits(x, rnn, fc, dropout=0.0):
     """GRU stack + sum of direction halves + output projection `fc` (an nn.Linear), fused:
     returns logits (B, T, V) - the encoder tail of CTC.forward_impl (ctc_model.py:25-32)."""
     ndir, weights = _gru_weights(rnn)
-    return GRUStackFunction.apply(x, ndir, rnn.hidden_size, float(dropout), fc.weight, fc.bias,
-                                  *weights)
+    return _batch_chunks(x, lambda xc: GRUStackFunction.apply(
+        xc, ndir, rnn.hidden_size, float(dropout), fc.weight, fc.bias, *weights))
 
 
 def gru_stack(x, rnn, dropout=0.0):
     """Run the sm_100a GRU stack with the parameters of an nn.GRU module (batch_first, h0 = 0)."""
-    ndir = 2 if rnn.bidirectional else 1
-    weights = []
-    for l in range(rnn.num_layers):
-        for d in range(ndir):
-            sfx = "_l%d%s" % (l, "_reverse" if d == 1 else "")
-            if not rnn.bias:
-                raise _lib.SpeechB200Error("GRU without bias is not supported")
-            weights += [getattr(rnn, "weight_ih" + sfx), getattr(rnn, "weight_hh" + sfx),
-                        getattr(rnn, "bias_ih" + sfx), getattr(rnn, "bias_hh" + sfx)]
-    return GRUStackFunction.apply(x, ndir, rnn.hidden_size, float(dropout), None, None, *weights)
+    ndir, weights = _gru_weights(rnn)
+    return _batch_chunks(x, lambda xc: GRUStackFunction.apply(
+        xc, ndir, rnn.hidden_size, float(dropout), None, None, *weights))
 
 
 def _transpose_bf16(src, rows_pad=8):
@@ -388,7 +392,9 @@ class ConvStackFunction(torch.autograd.Function):
     the reference's channel-major feature order (model.py:66-71)."""
 
     @staticmethod
-    def forward(ctx, x, specs, *params):
+    def forward(ctx, x, specs, dropout, *params):
+        """dropout > 0: nn.Dropout(p) after every ReLU (model.py:25-26) as a keep-byte mask
+        (scaled by 1/(1-p)) in the activations' own layout, applied by the kernels that read them."""
         _lib.require_cuda(x, "x")
         lib = _lib.load()
         dev = x.device
@@ -396,6 +402,8 @@ class ConvStackFunction(torch.autograd.Function):
         Ci = 1
         cur = x.detach().float().contiguous()
         saved = []
+        masks = []
+        mscale = 1.0 / (1.0 - dropout) if dropout > 0.0 else 1.0
         need_grad = any(ctx.needs_input_grad)
         sp = _lib.stream_ptr()
         for l, (kh, kw, s_) in enumerate(specs):
@@ -409,19 +417,28 @@ class ConvStackFunction(torch.autograd.Function):
             M = B * To * Fo
             A = torch.empty(M, Kp, dtype=torch.bfloat16, device=dev)
             src = cur
+            mprev = masks[l - 1] if l > 0 else None
             _launch("conv_im2col", 0.0,
-                    lambda: lib.sb_conv_im2col(src.data_ptr(), A.data_ptr(), B, Ti, Fi, Ci, kh, kw,
-                                               s_, Kp, 1 if l > 0 else 0, sp))
+                    lambda: lib.sb_conv_im2col(src.data_ptr(), _lib.ptr(mprev), mscale, A.data_ptr(), B, Ti,
+                                               Fi, Ci, kh, kw, s_, Kp, 1 if l > 0 else 0, sp))
             Wp = torch.zeros(Co, Kp, dtype=torch.bfloat16, device=dev)
             Wp[:, :K] = w.detach().permute(0, 2, 3, 1).reshape(Co, K)
             C = gemm_bf16_tn(A, Wp, bias=b.detach().float().contiguous())
+            mask = None
+            if dropout > 0.0:
+                mask = (torch.rand(M, Co, device=dev) >= dropout).to(torch.uint8)
+            masks.append(mask)
             if need_grad:
                 saved.append((A, cur, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp)))
             cur, Ti, Fi, Ci = C, To, Fo, Co
         out = torch.empty(B, Ti, Ci * Fi, dtype=torch.float32, device=dev)
         _launch("conv_relu_to_bct", 0.0,
-                lambda: lib.sb_conv_relu_to_bct(cur.data_ptr(), out.data_ptr(), B, Ti, Fi, Ci, sp))
+                lambda: lib.sb_conv_relu_to_bct(cur.data_ptr(), _lib.ptr(masks[-1]), mscale,
+                                                out.data_ptr(),
+                                                B, Ti, Fi, Ci, sp))
         ctx.saved = saved
+        ctx.masks = masks
+        ctx.mscale = mscale
         ctx.B = B
         ctx.nl = len(specs)
         return out
@@ -443,7 +460,9 @@ class ConvStackFunction(torch.autograd.Function):
                 db = torch.zeros(Co, dtype=torch.float32, device=dev)
                 dCl = dC
                 _launch("conv_dtop", 0.0,
-                        lambda: lib.sb_conv_dtop(dY.data_ptr(), C.data_ptr(), dCl.data_ptr(),
+                        lambda: lib.sb_conv_dtop(dY.data_ptr(), C.data_ptr(),
+                                                 _lib.ptr(ctx.masks[l]), ctx.mscale,
+                                                 dCl.data_ptr(),
                                                  db.data_ptr(), B, To, Fo, Co, sp))
             grads[2 * l + 1] = db
             # weight gradient: dWp[Co][Kp] = dC^T [Co][M] . A^T [Kp][M]^T   (K = M, split-K)
@@ -460,12 +479,15 @@ class ConvStackFunction(torch.autograd.Function):
                 db = torch.zeros(Ci, dtype=torch.float32, device=dev)
                 _launch("conv_col2im_relu", 0.0,
                         lambda: lib.sb_conv_col2im_relu(dA.data_ptr(), dA.stride(0),
-                                                        Pprev.data_ptr(), dCp.data_ptr(),
+                                                        Pprev.data_ptr(),
+                                                        _lib.ptr(ctx.masks[l - 1]), ctx.mscale,
+                                                        dCp.data_ptr(),
                                                         db.data_ptr(), B, Ti, Fi, Ci, kh, kw, s_,
                                                         sp))
                 dC = dCp
         ctx.saved = None
-        return (None, None) + tuple(grads)
+        ctx.masks = None
+        return (None, None, None) + tuple(grads)
 
 
 def conv_stack(x, conv, training):
@@ -473,12 +495,15 @@ def conv_stack(x, conv, training):
 
     x (B, T, F) -> (B, T', C*F') with the reference's channel-major feature flattening
     (transpose(1,2) of (B,C,T',F') then view, model.py:66-71).  Runs on our im2col + tcgen05
-    kernels; only a stack with ACTIVE conv dropout (training and p > 0) still goes through the
-    nn modules (cuDNN), because the dropout mask sits between ReLU and the next im2col.
+    kernels, including the Dropout after each ReLU when training.  Shapes the kernels do not
+    cover (grouped / dilated / padded convolutions, out_channels not a multiple of 8: none of
+    which the reference can express, model.py:21-23) go through the nn modules.
     """
     mods = list(conv.children())
     convs = [m for m in mods if isinstance(m, torch.nn.Conv2d)]
-    drop = any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in mods) and training
+    ps = [m.p for m in mods if isinstance(m, torch.nn.Dropout)]
+    p_drop = (ps[0] if ps else 0.0) if training else 0.0
+    drop = len(set(ps)) > 1
     simple = all(c.stride[0] == c.stride[1] and c.padding == (0, 0) and c.dilation == (1, 1)
                  and c.groups == 1 and c.bias is not None and c.out_channels % 8 == 0
                  for c in convs)
@@ -487,7 +512,7 @@ def conv_stack(x, conv, training):
         params = []
         for c in convs:
             params += [c.weight, c.bias]
-        return ConvStackFunction.apply(x, specs, *params)
+        return ConvStackFunction.apply(x, specs, float(p_drop), *params)
     y = conv(x.unsqueeze(1))
     b, c, t, f = y.shape
     return y.transpose(1, 2).reshape(b, t, c * f)

@@ -61,3 +61,55 @@ def test_conv_stack_forward_backward(cuda_lib, specs, B, T, F):
         ref = p64.grad
         err = (pc.grad.double().cpu() - ref).abs().max().item()
         assert err < 3e-2 * ref.abs().max().item() + 1e-4, (n, err, ref.abs().max().item())
+
+
+def test_conv_stack_dropout_matches_masked_reference(cuda_lib):
+    """Training-time Dropout after each ReLU (model.py:25-26) runs inside our kernels: the masks
+    are drawn with torch.rand in layer order, so re-seeding reproduces them for the reference."""
+    from speech_b200 import ops
+    specs, B, T, F, p = [[8, 5, 8, 2], [16, 3, 4, 1]], 3, 61, 40, 0.4
+    torch.manual_seed(5)
+    layers, in_c = [], 1
+    for out_c, h, w, s in specs:
+        layers += [torch.nn.Conv2d(in_c, out_c, (h, w), stride=(s, s)), torch.nn.ReLU(),
+                   torch.nn.Dropout(p)]
+        in_c = out_c
+    conv = torch.nn.Sequential(*layers).cuda()
+    x = torch.randn(B, T, F).cuda()
+
+    torch.manual_seed(99)
+    y = ops.conv_stack(x, conv, True)
+    wgt = torch.randn_like(y)
+    (y * wgt).sum().backward()
+    got = {n: q.grad.clone() for n, q in conv.named_parameters()}
+
+    def rnd(t):
+        return t + (t.detach().float().bfloat16().double() - t.detach())
+
+    torch.manual_seed(99)
+    h = rnd(x.double().unsqueeze(1))
+    params = {n: q.detach().double().requires_grad_(True) for n, q in conv.named_parameters()}
+    mods = [m for m in conv if isinstance(m, torch.nn.Conv2d)]
+    for li, m in enumerate(mods):
+        pre = torch.nn.functional.conv2d(h, rnd(params["%d.weight" % (3 * li)]),
+                                         params["%d.bias" % (3 * li)], stride=m.stride)
+        b, c, t, f = pre.shape
+        mask = (torch.rand(b * t * f, c, device="cuda") >= p).double() / (1.0 - p)
+        mask = mask.view(b, t, f, c).permute(0, 3, 1, 2)
+        h = torch.relu(pre) * mask
+        if li + 1 < len(mods):
+            h = rnd(h)
+    b, c, t, f = h.shape
+    y64 = h.transpose(1, 2).reshape(b, t, c * f)
+    (y64 * wgt.double()).sum().backward()
+    zero_frac = (y == 0).float().mean().item()
+    assert zero_frac > p * 0.8                      # dropout really happened
+    scale = y64.abs().max().item()
+    assert (y.double() - y64).abs().max().item() < 2e-3 * scale
+    for n, ref in params.items():
+        err = (got[n].double() - ref.grad).abs().max().item()
+        assert err < 3e-2 * ref.grad.abs().max().item() + 1e-4, (n, err)
+    # eval mode: no dropout, deterministic
+    y1 = ops.conv_stack(x, conv, False)
+    y2 = ops.conv_stack(x, conv, False)
+    assert torch.equal(y1, y2)

@@ -97,3 +97,16 @@ def test_gru_wgrad_accumulates_into_existing_grad(cuda_lib):
     gru_stack(x, rnn).sum().backward()
     for p, r in zip(rnn.parameters(), ref):
         assert torch.allclose(p.grad, 2 * r, rtol=1e-5, atol=1e-6)
+
+
+def test_gru_minibatch_above_one_launch_is_chunked(cuda_lib):
+    """A minibatch of more rows than one recurrence launch holds (128) runs as consecutive chunks;
+    utterances are independent, so outputs and gradients still match the fp64 reference."""
+    rnn64, x64, y64, rnn_c, xc, yc = _ref_and_ours(150, 5, 32, 64, 2, True, seed=150)
+    assert yc.shape == y64.shape
+    assert (yc.double().cpu() - y64).abs().max().item() < 2e-2
+    assert (xc.grad.double().cpu() - x64.grad).abs().max().item() < \
+        3e-2 * x64.grad.abs().max().item() + 1e-4
+    for (n, p64), (_, pc) in zip(rnn64.named_parameters(), rnn_c.named_parameters()):
+        ref = p64.grad
+        assert (pc.grad.double().cpu() - ref).abs().max().item() < 3e-2 * ref.abs().max().item() + 1e-4, n
