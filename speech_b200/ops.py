@@ -106,6 +106,26 @@ def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=N
     return out
 
 
+_grad_ready_hook = None
+_announce = True
+
+
+def set_grad_ready_hook(fn):
+    """fn(list_of_parameters) is called from inside GRUStackFunction.backward as soon as the
+    gradients of one layer's parameters are final in their .grad buffers (all producing kernels
+    enqueued on the current stream).  Used by optim.FlatSGD to start that layer's all-reduce
+    while the layers below are still being differentiated.  None disables."""
+    global _grad_ready_hook
+    _grad_ready_hook = fn
+
+
+def _bias_sink(param):
+    g = getattr(param, "grad", None)
+    if g is None or not g.is_cuda or g.dtype != torch.float32:
+        return None
+    return g
+
+
 def _grad_sink(param, rows=None):
     """The parameter's existing .grad (optionally a row slice) if the weight-gradient GEMM can
     accumulate straight into it (fp32, contiguous, 16-byte aligned rows), else None.  Writing
@@ -202,6 +222,7 @@ class GRUStackFunction(torch.autograd.Function):
                 saved.append((X, y, gates, xnT, mask))
             X = xn
         ctx.saved = saved
+        ctx.announce = _announce
         ctx.weights = weights
         ctx.dims = (B, T, In, Bp, H, ndir, L)
         ctx.fc = None
@@ -320,6 +341,21 @@ class GRUStackFunction(torch.autograd.Function):
                 grads[l * 4 * ndir + d * 4 + 1] = None if sink is not None else dwhh
                 grads[l * 4 * ndir + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
                 grads[l * 4 * ndir + d * 4 + 3] = dbhh[d * K3:(d + 1) * K3]
+            if _grad_ready_hook is not None and ctx.announce:
+                base = l * 4 * ndir
+                if all(grads[base + d * 4 + k] is None for d in range(ndir) for k in (0, 1)):
+                    # weights already sit in .grad; add the biases there too, then announce
+                    ok = True
+                    for d in range(ndir):
+                        for k in (2, 3):
+                            sink = _bias_sink(wl[d * 4 + k])
+                            if sink is None:
+                                ok = False
+                                continue
+                            sink.add_(grads[base + d * 4 + k])
+                            grads[base + d * 4 + k] = None
+                    if ok:
+                        _grad_ready_hook(list(wl))
             # ---- gradient w.r.t. the layer input ----
             if l > 0 or ctx.needs_input_grad[0]:
                 wihT = torch.zeros(Kl, ndir * K3, dtype=torch.bfloat16, device=dev)
@@ -351,9 +387,15 @@ GRU_MAX_BATCH = 128   # rows one recurrence launch keeps resident (gru.cu)
 def _batch_chunks(x, fn):
     """The recurrence is independent across utterances, so a minibatch larger than one launch
     holds is run as consecutive chunks of <= GRU_MAX_BATCH rows (exact, autograd sees a cat)."""
+    global _announce
     if x.shape[0] <= GRU_MAX_BATCH:
         return fn(x)
-    return torch.cat([fn(x[i:i + GRU_MAX_BATCH]) for i in range(0, x.shape[0], GRU_MAX_BATCH)], 0)
+    _announce = False     # several backward passes add into the same .grad: none of them is final
+    try:
+        return torch.cat([fn(x[i:i + GRU_MAX_BATCH])
+                          for i in range(0, x.shape[0], GRU_MAX_BATCH)], 0)
+    finally:
+        _announce = True
 
 
 def gru_stack_logits(x, rnn, fc, dropout=0.0):

@@ -10,18 +10,21 @@ Drop-in for the pair the reference uses (train.py:32-35,95-97):
     grad_norm = opt.step()                 # all-reduce (if world_size > 1) + clip + update
 
 Parameters and gradients are re-pointed to views of two contiguous fp32 buffers (state_dict names
-and values are unchanged), so zero_grad is one memset, the data-parallel all-reduce is one NCCL
-call, and clip + update are two kernels (csrc/elementwise.cu) with no host synchronisation: the
+and values are unchanged), so zero_grad is one memset, the data-parallel all-reduce runs over
+slices of one buffer (one per GRU layer, issued during backward so that it overlaps the remaining
+layers, plus one for the rest), and clip + update are two kernels (csrc/elementwise.cu) with no host synchronisation: the
 clip coefficient stays on the device.  `step()` returns the pre-clip gradient norm as a 0-dim
 CUDA tensor (what train.py logs as grad_norm).
 """
 import torch
 
 from . import _lib, ops
+from .parallel import BucketReducer
 
 
 class FlatSGD:
-    def __init__(self, model, lr, momentum=0.0, max_grad_norm=200.0, world_size=1, group=None):
+    def __init__(self, model, lr, momentum=0.0, max_grad_norm=200.0, world_size=1, group=None,
+                 overlap=True):
         self.lr = float(lr)
         self.momentum = float(momentum)
         self.max_norm = float(max_grad_norm)
@@ -40,19 +43,29 @@ class FlatSGD:
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.mom = torch.zeros(n, dtype=torch.float32, device=dev) if self.momentum != 0 else None
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.spans = {}
         for p, o in zip(self.params, offs):
             view = self.flat_p[o:o + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
             p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+            self.spans[id(p)] = (o, o + (p.numel() + 3) // 4 * 4)
+        self.reducer = BucketReducer(self.flat_g, world_size, group)
+        if world_size > 1 and overlap:
+            # GRU backward announces each layer's gradients as soon as they are final
+            ops.set_grad_ready_hook(self._grads_ready)
+
+    def _grads_ready(self, params):
+        spans = [self.spans.get(id(p)) for p in params]
+        if any(s is None for s in spans):
+            return
+        self.reducer.ready(min(s[0] for s in spans), max(s[1] for s in spans))
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
 
     def all_reduce(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        self.reducer.finish()
 
     def step(self):
         lib = _lib.load()
