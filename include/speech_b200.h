@@ -198,7 +198,9 @@ int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
 /* Developer hook (not part of the drop-in surface): device buffer of >= 64*16 uint64 receiving a
  * globaltimer timeline of CTA 0 for the next sb_gru_fwd launches; NULL disables. */
 int sb_debug_gru_timeline(void* dev_buffer);
-/* Developer hook: 1 forces the 128-row CTA tile in sb_gemm_bf16_tn (disables the 256-row variant). */
+/* Developer hook, kernel selection of sb_gemm_bf16_tn (default 1|4): bit 0 = no 256-row
+ * single-CTA tile variant, bit 1 = register-store epilogue instead of TMA stores, bit 2 = allow
+ * the CTA-pair (tcgen05 cta_group::2) kernel. */
 int sb_debug_gemm_mt1(int force);
 /* Developer hook: timing ablations of the forward GRU kernel (results become wrong; 0 = off). */
 int sb_debug_gru_flags(int flags);

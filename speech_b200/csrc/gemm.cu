@@ -34,6 +34,7 @@ struct GemmParams {
   int remap_B, remap_T, valid_B;
   int m_tiles, n_tiles;
   int tma_store;        // epilogue through swizzled smem + cp.async.bulk.tensor stores
+  int stream_k;         // pair kernel: balanced tiles x k-blocks partition (accumulate mode)
 };
 
 // MT = number of 128-row MMA sub-tiles per CTA tile.  MT = 2 (256 x BN CTA tile) re-uses every B
@@ -304,6 +305,318 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ----------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster compute one 256 x 256 tile.
+// Each CTA stages ITS 128 rows of A and ITS 128 rows of B; the pair's tensor cores read the B
+// halves from both shared memories, so per CTA and k-block the shared-memory traffic is
+// 16 KB written by TMA + 16 KB read by the MMA for 128x256x64 MACs, against 24 + 24 KB in the
+// single-CTA 128x256 tile - the single-CTA tile is bounded by shared-memory bandwidth
+// (~192 B/clk needed, 128 B/clk available => <= 67 % tensor utilisation, 55 % measured).
+//   * rank 0 (leader) issues every MMA; both CTAs run a TMA producer whose loads signal the
+//     LEADER's full barrier (cp.async.bulk.tensor.cta_group::2)
+//   * tcgen05.commit.multicast frees the smem slot in both CTAs and publishes the accumulator to
+//     both epilogues; the epilogues of both CTAs arrive on the leader's tmem-empty barrier
+// ----------------------------------------------------------------------------------------------
+SB_DEVINL uint32_t cta_rank_in_cluster() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SB_DEVINL void cluster_barrier_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+SB_DEVINL uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+SB_DEVINL void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t leader_bar, int32_t c0,
+                                int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar),
+        "r"(c0), "r"(c1)
+      : "memory");
+}
+SB_DEVINL void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+SB_DEVINL void umma_commit_pair(uint64_t* bar) {   // arrives at this offset in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+SB_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+SB_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > SB_SPIN_LIMIT) __trap();
+  }
+}
+
+// Work distribution of the pair kernel.  Classic: work item = (output tile, K split), round-robin.
+// Balanced ("stream-K", accumulate mode only): the tiles x k-blocks iteration space is cut into
+// one contiguous range per CTA pair, so every pair contracts the same number of k-blocks whatever
+// the tile count (the weight-gradient GEMMs have 2.6 waves of tiles: 14 % of the SMs idle in the
+// last wave otherwise); partial tiles are combined by the reduce-add epilogue.
+struct PairSched {
+  int stream, w, step, total_work, tiles_mn, kbt, kb_per_split, u, u1;
+  __device__ PairSched(const GemmParams& p, int pair_id, int n_pairs) {
+    stream = p.stream_k;
+    tiles_mn = p.m_tiles * p.n_tiles;
+    kbt = p.k_blocks_total;
+    total_work = tiles_mn * p.split_k;
+    kb_per_split = (kbt + p.split_k - 1) / p.split_k;
+    w = pair_id;
+    step = n_pairs;
+    const long long units = (long long)tiles_mn * kbt;
+    const long long per = (units + n_pairs - 1) / n_pairs;
+    long long a = per * pair_id, b = a + per;
+    if (a > units) a = units;
+    if (b > units) b = units;
+    u = (int)a;
+    u1 = (int)b;
+  }
+  // next piece of work: output tile index and k-block range [kb0, kb1)
+  __device__ bool next(int& tile, int& kb0, int& kb1) {
+    if (stream) {
+      if (u >= u1) return false;
+      tile = u / kbt;
+      kb0 = u - tile * kbt;
+      kb1 = kb0 + (u1 - u);
+      if (kb1 > kbt) kb1 = kbt;
+      u += kb1 - kb0;
+      return true;
+    }
+    if (w >= total_work) return false;
+    const int split = w / tiles_mn;
+    tile = w - split * tiles_mn;
+    kb0 = split * kb_per_split;
+    kb1 = kb0 + kb_per_split;
+    if (kb1 > kbt) kb1 = kbt;
+    w += step;
+    return true;
+  }
+};
+
+struct GemmPairCfg {
+  static constexpr int BN = 256;                              // N of the pair's tile
+  static constexpr int kStageBytes = (BM + BN / 2) * BK * 2;  // per CTA: 16 KB A + 16 KB B
+  static constexpr int kStages = 6;
+  static constexpr int kTmemCols = 512;                       // 2 accumulator stages x 256
+  static constexpr int kStageOutBytes = 4 * 2 * 4096;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  using Cfg = GemmPairCfg;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~static_cast<uintptr_t>(1023));
+  uint8_t* out_stage = tiles + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::kStageOutBytes);
+  uint64_t* full_bar = bars;                      // [kStages]  (the leader's are used)
+  uint64_t* empty_bar = bars + kStages;           // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;       // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]        (the leader's are used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cta_rank_in_cluster();
+  const int pair_id = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);   // 4 epilogue warps x 2 CTAs
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_barrier_all();   // the peer's barriers exist before anything signals them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  PairSched sched(p, pair_id, n_pairs);           // p.m_tiles counts 256-row pair tiles here
+  int tile, kb0, kb1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      while (sched.next(tile, kb0, kb1)) {
+        const int m_blk = tile / p.n_tiles;
+        const int n_blk = tile - m_blk * p.n_tiles;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * Cfg::kStageBytes;
+          uint8_t* sb_ = sa + BM * BK * 2;
+          const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          tma_load_2d_pair(sa, &tmap_a, lbar, kb * BK, m_blk * (2 * BM) + (int)rank * BM);
+          tma_load_2d_pair(sb_, &tmap_b, lbar, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      while (sched.next(tile, kb0, kb1)) {
+        if (lane == 0) mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+        __syncwarp();
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (lane == 0) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
+            const uint64_t da = umma_desc_sw128_kmajor(sa);
+            const uint64_t db = umma_desc_sw128_kmajor(sa + BM * BK * 2);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (kb1 <= kb0 && lane == 0) umma_commit_pair(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5, both CTAs) =====================
+    const int sub = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    unsigned int out_slot = 0;
+    while (sched.next(tile, kb0, kb1)) {
+      const int m_blk = tile / p.n_tiles;
+      const int n_blk = tile - m_blk * p.n_tiles;
+      const bool has_k = kb0 < kb1;
+      const bool add_bias = (p.bias != nullptr) && (kb0 == 0);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const int m0 = m_blk * (2 * BM) + (int)rank * BM + sub * 32;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(sub * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (has_k && n0 < p.N && m0 < p.M) {      // warp-uniform
+          uint8_t* buf = out_stage + ((warp - 2) * 2 + (out_slot & 1)) * 4096;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[j + 0]);
+            o.y = __uint_as_float(v[j + 1]);
+            o.z = __uint_as_float(v[j + 2]);
+            o.w = __uint_as_float(v[j + 3]);
+            if (add_bias) {
+              if (n0 + j + 0 < p.N) o.x += __ldg(p.bias + n0 + j + 0);
+              if (n0 + j + 1 < p.N) o.y += __ldg(p.bias + n0 + j + 1);
+              if (n0 + j + 2 < p.N) o.z += __ldg(p.bias + n0 + j + 2);
+              if (n0 + j + 3 < p.N) o.w += __ldg(p.bias + n0 + j + 3);
+            }
+            *reinterpret_cast<float4*>(buf + sw128_offset(lane, j >> 2)) = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.flags & SB_GEMM_ACCUMULATE)
+              asm volatile(
+                  "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group"
+                  " [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmap_c)),
+                  "r"(smem_u32(buf)), "r"(n0), "r"(m0)
+                  : "memory");
+            else
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group"
+                  " [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmap_c)),
+                  "r"(smem_u32(buf)), "r"(n0), "r"(m0)
+                  : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++out_slot;
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[acc]), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_barrier_all();   // neither CTA leaves while the pair's MMAs / remote arrives are in flight
+  if (warp == 1) {
+    tc_fence_after_sync();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -394,17 +707,44 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
 }
 
 static int g_gemm_force_mt1 = 1;   // the 256-row CTA tile measured slower (epilogue not overlapped)
+static int g_gemm_pair = 1;        // CTA-pair (cta_group::2) kernel for the large tiles
+
+// CTA-pair launch: needs the TMA-store epilogue (no row remap, 16-byte aligned C rows)
+static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p,
+                            cudaStream_t stream) {
+  using Cfg = GemmPairCfg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return SB_ERR_CUDA;
+    attr_set = true;
+  }
+  p.m_tiles = (p.M + 2 * BM - 1) / (2 * BM);
+  p.n_tiles = (p.N + Cfg::BN - 1) / Cfg::BN;
+  const int total = p.m_tiles * p.n_tiles * p.split_k;
+  int pairs = device_sm_count() / 2;
+  if (pairs > total) pairs = total;
+  CUtensorMap tc;
+  if (make_tmap_f32_c(&tc, p.C, p.M, p.N, p.ldc) != SB_OK) return SB_ERR_CUDA;
+  p.tma_store = 1;
+  gemm_bf16_tn_pair_kernel<<<2 * pairs, 192, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
+  return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
 
 }  // namespace sb
 
 using namespace sb;
 
-// developer hook: 1 disables the 256-row CTA tile variant
+// developer hook (kernel selection); the default state is force = 1 | 4
 extern "C" int sb_debug_gemm_mt1(int force) {
   // bit 0: 1 = 128-row CTA tiles only (default), 0 = allow the 256-row variant
   // bit 1: 1 = disable the TMA-store epilogue (register stores)
+  // bit 2: 1 = CTA-pair (cta_group::2) kernel for 256-wide tiles
   sb::g_gemm_force_mt1 = force & 1;
   sb::g_gemm_tma_store = (force & 2) ? 0 : 1;
+  sb::g_gemm_pair = (force & 4) ? 1 : 0;
   return SB_OK;
 }
 
@@ -423,6 +763,7 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   if (split_k > p.k_blocks_total) split_k = p.k_blocks_total;
   p.split_k = split_k; p.flags = flags;
   p.remap_B = remap_B; p.remap_T = remap_T; p.valid_B = valid_B;
+  p.stream_k = 0;
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = 0;
 
@@ -441,6 +782,22 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   if (bn == 256 && K >= 1024 && split_k == 1 && !g_gemm_force_mt1) {
     const long long tiles2 = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
     if (tiles2 >= 3LL * sms) mt = 2;
+  }
+  if (N > 128 && g_gemm_pair && g_gemm_tma_store && !(flags & SB_GEMM_ROW_REMAP) &&
+      (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+    const long long pair_tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
+    // accumulate mode: balanced tiles x k-blocks partition whatever split the caller suggested
+    const bool balanced = (flags & SB_GEMM_ACCUMULATE) != 0 &&
+                          pair_tiles * p.k_blocks_total >= 8LL * (sms / 2);
+    if (balanced || (bn == 256 && K >= 1024 && pair_tiles * split_k >= sms / 2)) {
+      p.stream_k = balanced ? 1 : 0;
+      CUtensorMap pa, pb;
+      int prc = make_tmap_bf16_2d(&pa, A, M, K, lda, BM);
+      if (prc != SB_OK) return prc;
+      prc = make_tmap_bf16_2d(&pb, B, N, K, ldb, 128);
+      if (prc != SB_OK) return prc;
+      return launch_gemm_pair(pa, pb, p, stream);
+    }
   }
   p.m_tiles = (M + mt * BM - 1) / (mt * BM);
   CUtensorMap ta, tb;

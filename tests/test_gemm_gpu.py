@@ -36,8 +36,9 @@ def _gemm(A, B, bias=None, accumulate_into=None, split_k=1, remap=None):
     (15808, 96, 480),     # layer-0 input projection shape class
     (1000, 6144, 2048),   # many tiles per CTA -> ring + TMEM double buffering wrap around
     (4096, 29, 2048),     # output projection N=29 (ldc not a multiple of 4 -> scalar stores)
-    (16000, 3072, 1024),  # long-K, many tiles -> 256-row CTA tile variant (MT=2)
+    (16000, 3072, 1024),  # long-K, many tiles -> CTA-pair kernel (cta_group::2, 256x256 tiles)
     (15808, 6144, 1088),  # same, ragged K (17 k-blocks) and ragged M (15808 = 61.75 x 256)
+    (9999, 2100, 1024),   # CTA-pair kernel with ragged M and N (second CTA partly out of range)
     (192, 48, 160),       # tests/shared.py tiny config
 ])
 def test_gemm_matches_fp32_reference(cuda_lib, M, N, K):
@@ -61,6 +62,40 @@ def test_gemm_split_k_accumulate(cuda_lib):
     ref = C0 + A.float() @ B.float().t()
     assert (C - ref).abs().max().item() < 0.5
     assert ((C - ref).abs().max() / ref.abs().max()).item() < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,split", [
+    (1024, 1024, 4096, 1),    # CTA-pair kernel, balanced tiles x k-blocks partition (stream-K)
+    (6144, 2048, 16000, 2),   # north-star dW_ih shape (the caller's split is only a hint)
+    (1000, 700, 5000, 3),     # ragged M, N, K
+])
+def test_gemm_pair_balanced_accumulate(cuda_lib, M, N, K, split):
+    torch.manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    C0 = torch.randn(M, N, device="cuda")
+    C = _gemm(A, B, bias, accumulate_into=C0.clone(), split_k=split)
+    ref = C0 + A.float() @ B.float().t() + bias
+    assert ((C - ref).abs().max() / ref.abs().max()).item() < 1e-4
+
+
+def test_gemm_pair_kernel_is_bit_identical_to_single_cta(cuda_lib):
+    """Same k order, same accumulator precision: the cta_group::2 kernel must reproduce the
+    single-CTA kernel bit for bit on a plain (non-accumulating) GEMM."""
+    from speech_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(7)
+    A = torch.randn(5000, 1536, device="cuda").bfloat16()
+    B = torch.randn(2048, 1536, device="cuda").bfloat16()
+    bias = torch.randn(2048, device="cuda")
+    try:
+        lib.sb_debug_gemm_mt1(1)          # single-CTA kernels only
+        C1 = _gemm(A, B, bias)
+    finally:
+        lib.sb_debug_gemm_mt1(1 | 4)      # default: CTA-pair kernel allowed
+    C2 = _gemm(A, B, bias)
+    assert torch.equal(C1, C2)
 
 
 def test_gemm_row_remap_time_major_to_batch_first(cuda_lib):
