@@ -191,13 +191,15 @@ class GRUStackFunction(torch.autograd.Function):
             b_ih = [wl[d * 4 + 2] for d in range(ndir)]
             b_hh = [wl[d * 4 + 3] for d in range(ndir)]
             Kl = X.shape[1]
-            if Kl == w_ih[0].shape[1]:
-                wih_cat = torch.cat([w.detach() for w in w_ih], 0).to(torch.bfloat16)
-            else:
-                wih_cat = torch.zeros(ndir * 3 * H, Kl, dtype=torch.bfloat16, device=dev)
-                wih_cat[:, :w_ih[0].shape[1]] = torch.cat([w.detach() for w in w_ih], 0)
+            # bf16 operand copies of the master weights: one fused cast+copy per matrix
+            In_l = w_ih[0].shape[1]
+            wih_cat = (torch.empty if Kl == In_l else torch.zeros)(
+                ndir * 3 * H, Kl, dtype=torch.bfloat16, device=dev)
+            whh = torch.empty(ndir, 3 * H, H, dtype=torch.bfloat16, device=dev)
+            for d in range(ndir):
+                wih_cat[d * 3 * H:(d + 1) * 3 * H, :In_l].copy_(w_ih[d].detach())
+                whh[d].copy_(w_hh[d].detach())
             bih_cat = torch.cat([b.detach() for b in b_ih]).float().contiguous()
-            whh = torch.stack([w.detach() for w in w_hh]).to(torch.bfloat16).contiguous()
             bhh = torch.stack([b.detach() for b in b_hh]).float().contiguous()
             gi = gemm_bf16_tn(X, wih_cat, bias=bih_cat)
             y = torch.empty(M, D, dtype=torch.float32, device=dev)
@@ -219,7 +221,7 @@ class GRUStackFunction(torch.autograd.Function):
                 mask = (torch.rand(M, D, device=dev) >= dropout).float() * (1.0 / (1.0 - dropout))
                 xn = xn * mask
             if need_grad:
-                saved.append((X, y, gates, xnT, mask))
+                saved.append((X, y, gates, xnT, mask, wih_cat, whh))
             X = xn
         ctx.saved = saved
         ctx.announce = _announce
@@ -280,14 +282,15 @@ class GRUStackFunction(torch.autograd.Function):
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
         grads = [None] * len(weights)
         for l in reversed(range(L)):
-            X, y, gates, xnT, mask = ctx.saved[l]
+            X, y, gates, xnT, mask, wih_cat, whh = ctx.saved[l]
             if mask is not None:
                 dY = dY * mask
             wl = weights[l * 4 * ndir:(l + 1) * 4 * ndir]
             Kl = X.shape[1]
             In_l = wl[0].shape[1]
-            whhT = torch.stack([wl[d * 4 + 1].detach().t() for d in range(ndir)]) \
-                .to(torch.bfloat16).contiguous()                        # [ndir][H][3H]
+            whhT = torch.empty(ndir, H, K3, dtype=torch.bfloat16, device=dev)   # [ndir][H][3H]
+            for d in range(ndir):
+                _transpose_bf16(whh[d], out=whhT[d])
             dgi = torch.empty(M, ndir * K3, dtype=torch.bfloat16, device=dev)
             dgiT = torch.empty(ndir * K3, M, dtype=torch.bfloat16, device=dev)
             dghnT = torch.empty(ndir, H, M, dtype=torch.bfloat16, device=dev)
@@ -358,8 +361,7 @@ class GRUStackFunction(torch.autograd.Function):
                         _grad_ready_hook(list(wl))
             # ---- gradient w.r.t. the layer input ----
             if l > 0 or ctx.needs_input_grad[0]:
-                wihT = torch.zeros(Kl, ndir * K3, dtype=torch.bfloat16, device=dev)
-                wihT[:In_l] = torch.cat([wl[d * 4].detach() for d in range(ndir)], 0).t()
+                wihT = _transpose_bf16(wih_cat)                           # [Kl][ndir*3H]
                 dY = gemm_bf16_tn(dgi, wihT)                              # [M][Kl] f32
         dx = None
         if ctx.needs_input_grad[0]:
@@ -413,13 +415,18 @@ def gru_stack(x, rnn, dropout=0.0):
         xc, ndir, rnn.hidden_size, float(dropout), None, None, *weights))
 
 
-def _transpose_bf16(src, rows_pad=8):
-    """[R][C] bf16 -> [C][Rp] bf16 (Rp = R rounded up so that rows stay 16-byte aligned)."""
+def _transpose_bf16(src, rows_pad=8, out=None):
+    """[R][C] bf16 -> [C][Rp] bf16 (Rp = R rounded up so that rows stay 16-byte aligned);
+    `out` (optional): a [C][>=R] bf16 destination with contiguous rows."""
     lib = _lib.load()
     R, C = src.shape
     Rp = _round_up(R, rows_pad)
-    dst = torch.zeros(C, Rp, dtype=torch.bfloat16, device=src.device) if Rp != R else \
-        torch.empty(C, Rp, dtype=torch.bfloat16, device=src.device)
+    if out is not None:
+        dst = out
+    elif Rp != R:
+        dst = torch.zeros(C, Rp, dtype=torch.bfloat16, device=src.device)
+    else:
+        dst = torch.empty(C, Rp, dtype=torch.bfloat16, device=src.device)
     sp = _lib.stream_ptr()
     _launch("transpose_bf16", 0.0,
             lambda: lib.sb_transpose_bf16(src.data_ptr(), dst.data_ptr(), R, C, src.stride(0),
