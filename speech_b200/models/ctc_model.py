@@ -14,8 +14,15 @@ class CTC(model.Model):
         self.blank = output_dim                      # blank is the LAST class (ctc_model.py:18)
         self.fc = model.LinearND(self.encoder_dim, output_dim + 1)
 
+    def _collated(self, batch):
+        """reference-style (inputs, labels) pair, or a loader.StagedBatch prepared ahead of time"""
+        from ..loader import StagedBatch
+        if isinstance(batch, StagedBatch):
+            return batch.tensors()
+        return self.collate(*batch)
+
     def forward(self, batch):
-        x, y, x_lens, y_lens = self.collate(*batch)
+        x, y, x_lens, y_lens = self._collated(batch)
         with self._grad_ctx():
             return self.forward_impl(x)
 
@@ -37,7 +44,7 @@ class CTC(model.Model):
         return ops.gru_stack_logits(x, self.rnn, self.fc.fc, dropout=p)
 
     def loss(self, batch):
-        x, y, x_lens, y_lens = self.collate(*batch)
+        x, y, x_lens, y_lens = self._collated(batch)
         with self._grad_ctx():
             out = self.forward_impl(x)
             return self.ctc_loss(out, y, x_lens, y_lens)
@@ -57,7 +64,7 @@ class CTC(model.Model):
         return [x, y, x_lens, y_lens]
 
     def infer(self, batch, beam_size=1):
-        x, y, x_lens, y_lens = self.collate(*batch)
+        x, y, x_lens, y_lens = self._collated(batch)
         with torch.no_grad():
             probs = self.forward_impl(x, softmax=True)
         return decode_batch(probs, beam_size=beam_size, blank=self.blank)
