@@ -34,7 +34,6 @@ struct GemmParams {
   int remap_B, remap_T, valid_B;
   int m_tiles, n_tiles;
   int tma_store;        // epilogue through swizzled smem + cp.async.bulk.tensor stores
-  int stream_k;         // pair kernel: balanced tiles x k-blocks partition (accumulate mode)
 };
 
 // MT = number of 128-row MMA sub-tiles per CTA tile.  MT = 2 (256 x BN CTA tile) re-uses every B
@@ -376,40 +375,20 @@ SB_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Work distribution of the pair kernel.  Classic: work item = (output tile, K split), round-robin.
-// Balanced ("stream-K", accumulate mode only): the tiles x k-blocks iteration space is cut into
-// one contiguous range per CTA pair, so every pair contracts the same number of k-blocks whatever
-// the tile count (the weight-gradient GEMMs have 2.6 waves of tiles: 14 % of the SMs idle in the
-// last wave otherwise); partial tiles are combined by the reduce-add epilogue.
+// Work distribution of the pair kernel: work item = (output tile, K split), round-robin over the
+// CTA pairs, so that the pairs of one wave walk the same k range together (L2 reuse of the panels).
 struct PairSched {
-  int stream, w, step, total_work, tiles_mn, kbt, kb_per_split, u, u1;
+  int w, step, total_work, tiles_mn, kbt, kb_per_split;
   __device__ PairSched(const GemmParams& p, int pair_id, int n_pairs) {
-    stream = p.stream_k;
     tiles_mn = p.m_tiles * p.n_tiles;
     kbt = p.k_blocks_total;
     total_work = tiles_mn * p.split_k;
     kb_per_split = (kbt + p.split_k - 1) / p.split_k;
     w = pair_id;
     step = n_pairs;
-    const long long units = (long long)tiles_mn * kbt;
-    const long long per = (units + n_pairs - 1) / n_pairs;
-    long long a = per * pair_id, b = a + per;
-    if (a > units) a = units;
-    if (b > units) b = units;
-    u = (int)a;
-    u1 = (int)b;
   }
   // next piece of work: output tile index and k-block range [kb0, kb1)
   __device__ bool next(int& tile, int& kb0, int& kb1) {
-    if (stream) {
-      if (u >= u1) return false;
-      tile = u / kbt;
-      kb0 = u - tile * kbt;
-      kb1 = kb0 + (u1 - u);
-      if (kb1 > kbt) kb1 = kbt;
-      u += kb1 - kb0;
-      return true;
-    }
     if (w >= total_work) return false;
     const int split = w / tiles_mn;
     tile = w - split * tiles_mn;
@@ -706,6 +685,24 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
+// K split of an ACCUMULATING GEMM (the caller's value is only a hint): the split whose work-item
+// count fills whole waves of `units` CTAs (or CTA pairs) - e.g. the dW_ih GEMM has 192 pair tiles
+// for 74 pairs: 2.6 waves unsplit, 12.97 waves with 5 splits - while every wave still walks K in
+// lockstep, which keeps the operand panels in L2.  (A contiguous tiles x k-blocks "stream-K"
+// partition was measured HBM-bound instead: 2.5 GB of DRAM reads for 0.26 GB of operands.)
+static int pick_wave_filling_split(long long tiles, int units, int k_blocks) {
+  int best_split = 1;
+  double best = -1.0;
+  for (int sp = 1; sp <= 16; ++sp) {
+    if (sp > 1 && k_blocks / sp < 8) break;
+    const double waves = (double)(tiles * sp) / units;
+    const double eff = waves / (double)((long long)(waves + 0.999999));
+    const double score = eff - 0.004 * sp;      // prefer fewer reduce-add passes
+    if (score > best) { best = score; best_split = sp; }
+  }
+  return best_split;
+}
+
 static int g_gemm_force_mt1 = 1;   // the 256-row CTA tile measured slower (epilogue not overlapped)
 static int g_gemm_pair = 1;        // CTA-pair (cta_group::2) kernel for the large tiles
 
@@ -763,7 +760,6 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   if (split_k > p.k_blocks_total) split_k = p.k_blocks_total;
   p.split_k = split_k; p.flags = flags;
   p.remap_B = remap_B; p.remap_T = remap_T; p.valid_B = valid_B;
-  p.stream_k = 0;
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = 0;
 
@@ -786,11 +782,15 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   if (N > 128 && g_gemm_pair && g_gemm_tma_store && !(flags & SB_GEMM_ROW_REMAP) &&
       (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
     const long long pair_tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
-    // accumulate mode: balanced tiles x k-blocks partition whatever split the caller suggested
-    const bool balanced = (flags & SB_GEMM_ACCUMULATE) != 0 &&
-                          pair_tiles * p.k_blocks_total >= 8LL * (sms / 2);
-    if (balanced || (bn == 256 && K >= 1024 && pair_tiles * split_k >= sms / 2)) {
-      p.stream_k = balanced ? 1 : 0;
+    const int pairs = sms / 2;
+    int pair_split = split_k;
+    if (flags & SB_GEMM_ACCUMULATE)
+      pair_split = pick_wave_filling_split(pair_tiles, pairs, p.k_blocks_total);
+    const bool use_pair = (flags & SB_GEMM_ACCUMULATE)
+                              ? (pair_tiles * pair_split * 2 >= pairs)
+                              : (bn == 256 && K >= 1024 && pair_tiles * split_k >= pairs);
+    if (use_pair) {
+      p.split_k = pair_split;
       CUtensorMap pa, pb;
       int prc = make_tmap_bf16_2d(&pa, A, M, K, lda, BM);
       if (prc != SB_OK) return prc;
@@ -800,6 +800,9 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
     }
   }
   p.m_tiles = (M + mt * BM - 1) / (mt * BM);
+  if (flags & SB_GEMM_ACCUMULATE)
+    p.split_k = pick_wave_filling_split((long long)p.m_tiles * ((N + bn - 1) / bn), sms,
+                                        p.k_blocks_total);
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, mt * BM);
   if (rc != SB_OK) return rc;

@@ -65,11 +65,11 @@ def test_gemm_split_k_accumulate(cuda_lib):
 
 
 @pytest.mark.parametrize("M,N,K,split", [
-    (1024, 1024, 4096, 1),    # CTA-pair kernel, balanced tiles x k-blocks partition (stream-K)
+    (1024, 1024, 4096, 1),    # CTA-pair kernel, wave-filling K split chosen by the library
     (6144, 2048, 16000, 2),   # north-star dW_ih shape (the caller's split is only a hint)
     (1000, 700, 5000, 3),     # ragged M, N, K
 ])
-def test_gemm_pair_balanced_accumulate(cuda_lib, M, N, K, split):
+def test_gemm_pair_accumulate_with_library_chosen_split(cuda_lib, M, N, K, split):
     torch.manual_seed(M + K)
     A = torch.randn(M, K, device="cuda").bfloat16()
     B = torch.randn(N, K, device="cuda").bfloat16()
