@@ -685,20 +685,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
-// K split of an ACCUMULATING GEMM (the caller's value is only a hint): the split whose work-item
-// count fills whole waves of `units` CTAs (or CTA pairs) - e.g. the dW_ih GEMM has 192 pair tiles
-// for 74 pairs: 2.6 waves unsplit, 12.97 waves with 5 splits - while every wave still walks K in
-// lockstep, which keeps the operand panels in L2.  (A contiguous tiles x k-blocks "stream-K"
-// partition was measured HBM-bound instead: 2.5 GB of DRAM reads for 0.26 GB of operands.)
+// K split of an ACCUMULATING GEMM (the caller's value is only a hint).  Work items = tiles x
+// splits are dealt round-robin to `units` CTAs (or CTA pairs), so the launch takes
+// ceil(tiles*split/units) rounds of (k-blocks per item + E) each, E ~ the epilogue / reduce-add
+// pass of an item expressed in k-block times.  The minimum of that product fills whole waves -
+// the dW_ih GEMM has 192 pair tiles for 74 pairs: 2.6 waves unsplit (3 rounds of 250 k-blocks),
+// 12.97 waves with 5 splits (13 rounds of 50) - while every wave still walks K in lockstep, which
+// keeps the operand panels in L2.  (A contiguous tiles x k-blocks "stream-K" partition was
+// measured HBM-bound instead: 2.5 GB of DRAM reads for 0.26 GB of operands, no reuse.)
 static int pick_wave_filling_split(long long tiles, int units, int k_blocks) {
+  const long long kEpilogue = 4;
   int best_split = 1;
-  double best = -1.0;
-  for (int sp = 1; sp <= 16; ++sp) {
+  long long best = -1;
+  for (int sp = 1; sp <= 512; ++sp) {
     if (sp > 1 && k_blocks / sp < 8) break;
-    const double waves = (double)(tiles * sp) / units;
-    const double eff = waves / (double)((long long)(waves + 0.999999));
-    const double score = eff - 0.004 * sp;      // prefer fewer reduce-add passes
-    if (score > best) { best = score; best_split = sp; }
+    const long long rounds = (tiles * sp + units - 1) / units;
+    const long long cost = rounds * ((k_blocks + sp - 1) / sp + kEpilogue);
+    if (best < 0 || cost < best) { best = cost; best_split = sp; }   // ties: fewer splits
   }
   return best_split;
 }

@@ -41,7 +41,8 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__cluster_dim_x", "launch__shared_mem_per_block_dynamic",
         "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__cycles_elapsed.max"]
-for k in ["gru_bwd_ks_kernel", "gru_fwd_kernel", "gemm_bf16_tn_kernel", "ctc_fwd_bwd_kernel"]:
+for k in ["gru_bwd_ks_kernel", "gru_fwd_kernel", "gemm_bf16_tn_pair_kernel", "gemm_bf16_tn_kernel",
+          "ctc_fwd_bwd_kernel"]:
     txt = subprocess.run(["ncu", "-i", "gpurun_out/prof_%s_%s.ncu-rep" % (R, k), "--page", "raw", "--csv"],
                          capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(txt)))
