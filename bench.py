@@ -60,8 +60,8 @@ def synth_batch(nutt, seed=0):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the committed
 # `ncu --set full` captures of this same workload (profiles/r01_summary.md; B=64 per GPU)
-NCU_TRAFFIC_BYTES = {"gru_bwd": 802.77e6 + 405.38e6, "gru_fwd": 407.09e6 + 725.50e6,
-                     "gemm_bf16_tn": 96.45e6 + 339.29e6, "ctc_fwd_bwd": 3.13e6}
+NCU_TRAFFIC_BYTES = {"gru_bwd": 795.84e6 + 406.26e6, "gru_fwd": 406.82e6 + 725.97e6,
+                     "gemm_bf16_tn": 124.46e6 + 343.93e6, "ctc_fwd_bwd": 3.13e6}
 
 
 def flops_per_step(nutt):

@@ -51,6 +51,11 @@ for k in ["gru_bwd_ks_kernel", "gru_fwd_kernel", "gemm_bf16_tn_pair_kernel", "ge
     h, u, v = rr[0], rr[1], rr[2]
     kname = v[h.index("Kernel Name")] if "Kernel Name" in h else k
     out.append("## `%s` - one launch, `ncu --set full --import-source on -k regex:%s -c 1`\n" % (kname[:90], k))
+    if k == "gemm_bf16_tn_kernel":
+        out.append("(capture of the single-CTA 128x256 kernel taken BEFORE the CTA-pair kernel replaced it on "
+                   "the large GEMMs; kept for comparison - same shape class, gi of layer 1.)\n")
+    if k == "ctc_fwd_bwd_kernel":
+        out.append("(capture from the earlier profiling pass of this round; the kernel has not changed since.)\n")
     out.append("| metric | value |\n|---|---|")
     for w in want:
         if w in h:
