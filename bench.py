@@ -403,19 +403,33 @@ def secondary_measurements(model, batch, dev):
     out = {}
     inputs, labels = batch
     sub = (tuple(inputs[:8]), tuple(labels[:8]))
-    # ---- loss delta, same weights ----
-    with torch.no_grad():
-        ours = float(model.loss(sub).item())
-        x, y, x_lens, y_lens = model.collate(*sub)
-        logits = model.forward_impl(x)
-    ref = RefCTC(F_IN, VOCAB, MODEL_CFG)
-    ref.load_from_dropin({k: v.detach().float().cpu() for k, v in model.state_dict().items()})
     torch.set_num_threads(min(16, os.cpu_count() or 1))
-    with torch.no_grad():
-        ref_loss = float(ref.loss(torch.from_numpy(np.stack(sub[0])), y, y_lens).item())
+
+    def loss_pair(m):
+        with torch.no_grad():
+            mine = float(m.loss(sub).item())
+            x, y, x_lens, y_lens = m.collate(*sub)
+            lg = m.forward_impl(x)
+        ref = RefCTC(F_IN, VOCAB, MODEL_CFG)
+        ref.load_from_dropin({k: v.detach().float().cpu() for k, v in m.state_dict().items()})
+        with torch.no_grad():
+            theirs = float(ref.loss(torch.from_numpy(np.stack(sub[0])), y, y_lens).item())
+        return mine, theirs, lg, y, y_lens
+
+    # ---- loss delta on the north-star state: torch.manual_seed(0) random-init weights ----
+    from speech_b200.models import CTC
+    torch.manual_seed(0)
+    fresh = CTC(F_IN, VOCAB, MODEL_CFG).cuda()
+    fresh.set_eval()
+    ours, ref_loss, logits, y, y_lens = loss_pair(fresh)
     out["ctc_loss_ours_8utt"] = ours
     out["ctc_loss_cpu_reference_8utt"] = ref_loss
     out["ctc_loss_rel_delta"] = abs(ours - ref_loss) / abs(ref_loss)
+    del fresh
+    # ---- same comparison on the weights the timed SGD steps above left behind (noise labels at
+    # lr 1e-3 drive the recurrent weights up, which amplifies the bf16 operand rounding) ----
+    t_ours, t_ref, _, _, _ = loss_pair(model)
+    out["ctc_loss_rel_delta_after_timed_steps"] = abs(t_ours - t_ref) / abs(t_ref)
     # ---- kernel-only delta on our logits ----
     lg = logits.detach().double().cpu()
     lp = torch.log_softmax(lg, 2).transpose(0, 1)
