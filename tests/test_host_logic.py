@@ -1,0 +1,136 @@
+"""CPU tests of the host-side mirror of the reference interface (SURVEY.md section 8 rows a2, a5,
+a19, b): batch assembly conventions, the conv output-size rule, and that the product path fails
+loudly - never falls back to a CPU implementation - when there is no CUDA device."""
+import numpy as np
+import pytest
+import torch
+
+TINY = {"dropout": 0.0, "encoder": {"conv": [[32, 5, 32, 2]],
+                                    "rnn": {"dim": 16, "bidirectional": False, "layers": 1}},
+        "decoder": {"embedding_dim": 16, "layers": 2}}
+WSJ = {"dropout": 0.4, "encoder": {"conv": [[32, 5, 8, 2], [32, 5, 8, 2]],
+                                   "rnn": {"dim": 32, "bidirectional": True, "layers": 2}}}
+
+
+def _batch(n=4, seed=0):
+    rng = np.random.RandomState(seed)
+    inputs = [rng.randn(50 + 9 * e, 40) for e in range(n)]          # float64, ragged lengths
+    labels = [rng.randint(0, 10, 4 + e).tolist() for e in range(n)]
+    return inputs, labels
+
+
+def test_zero_pad_concat_pads_with_zeros_and_casts_to_float32():
+    """reference model.py:135-141: (B, max T, F) float32, zero padded; fixtures arrive float64."""
+    from speech_b200.models.model import zero_pad_concat
+    inputs, _ = _batch()
+    cat = zero_pad_concat(inputs)
+    assert cat.dtype == np.float32 and cat.shape == (4, 77, 40)
+    for e, inp in enumerate(inputs):
+        assert np.array_equal(cat[e, :inp.shape[0]], inp.astype(np.float32))
+        assert not cat[e, inp.shape[0]:].any()
+
+
+@pytest.mark.parametrize("cfg,fdim", [(TINY, 40), (WSJ, 80)])
+def test_conv_out_size_equals_torch_valid_convolution(cfg, fdim):
+    """reference model.py:44-52: ceil((n-k+1)/s) per layer == torch's floor((n-k)/s)+1."""
+    from speech_b200.models import CTC
+    m = CTC(fdim, 10, cfg)
+    for n in (57, 100, 101, 333, 1000):
+        x = torch.zeros(1, 1, n, fdim)
+        with torch.no_grad():
+            for c in m.conv.children():
+                if isinstance(c, torch.nn.Conv2d):
+                    x = c(x)
+        assert m.conv_out_size(n, 0) == x.shape[2]
+        assert m.conv_out_size(fdim, 1) == x.shape[3]
+    assert m.rnn.input_size == x.shape[1] * x.shape[3]
+
+
+def test_dropout_shifts_conv_state_dict_indices_like_the_reference():
+    """model.py:25-26: a Dropout module after every ReLU => conv.{0,3,..} instead of conv.{0,2,..}."""
+    from speech_b200.models import CTC
+    keys = set(CTC(80, 10, WSJ).state_dict().keys())
+    assert {"conv.0.weight", "conv.3.weight"} <= keys and "conv.2.weight" not in keys
+    nodrop = dict(WSJ, dropout=0.0)
+    keys = set(CTC(80, 10, nodrop).state_dict().keys())
+    assert {"conv.0.weight", "conv.2.weight"} <= keys
+
+
+def test_ctc_collate_conventions():
+    """reference ctc_model.py:42-53: x_lens = T' of the padded batch for EVERY utterance, labels
+    flat int32 on the host, y_lens int32."""
+    from speech_b200.models import CTC
+    m = CTC(40, 10, TINY)
+    inputs, labels = _batch()
+    x, y, x_lens, y_lens = m.collate(inputs, labels)
+    assert x.shape == (4, 77, 40) and x.dtype == torch.float32
+    assert x_lens.dtype == torch.int32 and x_lens.tolist() == [m.conv_out_size(77, 0)] * 4
+    assert y.dtype == torch.int32 and y.tolist() == [t for l in labels for t in l]
+    assert y_lens.tolist() == [len(l) for l in labels]
+
+
+def test_seq2seq_and_transducer_label_padding_uses_the_end_token():
+    """reference seq2seq.py:239-248 / transducer_model.py:103-116: labels are padded with
+    labels[0][-1] (the end token), int64."""
+    from speech_b200.models import Seq2Seq, Transducer
+    from speech_b200.models.seq2seq import end_pad_concat
+    labels = [[7, 1, 2, 9], [7, 3, 9], [7, 4, 5, 6, 8, 9]]
+    cat = end_pad_concat(labels)
+    assert cat.dtype == np.int64 and cat.shape == (3, 6)
+    assert cat[1].tolist() == [7, 3, 9, 9, 9, 9] and cat[0].tolist() == [7, 1, 2, 9, 9, 9]
+    s = Seq2Seq(40, 10, TINY)
+    inputs = [np.zeros((60, 40)), np.zeros((50, 40)), np.zeros((55, 40))]
+    x, y = s.collate(inputs, labels)
+    assert x.shape == (3, 60, 40) and torch.equal(y, torch.from_numpy(cat))
+    t = Transducer(40, 10, TINY)
+    assert torch.equal(t.label_collate(labels), torch.from_numpy(cat))
+    x, yf, x_lens, y_lens = t.collate(inputs, labels)
+    assert yf.dtype == torch.int32 and y_lens.tolist() == [4, 3, 6]
+    assert x_lens.tolist() == [t.conv_out_size(60, 0)] * 3
+
+
+def test_product_path_raises_without_cuda_instead_of_falling_back():
+    """No CPU implementation is shipped: every entry point that would have to compute must raise
+    SpeechB200Error on CPU tensors (the oracle is test infrastructure only)."""
+    from speech_b200 import _lib
+    from speech_b200.functions.ctc import CTCLoss
+    from speech_b200.models import CTC
+    from speech_b200.models.ctc_decoder import decode
+    m = CTC(40, 10, TINY)          # parameters on the CPU
+    with pytest.raises(_lib.SpeechB200Error):
+        m.loss(_batch())
+    with pytest.raises(_lib.SpeechB200Error):
+        m.infer(_batch())
+    acts = torch.randn(2, 20, 11, requires_grad=True)
+    with pytest.raises(_lib.SpeechB200Error):
+        CTCLoss()(acts, torch.IntTensor([1, 2, 3]), torch.IntTensor([20, 20]),
+                  torch.IntTensor([2, 1]))
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SpeechB200Error):
+            decode(np.full((5, 4), 0.25, dtype=np.float32), beam_size=2, blank=0)
+
+
+def test_batch_prefetcher_requires_a_cuda_model():
+    from speech_b200.loader import BatchPrefetcher
+    from speech_b200.models import CTC
+    with pytest.raises(RuntimeError):
+        BatchPrefetcher(CTC(40, 10, TINY), [])
+
+
+def test_shims_resolve_to_the_library_operators():
+    """INTEGRATION.md option A: `import functions.ctc`, `import transducer...` from shims/."""
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "shims"))
+    try:
+        fc = importlib.import_module("functions.ctc")
+        tf = importlib.import_module("transducer.functions.transducer")
+        td = importlib.import_module("transducer.decoders")
+    finally:
+        sys.path.pop(0)
+    from speech_b200.functions import ctc, transducer
+    assert fc.CTCLoss is ctc.CTCLoss
+    assert tf.TransducerLoss is transducer.TransducerLoss
+    assert callable(td.decode_static)
