@@ -18,7 +18,8 @@ e2e      the same step through the public API with HOST numpy inputs: every step
          the reference's own loop shape, `model.loss((inputs, labels))` collating on the training
          thread.
 Under torchrun (N>1) the global batch is sharded B/N per rank (strong scaling), gradients are
-summed with one NCCL all-reduce per step; time is the max over ranks.
+summed over ranks with NCCL all-reduces (per GRU layer, overlapped with backward); time is the max
+over ranks.
 """
 import argparse
 import json
@@ -224,7 +225,8 @@ def run_ours(args):
     model = CTC(F_IN, VOCAB, MODEL_CFG).cuda()
     model.set_train()
     # clip(200) + SGD(lr 1e-3, momentum 0) of train.py:32-35,95-97, fused over flat buffers;
-    # step() also performs the data-parallel gradient all-reduce (one NCCL call)
+    # step() also completes the data-parallel gradient all-reduce (per-layer buckets started
+    # during backward, the remainder here)
     opt = FlatSGD(model, lr=1e-3, momentum=0.0, max_grad_norm=200.0, world_size=world)
     inputs, labels = synth_batch(GLOBAL_B)
     inputs = inputs[rank * nutt:(rank + 1) * nutt]

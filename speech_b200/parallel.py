@@ -1,13 +1,14 @@
 """Data-parallel gradient synchronisation: one process per GPU, minibatch sharded B/N per rank,
-ONE summed all-reduce of the gradients per step over NCCL (NVLink 5 / NVSwitch).
+the gradients summed over ranks once per step over NCCL (NVLink 5 / NVSwitch).
 
 The reference has no multi-GPU path at all (train.py:92); this adds exactly the
 collective the north star names.  Gradients are SUMMED (not averaged): the reference's loss is a
 sum over the minibatch (ctc_model.py:38-39), so the sum over ranks of per-shard gradients equals
 the single-GPU gradient of the global batch.
 
-All parameter gradients are views into one flat fp32 buffer, so the all-reduce is a single NCCL
-call (339.5 MB at the north-star config) and `zero_grad(set_to_none=False)` is one memset.
+All parameter gradients are views into one flat fp32 buffer (339.5 MB at the north-star config),
+so `zero_grad(set_to_none=False)` is one memset and the all-reduce runs over contiguous slices of
+it: one per GRU layer, started from inside the backward pass (BucketReducer), plus the rest.
 """
 import torch
 
