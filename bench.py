@@ -470,6 +470,34 @@ def secondary_measurements(model, batch, dev):
         torch.cuda.synchronize()
         out["infer_beam%d_utt_per_s" % beam] = len(inputs) / (time.perf_counter() - t0)
     model.set_train()
+    # ---- featuriser: 64 utterances of 10 s int16 PCM at 16 kHz -> the
+    # (64, 1000, 161) normalised log-spectrogram, host PCM in, device features out ----
+    try:
+        from oracle.specgram_ref import log_specgram as ref_specgram
+        from speech_b200.features import log_specgram_batch
+        rng = np.random.RandomState(1)
+        audios = [(rng.randn(160160) * 3000).astype(np.int16) for _ in range(GLOBAL_B)]
+        mean = np.zeros(161, np.float32)
+        std = np.ones(161, np.float32)
+        feats, n_frames = log_specgram_batch(audios, 16000, mean=mean, std=std)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            feats, n_frames = log_specgram_batch(audios, 16000, mean=mean, std=std)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        refs = [ref_specgram(a, 16000) for a in audios[:4]]
+        dt_cpu = (time.perf_counter() - t0) / 4
+        err = max(float(np.abs(feats[e, :n_frames[e]].cpu().numpy() - refs[e]).max())
+                  for e in range(4))
+        out["featuriser"] = {"utt_per_s": GLOBAL_B / dt, "ms_per_batch_of_64x10s": dt * 1e3,
+                             "frames": int(n_frames[0]), "cpu_oracle_utt_per_s_1core": 1.0 / dt_cpu,
+                             "max_abs_err_vs_f64_oracle": err,
+                             "note": "host int16 PCM in (pinned copy + H2D inside), device "
+                                     "features out"}
+    except Exception as e:      # never let a secondary number take the bench line down
+        out["featuriser"] = {"error": repr(e)}
     return out
 
 

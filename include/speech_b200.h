@@ -195,6 +195,23 @@ int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
                     int T, int U1, int V, int blank, float* costs, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Featuriser.  Replaces speech/loader.py:152-166 `log_specgram`
+ * (scipy.signal.spectrogram, periodic Hann window, one-sided density PSD, no detrend / padding,
+ * then log(float32(PSD) + eps)) and the normalisation of loader.py:65-67 `(x - mean) / std`.
+ *   pcm        int16 samples of all utterances, concatenated (device)
+ *   offsets    [B] index of each utterance's first sample in pcm (device, int64)
+ *   n_samples  [B] samples per utterance (device, int32)
+ *   nperseg    window length in samples (<= 1024), step = nperseg - noverlap
+ *   scale      1 / (sample_rate * sum(window^2)), computed by the caller in float64
+ *   mean, stdev [nperseg/2+1] per-bin statistics (device, float32) or NULL for the raw log PSD
+ *   out        [B][max_frames][nperseg/2+1] float32; frames past an utterance's end are set to 0
+ *              (the zero padding of model.py:135-141)
+ * Frames per utterance: (n_samples - noverlap) / step if n_samples >= nperseg, else 0. */
+int sb_log_specgram(const short* pcm, const long long* offsets, const int* n_samples, int B,
+                    int nperseg, int step, double scale, float eps, const float* mean,
+                    const float* stdev, float* out, int max_frames, void* stream);
+
 /* Developer hook (not part of the drop-in surface): device buffer of >= 64*16 uint64 receiving a
  * globaltimer timeline of CTA 0 for the next sb_gru_fwd launches; NULL disables. */
 int sb_debug_gru_timeline(void* dev_buffer);

@@ -140,3 +140,42 @@ def test_rnnt_oracle_matches_brute_force_enumeration():
             fd = (rnnt_ref.brute_force_nll(lp2, labels, V - 1) -
                   rnnt_ref.brute_force_nll(lp3, labels, V - 1)) / (2 * eps)
             assert abs(fd - g[idx]) < 1e-6
+
+
+def _specgram_noise_bound(ref_log):
+    """The reference computes its FFT in complex64 (scipy: result_type(int16, complex64)), so its
+    own output carries rounding noise ~ eps32 * sqrt(N) * (frame maximum / bin amplitude) relative
+    to exact arithmetic.  In the log-power domain that is 3e-7 * exp(-rel/2) for a bin whose log
+    power lies `rel` below the frame maximum (measured on the fixtures: 1.2e-6 at rel > -5,
+    1.5e-4 at -15, 1.4e-3 at -20), plus 1e-5 for the float32 log itself."""
+    rel = ref_log.astype(np.float64) - ref_log.max(axis=1, keepdims=True)
+    return 1e-5 + 3e-7 * np.exp(-rel / 2.0)
+
+
+def test_specgram_oracle_matches_reference_output_on_its_own_fixtures():
+    """oracle/specgram_ref.py (float64 restatement of loader.py:156-166) against the output of
+    the reference's own function on tests/test0.wav / test1.wav (golden/make_specgram_golden.py)."""
+    from oracle.specgram_ref import log_specgram
+    g = np.load(os.path.join(GOLD, "specgram.npz"))
+    for name in ("test0", "test1"):
+        ours = log_specgram(g[name + "_audio"], int(g[name + "_sr"]))
+        ref = g[name + "_logspec"]
+        assert ours.shape == ref.shape and ours.dtype == np.float32
+        assert (np.abs(ours.astype(np.float64) - ref) <= _specgram_noise_bound(ref)).all()
+    # loader_test.py:19-20 pins (time, freq) orientation and float32; wave_test.py:16 the duration
+    assert g["test0_logspec"].shape[1] == 161 and round(g["test0_audio"].shape[0] / 16000, 3) == 1.101
+
+
+def test_specgram_oracle_matches_scipy_on_random_audio():
+    import scipy.signal
+    from oracle.specgram_ref import log_specgram
+    rng = np.random.RandomState(0)
+    for sr, n in ((16000, 16000), (8000, 5000), (16050, 4001)):     # 16050 Hz: odd nperseg (321)
+        audio = (rng.randn(n) * 3000).astype(np.int16)
+        nperseg, noverlap = int(20 * sr / 1e3), int(10 * sr / 1e3)
+        _, _, spec = scipy.signal.spectrogram(audio, fs=sr, window="hann", nperseg=nperseg,
+                                              noverlap=noverlap, detrend=False)
+        ref = np.log(spec.T.astype(np.float32) + 1e-10)
+        ours = log_specgram(audio, sr)
+        assert ours.shape == ref.shape
+        assert (np.abs(ours.astype(np.float64) - ref) <= _specgram_noise_bound(ref)).all()
