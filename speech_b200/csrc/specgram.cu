@@ -51,6 +51,14 @@ log_specgram_kernel(const SpecParams p) {
   const int n_frames = ns >= N ? (ns - noverlap) / p.step : 0;
   const short* x = p.pcm + p.offsets[b];
 
+  if (f0 >= n_frames) {          // CTA entirely in the zero padding of a short utterance
+    for (int i = threadIdx.x; i < SPEC_FPB * p.nbins; i += blockDim.x) {
+      const int fr = f0 + i / p.nbins;
+      if (fr < p.max_frames)
+        p.out[((long long)b * p.max_frames + fr) * p.nbins + (i % p.nbins)] = 0.f;
+    }
+    return;
+  }
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     double s, c;
     sincospi(2.0 * (double)n / (double)N, &s, &c);
