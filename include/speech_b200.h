@@ -196,6 +196,12 @@ int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
                     size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Scoring, HOST function: Levenshtein distance of two int32 token
+ * sequences; replaces `editdistance.eval` in speech/utils/score.py:15-16.  Returns -1 on invalid
+ * arguments. */
+long long sb_edit_distance(const int* a, long long na, const int* b, long long nb);
+
+/* ---------------------------------------------------------------------------------------------
  * Featuriser.  Replaces speech/loader.py:152-166 `log_specgram`
  * (scipy.signal.spectrogram, periodic Hann window, one-sided density PSD, no detrend / padding,
  * then log(float32(PSD) + eps)) and the normalisation of loader.py:65-67 `(x - mean) / std`.

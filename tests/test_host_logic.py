@@ -134,3 +134,80 @@ def test_shims_resolve_to_the_library_operators():
     assert fc.CTCLoss is ctc.CTCLoss
     assert tf.TransducerLoss is transducer.TransducerLoss
     assert callable(td.decode_static)
+
+
+def _levenshtein(a, b):
+    prev = list(range(len(b) + 1))
+    for i, x in enumerate(a, 1):
+        cur = [i]
+        for j, y in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (x != y)))
+        prev = cur
+    return prev[-1]
+
+
+def test_edit_distance_and_cer_match_the_definition():
+    """speech/utils/score.py:7-18 with `editdistance.eval` replaced by the library's host function
+    sb_edit_distance: known answers plus a plain-Python dynamic programme on random sequences."""
+    import speech_b200
+    from speech_b200.utils.score import compute_cer, edit_distance
+    assert edit_distance("kitten", "sitting") == 3
+    assert edit_distance("", "abc") == 3 and edit_distance("abc", "") == 3
+    assert edit_distance([], []) == 0
+    assert edit_distance(("sil", "ae", "t"), ("sil", "t")) == 1          # phoneme tokens
+    rng = np.random.RandomState(0)
+    results = []
+    for _ in range(50):
+        a = rng.randint(0, 6, rng.randint(0, 40)).tolist()
+        b = rng.randint(0, 6, rng.randint(0, 40)).tolist()
+        assert edit_distance(a, b) == _levenshtein(a, b) == edit_distance(b, a)
+        results.append((a, b))
+    results = [r for r in results if len(r[0])]
+    want = sum(_levenshtein(a, b) for a, b in results) / sum(len(a) for a, _ in results)
+    assert compute_cer(results) == want
+    assert speech_b200.compute_cer is compute_cer                         # speech/__init__.py:2
+
+
+def test_save_load_round_trip_like_the_reference_io_test(tmp_path):
+    """tests/io_test.py of the reference: whole-module pickle + preprocessor pickle under the same
+    file names; plus the resume state the reference lacks."""
+    import pickle
+    import speech_b200
+    from speech_b200.models import CTC
+    from speech_b200.utils import io
+
+    class Preproc:                         # stands in for speech.loader.Preprocessor
+        def __init__(self):
+            self.mean, self.std = np.zeros(3), np.ones(3)
+            self.int_to_char = {0: "a"}
+            self.char_to_int = {"a": 0}
+    globals()["Preproc"] = Preproc
+    Preproc.__qualname__ = "Preproc"
+    Preproc.__module__ = __name__
+    torch.manual_seed(0)
+    m = CTC(40, 10, TINY)
+    speech_b200.save(m, Preproc(), str(tmp_path))
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["model", "preproc.pyc"]
+    speech_b200.save(m, Preproc(), str(tmp_path), tag="best")
+    assert (tmp_path / "best_model").exists() and (tmp_path / "best_preproc.pyc").exists()
+    s_model, s_preproc = speech_b200.load(str(tmp_path))
+    for attr in ("mean", "std", "int_to_char", "char_to_int"):
+        assert hasattr(s_preproc, attr)
+    msd = m.state_dict()
+    for k, v in s_model.state_dict().items():
+        assert k in msd and torch.equal(v, msd[k])
+    assert hasattr(s_model, "encoder_dim") and hasattr(s_model, "is_cuda")
+    # resume state: state_dict + optimiser + counters, written atomically
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9)
+    m.fc.fc.weight.grad = torch.ones_like(m.fc.fc.weight)
+    opt.step()
+    name = io.save_state(m, str(tmp_path), optimizer=opt, epoch=3, iteration=1234)
+    assert name.endswith("state") and not (tmp_path / "state.tmp").exists()
+    torch.manual_seed(1)
+    m2 = CTC(40, 10, TINY)
+    opt2 = torch.optim.SGD(m2.parameters(), lr=1e-3, momentum=0.9)
+    counters = io.load_state(m2, str(tmp_path), optimizer=opt2)
+    assert counters == {"epoch": 3, "iteration": 1234}
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert len(opt2.state_dict()["state"]) == len(opt.state_dict()["state"])
