@@ -115,6 +115,8 @@ def zero_pad_concat(inputs):
 
 _pinned = {}
 _pool = None
+_staging_lock = __import__("threading").Lock()   # the training thread and a loader.BatchPrefetcher
+                                                 # worker may both assemble batches
 
 
 def _staging(shape):
@@ -149,6 +151,11 @@ def zero_pad_concat_device(inputs, device, chunk=8, threads=4):
     chunk is copied to the device asynchronously while the next ones are still being filled, so
     the host memcpy and the PCIe transfer overlap.  Returns the (B, max T, F) float32 CUDA tensor
     zero-padded like the reference's zero_pad_concat (model.py:135-141)."""
+    with _staging_lock:
+        return _zero_pad_concat_device_locked(inputs, device, chunk, threads)
+
+
+def _zero_pad_concat_device_locked(inputs, device, chunk, threads):
     global _pool
     from concurrent.futures import ThreadPoolExecutor
     max_t = max(inp.shape[0] for inp in inputs)
