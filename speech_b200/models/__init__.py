@@ -1,7 +1,10 @@
-"""Host-side mirror of `speech.models` (reference speech/models/__init__.py:2-5)."""
-from .model import Model
-from .seq2seq import Seq2Seq
-from .ctc_model import CTC
-from .transducer_model import Transducer
+"""The model classes `train.py` / `eval.py` look up by name (`eval("models." + cfg["model"]["class"])`,
+reference train.py:88-91): same names as `speech.models`."""
+from . import ctc_model, model, seq2seq, transducer_model
 
-__all__ = ["Model", "Seq2Seq", "CTC", "Transducer"]
+Model = model.Model
+CTC = ctc_model.CTC
+Seq2Seq = seq2seq.Seq2Seq
+Transducer = transducer_model.Transducer
+
+__all__ = ["Model", "CTC", "Seq2Seq", "Transducer"]

@@ -54,14 +54,7 @@ class CTC(model.Model):
         return ctc.CTCLoss()(out, y, x_lens, y_lens)
 
     def collate(self, inputs, labels):
-        # every utterance is scored over the full padded T' (reference ctc_model.py:43-45)
-        max_t = self.conv_out_size(max(i.shape[0] for i in inputs), 0)
-        x_lens = torch.IntTensor([max_t] * len(inputs))
-        x = model.zero_pad_concat_device(inputs, next(self.parameters()).device) \
-            if self.is_cuda else torch.from_numpy(model.zero_pad_concat(inputs))
-        y_lens = torch.IntTensor([len(l) for l in labels])
-        y = torch.IntTensor([int(t) for label in labels for t in label])
-        return [x, y, x_lens, y_lens]
+        return self.lattice_batch(inputs, labels)
 
     def infer(self, batch, beam_size=1):
         x, y, x_lens, y_lens = self._collated(batch)

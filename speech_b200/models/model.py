@@ -86,6 +86,24 @@ class Model(nn.Module):
     def encoder_dim(self):
         return self._encoder_dim
 
+    # ---- batch assembly shared by the three model families ------------------------------------
+    def stage_inputs(self, inputs):
+        """list of (T_i, F) arrays -> zero padded (B, max T, F) float32 tensor, already on the
+        model's device when that is a GPU (pinned staging + asynchronous copy)."""
+        if self.is_cuda:
+            return zero_pad_concat_device(inputs, next(self.parameters()).device)
+        return torch.from_numpy(zero_pad_concat(inputs))
+
+    def lattice_batch(self, inputs, labels):
+        """[x, flat int32 labels, x_lens, y_lens] as the CTC and transducer losses take them
+        (ctc_model.py:42-53, transducer_model.py:79-90): every utterance is scored over the
+        padded T', labels and lengths stay on the host."""
+        frames = self.conv_out_size(max(i.shape[0] for i in inputs), 0)
+        x_lens = torch.full((len(inputs),), frames, dtype=torch.int32)
+        y_lens = torch.tensor([len(seq) for seq in labels], dtype=torch.int32)
+        flat = torch.tensor([int(tok) for seq in labels for tok in seq], dtype=torch.int32)
+        return [self.stage_inputs(inputs), flat, x_lens, y_lens]
+
     def _grad_ctx(self):
         # the reference marks eval batches `volatile`; on modern torch that is no_grad
         return torch.no_grad() if self.volatile else torch.enable_grad()
@@ -111,6 +129,17 @@ def zero_pad_concat(inputs):
     for e, inp in enumerate(inputs):
         out[e, :inp.shape[0], :] = inp
     return out
+
+
+def end_pad_labels(labels):
+    """(B, max U) int64 matrix of label sequences, short rows filled with the LAST token of the
+    FIRST sequence - the end token (seq2seq.py:239-248, transducer_model.py:103-116)."""
+    filler = labels[0][-1]
+    width = max(len(seq) for seq in labels)
+    mat = np.full((len(labels), width), fill_value=filler, dtype=np.int64)
+    for row, seq in enumerate(labels):
+        mat[row, :len(seq)] = seq
+    return mat
 
 
 _pinned = {}

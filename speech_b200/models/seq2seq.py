@@ -174,19 +174,10 @@ class Seq2Seq(model.Model):
             return [complete[0][0]]
 
     def collate(self, inputs, labels):
-        x = model.zero_pad_concat_device(inputs, next(self.parameters()).device) \
-            if self.is_cuda else torch.from_numpy(model.zero_pad_concat(inputs))
-        return x, torch.from_numpy(end_pad_concat(labels))
+        return self.stage_inputs(inputs), torch.from_numpy(end_pad_concat(labels))
 
 
-def end_pad_concat(labels):
-    """(B, max U) int64, padded with the first example's last token (the end token) (:239-248)."""
-    end_tok = labels[0][-1]
-    max_len = max(len(l) for l in labels)
-    cat = np.full((len(labels), max_len), fill_value=end_tok, dtype=np.int64)
-    for e, l in enumerate(labels):
-        cat[e, :len(l)] = l
-    return cat
+end_pad_concat = model.end_pad_labels      # the reference's module-level name (seq2seq.py:239)
 
 
 class NNAttention(nn.Module):

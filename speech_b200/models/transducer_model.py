@@ -5,7 +5,6 @@ sb_rnnt_fwd_bwd.  The joint (fc1 shared by both streams, transducer_model.py:71-
 log-softmax are torch ops in round 1; fusing joint -> log-softmax -> lattice so that the
 (B,T',U+1,H) intermediate is never materialised is the next kernel on this row.
 """
-import numpy as np
 import torch
 import torch.nn as nn
 
@@ -60,13 +59,7 @@ class Transducer(model.Model):
         return torch.log_softmax(out, dim=3)
 
     def collate(self, inputs, labels):
-        max_t = self.conv_out_size(max(i.shape[0] for i in inputs), 0)
-        x_lens = torch.IntTensor([max_t] * len(inputs))
-        x = model.zero_pad_concat_device(inputs, next(self.parameters()).device) \
-            if self.is_cuda else torch.from_numpy(model.zero_pad_concat(inputs))
-        y_lens = torch.IntTensor([len(l) for l in labels])
-        y = torch.IntTensor([int(t) for label in labels for t in label])
-        return [x, y, x_lens, y_lens]
+        return self.lattice_batch(inputs, labels)
 
     def infer(self, batch, beam_size=4):
         """Beam search on the TEACHER-FORCED lattice, as the reference does (:92-101), including
@@ -81,9 +74,4 @@ class Transducer(model.Model):
         return preds
 
     def label_collate(self, labels):
-        end_tok = labels[0][-1]
-        max_len = max(len(l) for l in labels)
-        cat = np.full((len(labels), max_len), fill_value=end_tok, dtype=np.int64)
-        for e, l in enumerate(labels):
-            cat[e, :len(l)] = l
-        return torch.from_numpy(cat)
+        return torch.from_numpy(model.end_pad_labels(labels))

@@ -211,3 +211,20 @@ def test_save_load_round_trip_like_the_reference_io_test(tmp_path):
     for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
         assert torch.equal(a, b), k
     assert len(opt2.state_dict()["state"]) == len(opt.state_dict()["state"])
+
+
+def test_stage_inputs_routes_to_the_device_assembler_when_the_model_is_on_a_gpu(monkeypatch):
+    """The CUDA branch of Model.stage_inputs cannot run here; check its wiring with a stand-in."""
+    from speech_b200.models import CTC, model as model_mod
+    m = CTC(40, 10, TINY)
+    calls = []
+
+    def fake(inputs, device):
+        calls.append((len(inputs), device))
+        return torch.from_numpy(model_mod.zero_pad_concat(inputs))
+    monkeypatch.setattr(model_mod, "zero_pad_concat_device", fake)
+    monkeypatch.setattr(type(m), "is_cuda", property(lambda self: True))
+    inputs, labels = _batch()
+    x, y, x_lens, y_lens = m.collate(inputs, labels)
+    assert calls == [(4, next(m.parameters()).device)]
+    assert x.shape == (4, 77, 40) and y.dtype == torch.int32
