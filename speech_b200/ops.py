@@ -539,14 +539,23 @@ class ConvStackFunction(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
+def _col2im_taps_ok(c):
+    """largest instantiation of col2im_relu_kernel<MAXI, MAXJ> (csrc/conv.cu): taps per stride phase"""
+    s = c.stride[0]
+    return -(-c.kernel_size[0] // s) <= 5 and -(-c.kernel_size[1] // s) <= 8
+
+
 def conv_stack(x, conv, training):
     """Conv2d+ReLU(+Dropout) front-end of the encoder (reference model.py:19-29,60-71).
 
     x (B, T, F) -> (B, T', C*F') with the reference's channel-major feature flattening
     (transpose(1,2) of (B,C,T',F') then view, model.py:66-71).  Runs on our im2col + tcgen05
     kernels, including the Dropout after each ReLU when training.  Shapes the kernels do not
-    cover (grouped / dilated / padded convolutions, out_channels not a multiple of 8: none of
-    which the reference can express, model.py:21-23) go through the nn modules.
+    cover go through the nn modules: grouped / dilated / padded convolutions and out_channels not
+    a multiple of 8 (none of which the reference can express, model.py:21-23), and - only when a
+    gradient is needed - an upper layer whose kernel spans more than 5 x 8 taps per stride phase
+    (the unrolled gather of `col2im_relu_kernel`; the TIMIT recipes' second layer [*, 5, 32, 1]
+    is the one shipped case: its forward / inference still runs on our kernels).
     """
     mods = list(conv.children())
     convs = [m for m in mods if isinstance(m, torch.nn.Conv2d)]
@@ -556,6 +565,9 @@ def conv_stack(x, conv, training):
     simple = all(c.stride[0] == c.stride[1] and c.padding == (0, 0) and c.dilation == (1, 1)
                  and c.groups == 1 and c.bias is not None and c.out_channels % 8 == 0
                  for c in convs)
+    needs_grad = torch.is_grad_enabled() and any(q.requires_grad for q in conv.parameters())
+    if needs_grad and not all(_col2im_taps_ok(c) for c in convs[1:]):
+        simple = False
     if convs and simple and not drop:
         specs = tuple((c.kernel_size[0], c.kernel_size[1], c.stride[0]) for c in convs)
         params = []

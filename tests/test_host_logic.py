@@ -228,3 +228,29 @@ def test_stage_inputs_routes_to_the_device_assembler_when_the_model_is_on_a_gpu(
     x, y, x_lens, y_lens = m.collate(inputs, labels)
     assert calls == [(4, next(m.parameters()).device)]
     assert x.shape == (4, 77, 40) and y.dtype == torch.int32
+
+
+def test_conv_stack_uses_the_nn_modules_when_backward_is_not_covered():
+    """The TIMIT recipes' second conv layer [*, 5, 32, 1] needs a 5 x 32 tap gather in backward,
+    beyond the unrolled col2im kernel: with gradients enabled conv_stack must take the nn-module
+    route (runs anywhere, hence testable here); the shipped WSJ / north-star stack must not."""
+    from speech_b200 import _lib, ops
+    from speech_b200.models import CTC
+    timit = {"dropout": 0.0, "encoder": {"conv": [[8, 5, 32, 2], [8, 5, 32, 1]],
+                                         "rnn": {"dim": 16, "bidirectional": True, "layers": 1}}}
+    m = CTC(161, 10, timit)
+    x = torch.randn(2, 40, 161)
+    y = ops.conv_stack(x, m.conv, True)                 # no CUDA needed: nn route
+    ref = m.conv(x.unsqueeze(1))
+    b, c, t, f = ref.shape
+    assert torch.equal(y, ref.transpose(1, 2).reshape(b, t, c * f))
+    y.sum().backward()
+    assert m.conv[0].weight.grad is not None and m.conv[2].weight.grad is not None
+    # the kernels' own route is chosen for the supported stack (and therefore demands CUDA) ...
+    wsj = CTC(80, 10, WSJ)
+    with pytest.raises(_lib.SpeechB200Error):
+        ops.conv_stack(torch.randn(2, 40, 80), wsj.conv, True)
+    # ... and for the TIMIT stack when no gradient is needed (inference)
+    with torch.no_grad(), pytest.raises(_lib.SpeechB200Error):
+        ops.conv_stack(x, m.conv, False)
+    assert ops._col2im_taps_ok(wsj.conv[0]) and not ops._col2im_taps_ok(m.conv[2])
