@@ -39,3 +39,29 @@ def test_encode_matches_reference_on_baseline_configs(cuda_lib, tag):
     err = np.abs(y.float().cpu().numpy() - ref)
     assert err.max() < 1e-2, err.max()
     assert err.mean() < 2e-3, err.mean()
+
+
+@pytest.mark.parametrize("tag", ["tiny", "timit"])
+def test_transducer_lattice_matches_reference_output(cuda_lib, tag):
+    """`Transducer.forward_impl` = decode(encode(x), y) -> (B, T', U+1, V+1) log-probabilities
+    (transducer_model.py:38-77) against the reference's own output (make_golden_transducer.py),
+    same seed => same weights.  The encoder and the prediction network run on the GRU kernels
+    (bf16 operands), the joint in fp32: emulating the operand rounding on the CPU moves the
+    lattice by <= 9e-4 (mean 1.7e-4); bars 1e-2 / 1.5e-3."""
+    from make_golden_transducer import CONFIGS as TCONF, batch_for, weight_checksum
+    from speech_b200.models import Transducer
+    g = np.load(os.path.join(GOLD, "transducer.npz"))
+    fdim, vocab, cfg, seed, _, _ = TCONF[tag]
+    torch.manual_seed(seed)
+    m = Transducer(fdim, vocab, cfg)
+    assert abs(weight_checksum(m) - float(g[tag + "_wsum"])) <= 1e-9 * float(g[tag + "_wsum"])
+    m.cuda()
+    m.set_eval()
+    out = m(batch_for(tag))
+    ref = g[tag + "_out"]
+    assert tuple(out.shape) == ref.shape
+    err = np.abs(out.float().cpu().numpy() - ref)
+    assert err.max() < 1e-2, err.max()
+    assert err.mean() < 1.5e-3, err.mean()
+    # rows are normalised log-probabilities
+    assert np.allclose(np.exp(out.double().cpu().numpy()).sum(-1), 1.0, atol=1e-5)
