@@ -65,3 +65,29 @@ def test_transducer_lattice_matches_reference_output(cuda_lib, tag):
     assert err.mean() < 1.5e-3, err.mean()
     # rows are normalised log-probabilities
     assert np.allclose(np.exp(out.double().cpu().numpy()).sum(-1), 1.0, atol=1e-5)
+
+
+def test_seq2seq_wsj_shape_matches_reference_output(cuda_lib):
+    """WSJ-shaped attention model (BASELINE.json configs[3]: north-star conv stack, 3-layer
+    biGRU-512, NNAttention with log_t): encoder states, teacher-forced logits, alignments and the
+    loss of the reference's own run (make_golden_seq2seq_wsj.py), same seed => same weights.
+    Emulating the kernels' bf16 operand rounding on the CPU moves them by 1.3e-3 / 3.2e-4 / 3e-5 /
+    5e-6 (relative); bars 1e-2 / 5e-3 / 1e-3 / 1e-4."""
+    from make_golden_seq2seq_wsj import CFG, FDIM, SEED, VOCAB, batch, weight_checksum
+    from speech_b200.models import Seq2Seq
+    g = np.load(os.path.join(GOLD, "seq2seq_wsj.npz"))
+    torch.manual_seed(SEED)
+    m = Seq2Seq(FDIM, VOCAB, CFG)
+    assert abs(weight_checksum(m) - float(g["wsum"])) <= 1e-9 * float(g["wsum"])
+    m.cuda()
+    m.set_eval()
+    b = batch()
+    with torch.no_grad():
+        x, y = m.collate(*b)
+        x_enc = m.encode(x.cuda())
+        out, aligns = m.decode(x_enc, y.cuda())
+        loss = m.loss(b)
+    assert np.abs(x_enc.cpu().numpy() - g["x_enc"]).max() < 1e-2
+    assert np.abs(out.cpu().numpy() - g["out"]).max() < 5e-3
+    assert np.abs(aligns.cpu().numpy() - g["aligns"]).max() < 1e-3
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < 1e-4
