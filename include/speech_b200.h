@@ -62,9 +62,16 @@ int sb_ctc_fwd_bwd(const float* acts, float* grads, const int* labels, const int
  *   flags        SB_GEMM_ACCUMULATE: C += (atomic adds; required when split_k > 1)
  *                SB_GEMM_ROW_REMAP : row m = t*remap_B + b is stored at row b*remap_T + t
  *                                    (time-major -> batch-first), rows with b >= valid_B dropped
+ *                SB_GEMM_A_MN      : A is given as [K][M] (lda = elements per K row; M contiguous)
+ *                SB_GEMM_B_MN      : B is given as [K][N] (ldb = elements per K row; N contiguous)
+ *                                    -- the contraction runs over the ROWS of the matrix, which is
+ *                                    how activations [tokens][features] enter a weight gradient
+ *                                    (dW = dY^T X): no transposed copies are needed
  * ------------------------------------------------------------------------------------- */
 #define SB_GEMM_ACCUMULATE 1
 #define SB_GEMM_ROW_REMAP 2
+#define SB_GEMM_A_MN 4
+#define SB_GEMM_B_MN 8
 int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, float* C,
                     long long ldc, const float* bias, int M, int N, int K, int flags, int split_k,
                     int remap_B, int remap_T, int valid_B, void* stream);
@@ -225,6 +232,7 @@ int sb_debug_gru_timeline(void* dev_buffer);
  * single-CTA tile variant, bit 1 = register-store epilogue instead of TMA stores, bit 2 = allow
  * the CTA-pair (tcgen05 cta_group::2) kernel. */
 int sb_debug_gemm_mt1(int force);
+int sb_debug_umma_mn(int lbo_bytes, int sbo_bytes, int kadv_bytes);
 /* Developer hook: timing ablations of the forward GRU kernel (results become wrong; 0 = off). */
 int sb_debug_gru_flags(int flags);
 /* Developer hook: enable (1, default) / disable (0) the K-split backward GRU kernel. */

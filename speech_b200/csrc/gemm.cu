@@ -34,7 +34,28 @@ struct GemmParams {
   int remap_B, remap_T, valid_B;
   int m_tiles, n_tiles;
   int tma_store;        // epilogue through swizzled smem + cp.async.bulk.tensor stores
+  int a_mn, b_mn;       // operand given MN-major ([K][M] / [K][N], contraction dim slowest)
 };
+
+// MN-major operand tiles: the contraction runs over the ROWS of the global matrix ([K][MN], MN
+// contiguous), which is how activations [tokens][features] look to a weight-gradient GEMM.  A TMA
+// box {64 MN (inner, 128 B), 64 K rows} with SWIZZLE_128B lands as one 8 KB block that is exactly
+// the canonical UMMA MN-major SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte
+// units: 8 K-rows of 128 B per swizzle atom (SBO = 1024 B between atoms), the next 64 MN at
+// LBO = 8192 B (the next box).  One MMA (K = 16) spans two atoms; the next MMA starts 2048 B on.
+static constexpr int MN_BOX_BYTES = 64 * 64 * 2;
+static int g_mn_lbo = MN_BOX_BYTES, g_mn_sbo = 1024, g_mn_kadv = 2048;   // developer knobs
+
+struct MnDesc { uint32_t lbo, sbo, kadv; };
+SB_DEVINL uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 
 // MT = number of 128-row MMA sub-tiles per CTA tile.  MT = 2 (256 x BN CTA tile) re-uses every B
 // tile for two MMAs: operand traffic per FLOP drops 1.5x at BN = 256 (the 128x256 tile measured
@@ -57,7 +78,8 @@ template <int BN, int MT>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_c, const GemmParams p,
+                    const MnDesc mn) {
   using Cfg = GemmCfg<BN, MT>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAcc = Cfg::kAccStages;
@@ -118,15 +140,32 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           uint8_t* sb_ = sa + MT * BM * BK * 2;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * (MT * BM));
-          tma_load_2d(sb_, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (p.a_mn) {
+#pragma unroll
+            for (int b = 0; b < MT * BM / 64; ++b)
+              tma_load_2d(sa + b * MN_BOX_BYTES, &tmap_a, &full_bar[stage],
+                          m_blk * (MT * BM) + b * 64, kb * BK);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * (MT * BM));
+          }
+          if (p.b_mn) {
+#pragma unroll
+            for (int b = 0; b < (BN + 63) / 64; ++b)
+              tma_load_2d(sb_ + b * MN_BOX_BYTES, &tmap_b, &full_bar[stage], n_blk * BN + b * 64,
+                          kb * BK);
+          } else {
+            tma_load_2d(sb_, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    const uint32_t idesc = umma_idesc_bf16_f32(BM, BN) | (p.a_mn ? (1u << 15) : 0u) |
+                           (p.b_mn ? (1u << 16) : 0u);
+    const uint64_t a_step = p.a_mn ? (uint64_t)(mn.kadv >> 4) : 2u;
+    const uint64_t b_step = p.b_mn ? (uint64_t)(mn.kadv >> 4) : 2u;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -146,14 +185,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint32_t sb_ = sa + MT * BM * BK * 2;
-          const uint64_t db = umma_desc_sw128_kmajor(sb_);
+          const uint64_t db = p.b_mn ? umma_desc_sw128_mnmajor(sb_, mn.lbo, mn.sbo)
+                                     : umma_desc_sw128_kmajor(sb_);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t da = umma_desc_sw128_kmajor(sa + mt * BM * BK * 2);
+            const uint64_t da = p.a_mn
+                                    ? umma_desc_sw128_mnmajor(sa + mt * BM * BK * 2, mn.lbo, mn.sbo)
+                                    : umma_desc_sw128_kmajor(sa + mt * BM * BK * 2);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the >>4 field
-              umma_bf16_ss(tmem_d + mt * BN, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+              // K-major: advance 16 bf16 = 32 bytes along K inside the swizzle atom (+2 in the
+              // >>4 field); MN-major: 16 K-rows of 128 B = 2048 bytes
+              umma_bf16_ss(tmem_d + mt * BN, da + a_step * k, db + b_step * k, idesc,
                            (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
@@ -412,7 +455,8 @@ struct GemmPairCfg {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_c, const GemmParams p,
+                         const MnDesc mn) {
   using Cfg = GemmPairCfg;
   constexpr int kStages = Cfg::kStages;
   constexpr int BN = Cfg::BN;
@@ -477,8 +521,22 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint8_t* sb_ = sa + BM * BK * 2;
           const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-          tma_load_2d_pair(sa, &tmap_a, lbar, kb * BK, m_blk * (2 * BM) + (int)rank * BM);
-          tma_load_2d_pair(sb_, &tmap_b, lbar, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          if (p.a_mn) {
+#pragma unroll
+            for (int b = 0; b < BM / 64; ++b)
+              tma_load_2d_pair(sa + b * MN_BOX_BYTES, &tmap_a, lbar,
+                               m_blk * (2 * BM) + (int)rank * BM + b * 64, kb * BK);
+          } else {
+            tma_load_2d_pair(sa, &tmap_a, lbar, kb * BK, m_blk * (2 * BM) + (int)rank * BM);
+          }
+          if (p.b_mn) {
+#pragma unroll
+            for (int b = 0; b < BN / 2 / 64; ++b)
+              tma_load_2d_pair(sb_ + b * MN_BOX_BYTES, &tmap_b, lbar,
+                               n_blk * BN + (int)rank * (BN / 2) + b * 64, kb * BK);
+          } else {
+            tma_load_2d_pair(sb_, &tmap_b, lbar, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -486,7 +544,10 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN);
+      const uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN) | (p.a_mn ? (1u << 15) : 0u) |
+                             (p.b_mn ? (1u << 16) : 0u);
+      const uint64_t a_step = p.a_mn ? (uint64_t)(mn.kadv >> 4) : 2u;
+      const uint64_t b_step = p.b_mn ? (uint64_t)(mn.kadv >> 4) : 2u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -501,11 +562,13 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after_sync();
             const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
-            const uint64_t da = umma_desc_sw128_kmajor(sa);
-            const uint64_t db = umma_desc_sw128_kmajor(sa + BM * BK * 2);
+            const uint64_t da = p.a_mn ? umma_desc_sw128_mnmajor(sa, mn.lbo, mn.sbo)
+                                       : umma_desc_sw128_kmajor(sa);
+            const uint64_t db = p.b_mn ? umma_desc_sw128_mnmajor(sa + BM * BK * 2, mn.lbo, mn.sbo)
+                                       : umma_desc_sw128_kmajor(sa + BM * BK * 2);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_ss_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+              umma_bf16_ss_pair(tmem_d, da + a_step * k, db + b_step * k, idesc,
                                 (kb > kb0 || k > 0) ? 1u : 0u);
             umma_commit_pair(&empty_bar[stage]);
             if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);
@@ -681,7 +744,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams 
       (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
     if (make_tmap_f32_c(&tc, p.C, p.M, p.N, p.ldc) == SB_OK) p.tma_store = 1;
   }
-  gemm_bf16_tn_kernel<BN, MT><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
+  const MnDesc mn = {(uint32_t)g_mn_lbo, (uint32_t)g_mn_sbo, (uint32_t)g_mn_kadv};
+  gemm_bf16_tn_kernel<BN, MT><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p, mn);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
@@ -729,7 +793,8 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
   CUtensorMap tc;
   if (make_tmap_f32_c(&tc, p.C, p.M, p.N, p.ldc) != SB_OK) return SB_ERR_CUDA;
   p.tma_store = 1;
-  gemm_bf16_tn_pair_kernel<<<2 * pairs, 192, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
+  const MnDesc mn = {(uint32_t)g_mn_lbo, (uint32_t)g_mn_sbo, (uint32_t)g_mn_kadv};
+  gemm_bf16_tn_pair_kernel<<<2 * pairs, 192, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p, mn);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
@@ -738,6 +803,14 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
 using namespace sb;
 
 // developer hook (kernel selection); the default state is force = 1 | 4
+// developer hook: override the MN-major descriptor fields (bytes); 0 keeps a field
+extern "C" int sb_debug_umma_mn(int lbo, int sbo, int kadv) {
+  if (lbo > 0) sb::g_mn_lbo = lbo;
+  if (sbo > 0) sb::g_mn_sbo = sbo;
+  if (kadv > 0) sb::g_mn_kadv = kadv;
+  return SB_OK;
+}
+
 extern "C" int sb_debug_gemm_mt1(int force) {
   // bit 0: 1 = 128-row CTA tiles only (default), 0 = allow the 256-row variant
   // bit 1: 1 = disable the TMA-store epilogue (register stores)
@@ -765,6 +838,16 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   p.remap_B = remap_B; p.remap_T = remap_T; p.valid_B = valid_B;
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = 0;
+  p.a_mn = (flags & SB_GEMM_A_MN) ? 1 : 0;
+  p.b_mn = (flags & SB_GEMM_B_MN) ? 1 : 0;
+  // tensor maps: K-major operands are [rows][K] with box {64 K, rows}; MN-major operands are
+  // [K][rows] with box {64 rows, 64 K}
+  auto tmap_a = [&](CUtensorMap* m, int box_rows) {
+    return p.a_mn ? make_tmap_bf16_2d(m, A, K, M, lda, 64) : make_tmap_bf16_2d(m, A, M, K, lda, box_rows);
+  };
+  auto tmap_b = [&](CUtensorMap* m, int box_rows) {
+    return p.b_mn ? make_tmap_bf16_2d(m, B, K, N, ldb, 64) : make_tmap_bf16_2d(m, B, N, K, ldb, box_rows);
+  };
 
   // tile-N choice: the widest tile that still leaves >= ~1 wave of work
   const int sms = device_sm_count();
@@ -795,9 +878,9 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
     if (use_pair) {
       p.split_k = pair_split;
       CUtensorMap pa, pb;
-      int prc = make_tmap_bf16_2d(&pa, A, M, K, lda, BM);
+      int prc = tmap_a(&pa, BM);
       if (prc != SB_OK) return prc;
-      prc = make_tmap_bf16_2d(&pb, B, N, K, ldb, 128);
+      prc = tmap_b(&pb, 128);
       if (prc != SB_OK) return prc;
       return launch_gemm_pair(pa, pb, p, stream);
     }
@@ -807,9 +890,9 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
     p.split_k = pick_wave_filling_split((long long)p.m_tiles * ((N + bn - 1) / bn), sms,
                                         p.k_blocks_total);
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, mt * BM);
+  int rc = tmap_a(&ta, mt * BM);
   if (rc != SB_OK) return rc;
-  rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, bn);
+  rc = tmap_b(&tb, bn);
   if (rc != SB_OK) return rc;
   if (mt == 2) return launch_gemm<256, 2>(ta, tb, p, stream);
   switch (bn) {

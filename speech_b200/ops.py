@@ -12,6 +12,8 @@ from . import _lib
 
 GEMM_ACCUMULATE = 1
 GEMM_ROW_REMAP = 2
+GEMM_A_MN = 4
+GEMM_B_MN = 8
 
 
 def _round_up(x, m):
@@ -74,17 +76,20 @@ def _launch(name, flops, fn):
     return _lib.check(rc, name)
 
 
-def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=None):
+def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=None,
+                 a_mn=False, b_mn=False):
     """out[M,N] (f32) (+)= A[M,K] (bf16) @ B[N,K]^T (bf16) (+ bias).  A/B may be row-strided views.
 
+    a_mn / b_mn: that operand is given as [K][M] / [K][N] (the contraction runs over its rows).
     remap=(Bp, T, valid_B): rows m = t*Bp + b are written batch-first to row b*T + t.
     """
     lib = _lib.load()
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
-    assert A.stride(1) == 1 and B.stride(1) == 1 and A.shape[1] == B.shape[1]
-    M, K = A.shape
-    N = B.shape[0]
-    flags = 0
+    assert A.stride(1) == 1 and B.stride(1) == 1
+    K, M = A.shape if a_mn else (A.shape[1], A.shape[0])
+    Kb, N = B.shape if b_mn else (B.shape[1], B.shape[0])
+    assert K == Kb
+    flags = (GEMM_A_MN if a_mn else 0) | (GEMM_B_MN if b_mn else 0)
     rB = rT = vB = 0
     if remap is not None:
         rB, rT, vB = remap
@@ -108,18 +113,37 @@ def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=N
 
 _grad_ready_hook = None
 _announce = True
+_grad_sink_enabled = False
 
 
-def set_grad_ready_hook(fn):
+def set_grad_sink(enabled):
+    """Opt-in (optim.FlatSGD): let the weight-gradient GEMMs of GRUStackFunction.backward
+    accumulate straight into the parameters' existing .grad buffers and return None to autograd
+    for them.  Off by default, so that torch.autograd.grad, gradcheck, tensor hooks and gradient
+    accumulation see ordinary returned gradients."""
+    global _grad_sink_enabled
+    _grad_sink_enabled = bool(enabled)
+
+
+_grad_guard = None
+
+
+def set_grad_ready_hook(fn, guard=None):
     """fn(list_of_parameters) is called from inside GRUStackFunction.backward as soon as the
     gradients of one layer's parameters are final in their .grad buffers (all producing kernels
     enqueued on the current stream).  Used by optim.FlatSGD to start that layer's all-reduce
-    while the layers below are still being differentiated.  None disables."""
-    global _grad_ready_hook
+    while the layers below are still being differentiated.  None disables.
+    guard() (optional) runs at the START of every announcing backward pass, before any gradient
+    buffer is touched: it raises if an earlier backward of the same step already announced
+    (a second pass would add local gradients into slices that are being all-reduced)."""
+    global _grad_ready_hook, _grad_guard
     _grad_ready_hook = fn
+    _grad_guard = guard if fn is not None else None
 
 
 def _bias_sink(param):
+    if not _grad_sink_enabled:
+        return None
     g = getattr(param, "grad", None)
     if g is None or not g.is_cuda or g.dtype != torch.float32:
         return None
@@ -132,6 +156,8 @@ def _grad_sink(param, rows=None):
     dW with the GEMM's reduce-add epilogue into .grad replaces a zero-filled temporary plus
     autograd's separate `grad += dW` pass (the gradient-accumulation fusion used by large-model
     trainers); the Function then returns None for that parameter."""
+    if not _grad_sink_enabled:
+        return None
     g = getattr(param, "grad", None)
     if g is None or not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous():
         return None
@@ -219,7 +245,9 @@ class GRUStackFunction(torch.autograd.Function):
             if dropout > 0.0 and l + 1 < L:
                 # inter-layer dropout of nn.GRU(dropout=p): applied to every layer output but the last
                 mask = (torch.rand(M, D, device=dev) >= dropout).float() * (1.0 / (1.0 - dropout))
-                xn = xn * mask
+                # the next layer's operand stays bf16 (bf16 * f32 would promote to f32): mask the
+                # fp32 state and round once
+                xn = (y * mask).to(torch.bfloat16)
             if need_grad:
                 saved.append((X, y, gates, xnT, mask, wih_cat, whh))
             X = xn
@@ -246,6 +274,8 @@ class GRUStackFunction(torch.autograd.Function):
         lib = _lib.load()
         B, T, In, Bp, H, ndir, L = ctx.dims
         weights = ctx.weights
+        if _grad_ready_hook is not None and ctx.announce and _grad_guard is not None:
+            _grad_guard()
         dev = dout.device
         M = T * Bp
         D = ndir * H

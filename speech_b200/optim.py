@@ -51,9 +51,49 @@ class FlatSGD:
             p.grad = self.flat_g[o:o + p.numel()].view_as(p)
             self.spans[id(p)] = (o, o + (p.numel() + 3) // 4 * 4)
         self.reducer = BucketReducer(self.flat_g, world_size, group)
+        # the weight-gradient GEMMs accumulate straight into the flat gradient buffer (opt-in)
+        ops.set_grad_sink(True)
         if world_size > 1 and overlap:
             # GRU backward announces each layer's gradients as soon as they are final
-            ops.set_grad_ready_hook(self._grads_ready)
+            ops.set_grad_ready_hook(self._grads_ready, guard=self._guard_second_backward)
+
+    def _guard_second_backward(self):
+        if self.reducer.pending:
+            raise RuntimeError(
+                "FlatSGD(overlap=True): a second backward pass before step() would add local "
+                "gradients into slices that are already being all-reduced; use overlap=False "
+                "for gradient accumulation")
+
+    def _check_views(self):
+        """model.cuda()/.to() or zero_grad(set_to_none=True) silently detach the flat views"""
+        lo, hi = self.flat_p.data_ptr(), self.flat_p.data_ptr() + 4 * self.n
+        glo, ghi = self.flat_g.data_ptr(), self.flat_g.data_ptr() + 4 * self.n
+        for p in self.params:
+            if not (lo <= p.data_ptr() < hi):
+                raise RuntimeError("FlatSGD: a parameter no longer lives in the flat buffer "
+                                   "(model moved after the optimizer was built?)")
+            if p.grad is None or not (glo <= p.grad.data_ptr() < ghi):
+                raise RuntimeError("FlatSGD: a .grad no longer lives in the flat gradient buffer "
+                                   "(zero_grad(set_to_none=True)? use FlatSGD.zero_grad())")
+
+    def state_dict(self):
+        return {"lr": self.lr, "momentum": self.momentum, "max_grad_norm": self.max_norm,
+                "mom": None if self.mom is None else self.mom.detach().cpu().clone()}
+
+    def load_state_dict(self, state):
+        self.lr = float(state["lr"])
+        self.momentum = float(state["momentum"])
+        self.max_norm = float(state.get("max_grad_norm", self.max_norm))
+        mom = state.get("mom")
+        if self.momentum != 0:
+            if self.mom is None:
+                self.mom = torch.zeros_like(self.flat_p)
+            if mom is not None:
+                if mom.numel() != self.n:
+                    raise ValueError("FlatSGD.load_state_dict: momentum buffer size mismatch")
+                self.mom.copy_(mom.to(self.mom.device))
+        else:
+            self.mom = None
 
     def _grads_ready(self, params):
         spans = [self.spans.get(id(p)) for p in params]
@@ -69,6 +109,7 @@ class FlatSGD:
 
     def step(self):
         lib = _lib.load()
+        self._check_views()
         self.all_reduce()
         sp = _lib.stream_ptr()
         ops._launch("sumsq", 0.0, lambda: lib.sb_sumsq(self.flat_g.data_ptr(), self.n,

@@ -88,5 +88,8 @@ class GradSync:
 
     def shard(self, items, rank):
         """contiguous B/N shard of a per-utterance list for `rank`."""
+        if len(items) % self.world != 0:
+            raise ValueError("minibatch of %d utterances is not divisible by world size %d"
+                             % (len(items), self.world))
         per = len(items) // self.world
         return items[rank * per:(rank + 1) * per]

@@ -29,3 +29,13 @@ def cuda_lib():
     build.build()
     from speech_b200 import _lib
     return _lib.load()
+
+
+@pytest.fixture(autouse=True)
+def _reset_grad_plumbing():
+    """optim.FlatSGD switches on process-wide hooks of speech_b200.ops (in-place gradient sink,
+    grad-ready announcements); no test may leak them into the next one."""
+    yield
+    from speech_b200 import ops
+    ops.set_grad_sink(False)
+    ops.set_grad_ready_hook(None)
