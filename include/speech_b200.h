@@ -101,13 +101,17 @@ int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bhh, float* y
  *   dgi    [T*Bp][ndir*3H] bf16 (out) gradient w.r.t. gi        -> dX = dgi * W_ih
  *   dgiT   [ndir*3H][T*Bp] bf16 (out) same, transposed          -> dW_ih, dW_hh (r,z rows)
  *   dghnT  [ndir][H][T*Bp] bf16 (out) r * dn_pre, transposed    -> dW_hh (n rows)
+ *          (dgiT and dghnT may both be NULL: the weight gradients then contract the token-major
+ *           dgi / dghn directly with SB_GEMM_A_MN | SB_GEMM_B_MN)
+ *   dghn   [T*Bp][ndir*H] bf16 (out) r * dn_pre, token-major    -> dW_hh (n rows); may be NULL
+ *          when dghnT is given
  *   dbih, dbhh [ndir*3H] f32 accumulated (+=)
  */
 int sb_gru_bwd_workspace_size(int Bp, int H, int ndir, size_t* bytes);
 int sb_gru_bwd(const float* dy, const float* y, const float* gates, const void* whhT_bf16,
-               void* dgi_bf16, void* dgiT_bf16, void* dghnT_bf16, float* dbih, float* dbhh,
-               void* workspace, size_t workspace_bytes, unsigned int* barrier, int T, int Bp, int H,
-               int ndir, void* stream);
+               void* dgi_bf16, void* dgiT_bf16, void* dghnT_bf16, void* dghn_bf16, float* dbih,
+               float* dbhh, void* workspace, size_t workspace_bytes, unsigned int* barrier, int T,
+               int Bp, int H, int ndir, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * CTC prefix beam search, one CTA per utterance.

@@ -187,6 +187,59 @@ col2im_relu_kernel(const float* __restrict__ dA, long long ldA, const float* __r
     if (dbs[c] != 0.f) atomicAdd(db + c, dbs[c]);
 }
 
+// Any tap count (runtime loops): the TIMIT recipes' second layer [*, 5, 32, 1] has 5 x 32 taps per
+// input pixel, far beyond the unrolled instantiations above.  The inner loop over j is unrolled by
+// 4 with the loads issued before their use, so 4 loads are in flight per thread.
+__global__ void __launch_bounds__(256)
+col2im_relu_generic_kernel(const float* __restrict__ dA, long long ldA,
+                           const float* __restrict__ Pprev,
+                           const unsigned char* __restrict__ maskprev, float mscale,
+                           bf16* __restrict__ dCprev, float* __restrict__ db, int B, int Ti, int Fi,
+                           int Ci, int kh, int kw, int s, int To, int Fo) {
+  extern __shared__ float dbs[];
+  for (int c = threadIdx.x; c < Ci; c += 256) dbs[c] = 0.f;
+  __syncthreads();
+  const long long total = (long long)B * Ti * Fi * Ci;
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * 256) {
+    const int ci = (int)(idx % Ci);
+    const int px = (int)(idx / Ci);
+    const int fi = px % Fi;
+    const int bt = px / Fi;
+    const int ti = bt % Ti;
+    const int b = bt / Ti;
+    const float mask = __ldg(Pprev + idx);
+    float g = 0.f;
+    if (mask > 0.f) {
+      for (int i = ti % s; i < kh && i <= ti; i += s) {
+        const int t = (ti - i) / s;
+        if (t >= To) continue;
+        const float* rowp = dA + ((long long)b * To + t) * Fo * ldA + (long long)i * kw * Ci + ci;
+        int j = fi % s;
+        for (; j + 3 * s < kw && j + 3 * s <= fi; j += 4 * s) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int f = (fi - j - u * s) / s;
+            v[u] = f < Fo ? __ldcs(rowp + (long long)f * ldA + (j + u * s) * Ci) : 0.f;
+          }
+          g += (v[0] + v[1]) + (v[2] + v[3]);
+        }
+        for (; j < kw && j <= fi; j += s) {
+          const int f = (fi - j) / s;
+          if (f < Fo) g += __ldcs(rowp + (long long)f * ldA + j * Ci);
+        }
+      }
+      if (maskprev) g = maskprev[idx] ? g * mscale : 0.f;
+    }
+    dCprev[idx] = __float2bfloat16_rn(g);
+    if (g != 0.f) atomicAdd(&dbs[ci], g);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Ci; c += 256)
+    if (dbs[c] != 0.f) atomicAdd(db + c, dbs[c]);
+}
+
 // ---- bf16 matrix transpose [R][C] -> [C][ld_dst] ------------------------------------------------
 // 64x64 tiles, 32-bit (bf16x2) global accesses on both sides, padded shared tile.
 __global__ void __launch_bounds__(256)
@@ -303,7 +356,10 @@ extern "C" int sb_conv_col2im_relu(const float* dA, long long ldA, const float* 
   if (ni <= 2 && nj <= 2) SB_C2I(2, 2);
   else if (ni <= 3 && nj <= 4) SB_C2I(3, 4);
   else if (ni <= 5 && nj <= 8) SB_C2I(5, 8);
-  else return SB_ERR_UNSUPPORTED;
+  else
+    col2im_relu_generic_kernel<<<g, 256, sm, stream>>>(
+        dA, ldA, Pprev, reinterpret_cast<const unsigned char*>(maskprev_u8), mscale, out, db, B, Ti,
+        Fi, Ci, kh, kw, stride, To, Fo);
 #undef SB_C2I
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }

@@ -852,7 +852,7 @@ extern "C" int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   // tile-N choice: the widest tile that still leaves >= ~1 wave of work
   const int sms = device_sm_count();
   int bn;
-  if (N <= 32) bn = 32;
+  if (N <= 32 && !p.b_mn) bn = 32;   // (an MN-major B tile is made of 64-wide boxes)
   else if (N <= 64) bn = 64;
   else if (N <= 128) bn = 128;
   else {

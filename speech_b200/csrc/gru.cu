@@ -65,7 +65,8 @@ struct GruBwdParams {
   const bf16* whhT;    // [ndir][H][3H]    W_hh^T, bf16
   bf16* dgi;           // [T*Bp][ndir*3H]  d(pre-activation) of the input projection, bf16
   bf16* dgiT;          // [ndir*3H][T*Bp]  same, transposed (wgrad operand)
-  bf16* dghnT;         // [ndir][H][T*Bp]  dn_pre * r, transposed (wgrad of W_hn)
+  bf16* dghnT;         // [ndir][H][T*Bp]  dn_pre * r, transposed (wgrad of W_hn); may be null
+  bf16* dghn;          // [T*Bp][ndir*H]   dn_pre * r, token-major (MN-major wgrad operand); may be null
   bf16* xchg;          // [ndir][2][Bp][3H] per-step exchange of dgh_t
   float* dbih;         // [ndir*3H] += sum_{t,b} dgi
   float* dbhh;         // [ndir*3H] += sum_{t,b} dgh
@@ -606,14 +607,17 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
         st_stream_u4(o, pack8(dr));
         st_stream_u4(o + H, pack8(dz));
         st_stream_u4(o + 2 * H, pack8(dn));
-        bf16* gt = p.dgiT + ((long long)dir * K3 + ju) * M + m;
-        bf16* nt = p.dghnT + ((long long)dir * H + ju) * M + m;
+        if (p.dghn) st_stream_u4(p.dghn + m * D + dir * H + ju, pack8(dnr));
+        if (p.dgiT) {
+          bf16* gt = p.dgiT + ((long long)dir * K3 + ju) * M + m;
+          bf16* nt = p.dghnT + ((long long)dir * H + ju) * M + m;
 #pragma unroll
-        for (int jj = 0; jj < GRU_UPT; ++jj) {
-          st_stream_bf16(gt + (long long)jj * M, dr[jj]);
-          st_stream_bf16(gt + (long long)(H + jj) * M, dz[jj]);
-          st_stream_bf16(gt + (long long)(2 * H + jj) * M, dn[jj]);
-          st_stream_bf16(nt + (long long)jj * M, dnr[jj]);
+          for (int jj = 0; jj < GRU_UPT; ++jj) {
+            st_stream_bf16(gt + (long long)jj * M, dr[jj]);
+            st_stream_bf16(gt + (long long)(H + jj) * M, dz[jj]);
+            st_stream_bf16(gt + (long long)(2 * H + jj) * M, dn[jj]);
+            st_stream_bf16(nt + (long long)jj * M, dnr[jj]);
+          }
         }
       }
       if (tid == 0) GRU_STAMP(10);
@@ -924,14 +928,17 @@ gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
         st_stream_u4(o, pack8(dr));
         st_stream_u4(o + H, pack8(dz));
         st_stream_u4(o + 2 * H, pack8(dn));
-        bf16* gt = p.dgiT + ((long long)dir * K3 + ju) * M + m;
-        bf16* nt = p.dghnT + ((long long)dir * H + ju) * M + m;
+        if (p.dghn) st_stream_u4(p.dghn + m * D + dir * H + ju, pack8(dnr));
+        if (p.dgiT) {
+          bf16* gt = p.dgiT + ((long long)dir * K3 + ju) * M + m;
+          bf16* nt = p.dghnT + ((long long)dir * H + ju) * M + m;
 #pragma unroll
-        for (int jj = 0; jj < GRU_UPT; ++jj) {
-          st_stream_bf16(gt + (long long)jj * M, dr[jj]);
-          st_stream_bf16(gt + (long long)(H + jj) * M, dz[jj]);
-          st_stream_bf16(gt + (long long)(2 * H + jj) * M, dn[jj]);
-          st_stream_bf16(nt + (long long)jj * M, dnr[jj]);
+          for (int jj = 0; jj < GRU_UPT; ++jj) {
+            st_stream_bf16(gt + (long long)jj * M, dr[jj]);
+            st_stream_bf16(gt + (long long)(H + jj) * M, dz[jj]);
+            st_stream_bf16(gt + (long long)(2 * H + jj) * M, dn[jj]);
+            st_stream_bf16(nt + (long long)jj * M, dnr[jj]);
+          }
         }
       }
       if (tid == 0) GRU_STAMP(10);
@@ -1166,14 +1173,17 @@ extern "C" int sb_gru_bwd_workspace_size(int Bp, int H, int ndir, size_t* bytes)
 
 extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
                           const void* whhT_bf16, void* dgi_bf16, void* dgiT_bf16,
-                          void* dghnT_bf16, float* dbih, float* dbhh, void* workspace,
+                          void* dghnT_bf16, void* dghn_bf16, float* dbih, float* dbhh,
+                          void* workspace,
                           size_t workspace_bytes, unsigned int* barrier, int T, int Bp, int H,
                           int ndir, void* stream_) {
   int rc = gru_check(T, Bp, H, ndir);
   if (rc != SB_OK) return rc;
-  if (!dy || !y || !gates || !whhT_bf16 || !dgi_bf16 || !dgiT_bf16 || !dghnT_bf16 || !dbih ||
-      !dbhh || !workspace || !barrier)
+  if (!dy || !y || !gates || !whhT_bf16 || !dgi_bf16 || !dbih || !dbhh || !workspace || !barrier)
     return SB_ERR_INVALID;
+  // the W_hn gradient operand in at least one of its two layouts; the transposed pair goes together
+  if ((dgiT_bf16 == nullptr) != (dghnT_bf16 == nullptr)) return SB_ERR_INVALID;
+  if (!dghnT_bf16 && !dghn_bf16) return SB_ERR_INVALID;
   size_t need = 0;
   sb_gru_bwd_workspace_size(Bp, H, ndir, &need);
   if (workspace_bytes < need) return SB_ERR_WORKSPACE;
@@ -1182,6 +1192,7 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   p.dy = dy; p.y = y; p.gates = gates; p.whhT = reinterpret_cast<const bf16*>(whhT_bf16);
   p.dgi = reinterpret_cast<bf16*>(dgi_bf16); p.dgiT = reinterpret_cast<bf16*>(dgiT_bf16);
   p.dghnT = reinterpret_cast<bf16*>(dghnT_bf16);
+  p.dghn = reinterpret_cast<bf16*>(dghn_bf16);
   p.xchg = reinterpret_cast<bf16*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   p.dbih = dbih; p.dbhh = dbhh; p.barrier = barrier; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
   p.dbg = g_gru_dbg;

@@ -111,6 +111,11 @@ def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=N
     return out
 
 
+# Weight-gradient GEMMs contract the token-major activations directly (MN-major UMMA operands,
+# SB_GEMM_A_MN | SB_GEMM_B_MN): no transposed copies (xnT / dgiT / dghnT) are produced at all.
+# False restores the K-major path over transposed copies (developer knob, SB_WGRAD_MN=0).
+USE_MN = __import__("os").environ.get("SB_WGRAD_MN", "1") != "0"
+
 _grad_ready_hook = None
 _announce = True
 _grad_sink_enabled = False
@@ -232,9 +237,10 @@ class GRUStackFunction(torch.autograd.Function):
             xn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
             xnT = gates = None
             if need_grad:
-                xnT = torch.empty(D, (T + 2) * Bp, dtype=torch.bfloat16, device=dev)
-                xnT[:, :Bp].zero_()                     # h_{-1} = 0 (forward direction)
-                xnT[:, (T + 1) * Bp:].zero_()           # h_{T}  = 0 (backward direction)
+                if not USE_MN:
+                    xnT = torch.empty(D, (T + 2) * Bp, dtype=torch.bfloat16, device=dev)
+                    xnT[:, :Bp].zero_()                     # h_{-1} = 0 (forward direction)
+                    xnT[:, (T + 1) * Bp:].zero_()           # h_{T}  = 0 (backward direction)
                 gates = torch.empty(M, ndir, 4, H, dtype=torch.float32, device=dev)
             sp = _lib.stream_ptr()
             _launch("gru_fwd", 2.0 * M * 3 * H * H * ndir,
@@ -242,6 +248,7 @@ class GRUStackFunction(torch.autograd.Function):
                                            y.data_ptr(), xn.data_ptr(), _lib.ptr(xnT),
                                            _lib.ptr(gates), barrier.data_ptr(), T, Bp, H, ndir, sp))
             mask = None
+            hb = xn                                     # bf16 h_t (un-masked): dW_hh operand
             if dropout > 0.0 and l + 1 < L:
                 # inter-layer dropout of nn.GRU(dropout=p): applied to every layer output but the last
                 mask = (torch.rand(M, D, device=dev) >= dropout).float() * (1.0 / (1.0 - dropout))
@@ -249,7 +256,7 @@ class GRUStackFunction(torch.autograd.Function):
                 # fp32 state and round once
                 xn = (y * mask).to(torch.bfloat16)
             if need_grad:
-                saved.append((X, y, gates, xnT, mask, wih_cat, whh))
+                saved.append((X, y, gates, xnT, mask, wih_cat, whh, hb))
             X = xn
         ctx.saved = saved
         ctx.announce = _announce
@@ -293,10 +300,14 @@ class GRUStackFunction(torch.autograd.Function):
             for d in range(ndir):
                 wT[d * H:(d + 1) * H, :V] = w.t()
             dY = gemm_bf16_tn(dl, wT)                                         # [M][D] f32
-            top_xnT = ctx.saved[L - 1][3]
             dw2 = torch.zeros(Vp, D, dtype=torch.float32, device=dev)
-            gemm_bf16_tn(dl.t().contiguous(), top_xnT[:, Bp:Bp + M], out=dw2, accumulate=True,
-                         split_k=_wgrad_split(Vp, D, M))
+            if USE_MN:
+                gemm_bf16_tn(dl, Xtop, out=dw2, accumulate=True, split_k=_wgrad_split(Vp, D, M),
+                             a_mn=True, b_mn=True)
+            else:
+                top_xnT = ctx.saved[L - 1][3]
+                gemm_bf16_tn(dl.t().contiguous(), top_xnT[:, Bp:Bp + M], out=dw2, accumulate=True,
+                             split_k=_wgrad_split(Vp, D, M))
             dfc_w = dw2[:V, :H] if ndir == 1 else dw2[:V, :H] + dw2[:V, H:]
             dfc_b = dout.sum((0, 1))
         elif B == Bp:
@@ -312,7 +323,7 @@ class GRUStackFunction(torch.autograd.Function):
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
         grads = [None] * len(weights)
         for l in reversed(range(L)):
-            X, y, gates, xnT, mask, wih_cat, whh = ctx.saved[l]
+            X, y, gates, xnT, mask, wih_cat, whh, hb = ctx.saved[l]
             if mask is not None:
                 dY = dY * mask
             wl = weights[l * 4 * ndir:(l + 1) * 4 * ndir]
@@ -322,58 +333,51 @@ class GRUStackFunction(torch.autograd.Function):
             for d in range(ndir):
                 _transpose_bf16(whh[d], out=whhT[d])
             dgi = torch.empty(M, ndir * K3, dtype=torch.bfloat16, device=dev)
-            dgiT = torch.empty(ndir * K3, M, dtype=torch.bfloat16, device=dev)
-            dghnT = torch.empty(ndir, H, M, dtype=torch.bfloat16, device=dev)
+            dgiT = dghnT = dghn = None
+            if USE_MN:
+                dghn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+            else:
+                dgiT = torch.empty(ndir * K3, M, dtype=torch.bfloat16, device=dev)
+                dghnT = torch.empty(ndir, H, M, dtype=torch.bfloat16, device=dev)
             dbih = torch.zeros(ndir * K3, dtype=torch.float32, device=dev)
             dbhh = torch.zeros(ndir * K3, dtype=torch.float32, device=dev)
             sp = _lib.stream_ptr()
             _launch("gru_bwd", 2.0 * M * 3 * H * H * ndir,
                     lambda dY=dY: lib.sb_gru_bwd(dY.data_ptr(), y.data_ptr(), gates.data_ptr(),
-                                                 whhT.data_ptr(), dgi.data_ptr(), dgiT.data_ptr(),
-                                                 dghnT.data_ptr(), dbih.data_ptr(), dbhh.data_ptr(),
-                                                 ws.data_ptr(), nbytes.value, barrier.data_ptr(),
-                                                 T, Bp, H, ndir, sp))
-            # ---- weight gradients: K = T*Bp contractions on the transposed copies ----
-            if l > 0 and ctx.saved[l - 1][4] is None:
-                XT = ctx.saved[l - 1][3][:, Bp:Bp + M]                   # [In_l][M] view
-            else:
-                XT = X.t().contiguous()                                   # [Kl][M]
-            sinks_ih = [_grad_sink(wl[d * 4]) if XT.shape[0] == In_l else None
-                        for d in range(ndir)]
-            if all(g is not None for g in sinks_ih):
-                # accumulate dW_ih of each direction straight into the parameter's .grad
+                                                 whhT.data_ptr(), dgi.data_ptr(), _lib.ptr(dgiT),
+                                                 _lib.ptr(dghnT), _lib.ptr(dghn), dbih.data_ptr(),
+                                                 dbhh.data_ptr(), ws.data_ptr(), nbytes.value,
+                                                 barrier.data_ptr(), T, Bp, H, ndir, sp))
+            base = l * 4 * ndir
+            if USE_MN:
+                # ---- weight gradients: contract the token-major operands over their rows ----
+                Ms = M - Bp                      # tokens that have a predecessor in the recurrence
                 for d in range(ndir):
-                    gemm_bf16_tn(dgiT[d * K3:(d + 1) * K3], XT, out=sinks_ih[d], accumulate=True,
-                                 split_k=_wgrad_split(K3, In_l, M))
-                dwih = None
+                    # dW_ih[d] (3H x In_l) = dgi[:, d]^T X
+                    sink = _grad_sink(wl[d * 4])
+                    dwih = sink if sink is not None else \
+                        torch.zeros(K3, In_l, dtype=torch.float32, device=dev)
+                    gemm_bf16_tn(dgi[:, d * K3:(d + 1) * K3], X[:, :In_l], out=dwih,
+                                 accumulate=True, a_mn=True, b_mn=True)
+                    # dW_hh[d] = [dgi_r | dgi_z | dghn]^T h_prev: h_prev of token (t, b) is token
+                    # (t-1, b) in the forward direction and (t+1, b) in the reverse one, so the
+                    # shift is a row offset of Bp on one of the two operands
+                    sink_hh = _grad_sink(wl[d * 4 + 1])
+                    dwhh = sink_hh if sink_hh is not None else \
+                        torch.zeros(K3, H, dtype=torch.float32, device=dev)
+                    if Ms > 0:
+                        ga, hp = (slice(Bp, M), slice(0, Ms)) if d == 0 else \
+                            (slice(0, Ms), slice(Bp, M))
+                        gemm_bf16_tn(dgi[ga, d * K3:d * K3 + 2 * H], hb[hp, d * H:(d + 1) * H],
+                                     out=dwhh[:2 * H], accumulate=True, a_mn=True, b_mn=True)
+                        gemm_bf16_tn(dghn[ga, d * H:(d + 1) * H], hb[hp, d * H:(d + 1) * H],
+                                     out=dwhh[2 * H:], accumulate=True, a_mn=True, b_mn=True)
+                    grads[base + d * 4 + 0] = None if sink is not None else dwih
+                    grads[base + d * 4 + 1] = None if sink_hh is not None else dwhh
+                    grads[base + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
+                    grads[base + d * 4 + 3] = dbhh[d * K3:(d + 1) * K3]
             else:
-                sk = _wgrad_split(ndir * K3, XT.shape[0], M)
-                if sk == 1:
-                    dwih = gemm_bf16_tn(dgiT, XT)
-                else:
-                    dwih = torch.zeros(ndir * K3, XT.shape[0], dtype=torch.float32, device=dev)
-                    gemm_bf16_tn(dgiT, XT, out=dwih, accumulate=True, split_k=sk)
-            for d in range(ndir):
-                hprevT = xnT[d * H:(d + 1) * H, (0 if d == 0 else 2 * Bp):][:, :M]
-                sk = _wgrad_split(2 * H, H, M)
-                sink = _grad_sink(wl[d * 4 + 1])
-                if sink is not None:
-                    dwhh = sink
-                    acc = True
-                elif sk == 1:
-                    dwhh = torch.empty(K3, H, dtype=torch.float32, device=dev)
-                    acc = False
-                else:
-                    dwhh = torch.zeros(K3, H, dtype=torch.float32, device=dev)
-                    acc = True
-                gemm_bf16_tn(dgiT[d * K3:d * K3 + 2 * H], hprevT, out=dwhh[:2 * H],
-                             accumulate=acc, split_k=sk)
-                gemm_bf16_tn(dghnT[d], hprevT, out=dwhh[2 * H:], accumulate=acc, split_k=sk)
-                grads[l * 4 * ndir + d * 4 + 0] = None if dwih is None else \
-                    dwih[d * K3:(d + 1) * K3, :In_l]
-                grads[l * 4 * ndir + d * 4 + 1] = None if sink is not None else dwhh
-                grads[l * 4 * ndir + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
-                grads[l * 4 * ndir + d * 4 + 3] = dbhh[d * K3:(d + 1) * K3]
+                _wgrad_kmajor(ctx, l, X, xnT, dgiT, dghnT, dbih, dbhh, wl, grads, dev)
             if _grad_ready_hook is not None and ctx.announce:
                 base = l * 4 * ndir
                 if all(grads[base + d * 4 + k] is None for d in range(ndir) for k in (0, 1)):
@@ -391,13 +395,62 @@ class GRUStackFunction(torch.autograd.Function):
                         _grad_ready_hook(list(wl))
             # ---- gradient w.r.t. the layer input ----
             if l > 0 or ctx.needs_input_grad[0]:
-                wihT = _transpose_bf16(wih_cat)                           # [Kl][ndir*3H]
-                dY = gemm_bf16_tn(dgi, wihT)                              # [M][Kl] f32
+                if USE_MN:
+                    dY = gemm_bf16_tn(dgi, wih_cat, b_mn=True)            # [M][Kl] f32
+                else:
+                    wihT = _transpose_bf16(wih_cat)                       # [Kl][ndir*3H]
+                    dY = gemm_bf16_tn(dgi, wihT)                          # [M][Kl] f32
         dx = None
         if ctx.needs_input_grad[0]:
             dx = dY.view(T, Bp, -1)[:, :B, :In].transpose(0, 1).contiguous()
         ctx.saved = None
         return (dx, None, None, None, dfc_w, dfc_b) + tuple(grads)
+
+def _wgrad_kmajor(ctx, l, X, xnT, dgiT, dghnT, dbih, dbhh, wl, grads, dev):
+    """Weight gradients of layer l over TRANSPOSED copies (K-major operands): the path used before
+    the MN-major operand support; kept behind SB_WGRAD_MN=0 as a cross-check."""
+    B, T, In, Bp, H, ndir, L = ctx.dims
+    M = T * Bp
+    K3 = 3 * H
+    In_l = wl[0].shape[1]
+    if l > 0 and ctx.saved[l - 1][4] is None:
+        XT = ctx.saved[l - 1][3][:, Bp:Bp + M]                   # [In_l][M] view
+    else:
+        XT = X.t().contiguous()                                   # [Kl][M]
+    sinks_ih = [_grad_sink(wl[d * 4]) if XT.shape[0] == In_l else None for d in range(ndir)]
+    if all(g is not None for g in sinks_ih):
+        for d in range(ndir):
+            gemm_bf16_tn(dgiT[d * K3:(d + 1) * K3], XT, out=sinks_ih[d], accumulate=True,
+                         split_k=_wgrad_split(K3, In_l, M))
+        dwih = None
+    else:
+        sk = _wgrad_split(ndir * K3, XT.shape[0], M)
+        if sk == 1:
+            dwih = gemm_bf16_tn(dgiT, XT)
+        else:
+            dwih = torch.zeros(ndir * K3, XT.shape[0], dtype=torch.float32, device=dev)
+            gemm_bf16_tn(dgiT, XT, out=dwih, accumulate=True, split_k=sk)
+    for d in range(ndir):
+        hprevT = xnT[d * H:(d + 1) * H, (0 if d == 0 else 2 * Bp):][:, :M]
+        sk = _wgrad_split(2 * H, H, M)
+        sink = _grad_sink(wl[d * 4 + 1])
+        if sink is not None:
+            dwhh = sink
+            acc = True
+        elif sk == 1:
+            dwhh = torch.empty(K3, H, dtype=torch.float32, device=dev)
+            acc = False
+        else:
+            dwhh = torch.zeros(K3, H, dtype=torch.float32, device=dev)
+            acc = True
+        gemm_bf16_tn(dgiT[d * K3:d * K3 + 2 * H], hprevT, out=dwhh[:2 * H],
+                     accumulate=acc, split_k=sk)
+        gemm_bf16_tn(dghnT[d], hprevT, out=dwhh[2 * H:], accumulate=acc, split_k=sk)
+        grads[l * 4 * ndir + d * 4 + 0] = None if dwih is None else \
+            dwih[d * K3:(d + 1) * K3, :In_l]
+        grads[l * 4 * ndir + d * 4 + 1] = None if sink is not None else dwhh
+        grads[l * 4 * ndir + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
+        grads[l * 4 * ndir + d * 4 + 3] = dbhh[d * K3:(d + 1) * K3]
 
 
 def _gru_weights(rnn):
@@ -544,15 +597,24 @@ class ConvStackFunction(torch.autograd.Function):
                                                  dCl.data_ptr(),
                                                  db.data_ptr(), B, To, Fo, Co, sp))
             grads[2 * l + 1] = db
-            # weight gradient: dWp[Co][Kp] = dC^T [Co][M] . A^T [Kp][M]^T   (K = M, split-K)
-            dCT = _transpose_bf16(dC)
-            AT = _transpose_bf16(A)
-            dWp = torch.zeros(Co, Kp, dtype=torch.float32, device=dev)
-            gemm_bf16_tn(dCT, AT, out=dWp, accumulate=True, split_k=_wgrad_split(Co, Kp, M))
+            # weight gradient: contraction over the M = B*To*Fo patch rows (split-K over all SMs)
+            if USE_MN:
+                # dWp^T [Kp][Co] = A^T dC with both operands read token-major (MN-major UMMA)
+                dWpT = torch.zeros(Kp, Co, dtype=torch.float32, device=dev)
+                gemm_bf16_tn(A, dC, out=dWpT, accumulate=True, a_mn=True, b_mn=True)
+                dWp = dWpT.t()
+            else:
+                dCT = _transpose_bf16(dC)
+                AT = _transpose_bf16(A)
+                dWp = torch.zeros(Co, Kp, dtype=torch.float32, device=dev)
+                gemm_bf16_tn(dCT, AT, out=dWp, accumulate=True, split_k=_wgrad_split(Co, Kp, M))
             grads[2 * l] = dWp[:, :K].reshape(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
             if l > 0:
-                WpT = Wp.t().contiguous()                       # [Kp][Co]
-                dA = gemm_bf16_tn(dC, WpT)                      # [M][Kp] f32 patch gradient
+                if USE_MN:
+                    dA = gemm_bf16_tn(dC, Wp, b_mn=True)        # [M][Kp] f32 patch gradient
+                else:
+                    WpT = Wp.t().contiguous()                   # [Kp][Co]
+                    dA = gemm_bf16_tn(dC, WpT)                  # [M][Kp] f32 patch gradient
                 Mp = B * Ti * Fi
                 dCp = torch.empty(Mp, Ci, dtype=torch.bfloat16, device=dev)
                 db = torch.zeros(Ci, dtype=torch.float32, device=dev)
@@ -567,12 +629,6 @@ class ConvStackFunction(torch.autograd.Function):
         ctx.saved = None
         ctx.masks = None
         return (None, None, None) + tuple(grads)
-
-
-def _col2im_taps_ok(c):
-    """largest instantiation of col2im_relu_kernel<MAXI, MAXJ> (csrc/conv.cu): taps per stride phase"""
-    s = c.stride[0]
-    return -(-c.kernel_size[0] // s) <= 5 and -(-c.kernel_size[1] // s) <= 8
 
 
 def conv_stack(x, conv, training):
@@ -595,18 +651,16 @@ def conv_stack(x, conv, training):
     simple = all(c.stride[0] == c.stride[1] and c.padding == (0, 0) and c.dilation == (1, 1)
                  and c.groups == 1 and c.bias is not None and c.out_channels % 8 == 0
                  for c in convs)
-    needs_grad = torch.is_grad_enabled() and any(q.requires_grad for q in conv.parameters())
-    if needs_grad and not all(_col2im_taps_ok(c) for c in convs[1:]):
-        simple = False
-    if convs and simple and not drop:
-        specs = tuple((c.kernel_size[0], c.kernel_size[1], c.stride[0]) for c in convs)
-        params = []
-        for c in convs:
-            params += [c.weight, c.bias]
-        return ConvStackFunction.apply(x, specs, float(p_drop), *params)
-    y = conv(x.unsqueeze(1))
-    b, c, t, f = y.shape
-    return y.transpose(1, 2).reshape(b, t, c * f)
+    if not (convs and simple and not drop):
+        raise _lib.SpeechB200Error(
+            "conv_stack: unsupported convolution stack (needs square stride, no padding / "
+            "dilation / groups, bias, out_channels % 8 == 0, one dropout rate); this package has "
+            "no cuDNN fallback")
+    specs = tuple((c.kernel_size[0], c.kernel_size[1], c.stride[0]) for c in convs)
+    params = []
+    for c in convs:
+        params += [c.weight, c.bias]
+    return ConvStackFunction.apply(x, specs, float(p_drop), *params)
 
 
 def beam_topk(scores, k):

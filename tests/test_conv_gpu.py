@@ -27,6 +27,10 @@ def _build(specs, in_c=1):
     ([[8, 5, 8, 2], [8, 5, 8, 2]], 3, 61, 80),          # golden 'bi' config
     ([[32, 5, 8, 2], [32, 5, 8, 2]], 2, 90, 80),        # north-star conv stack (WSJ)
     ([[16, 3, 4, 1], [8, 2, 3, 3]], 2, 33, 21),          # odd geometry, stride 1 and 3
+    # the shipped TIMIT recipe (examples/timit/ctc_config.json: second layer [32, 5, 32, 1] =
+    # 5 x 32 taps per input pixel -> the runtime-loop col2im gather; was a cuDNN fallback)
+    ([[32, 5, 32, 2], [32, 5, 32, 1]], 2, 60, 161),
+    ([[8, 7, 12, 1], [8, 6, 11, 2]], 2, 40, 48),         # > 5 x 8 taps per stride phase, stride 2
 ])
 def test_conv_stack_forward_backward(cuda_lib, specs, B, T, F):
     from speech_b200 import ops

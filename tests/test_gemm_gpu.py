@@ -106,3 +106,42 @@ def test_gemm_row_remap_time_major_to_batch_first(cuda_lib):
     C = _gemm(A, B, None, remap=(Bp, T, Bv))
     ref = (A.float() @ B.float().t()).view(T, Bp, N)[:, :Bv].transpose(0, 1).reshape(Bv * T, N)
     assert (C - ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 64, 64),        # one tile, one k-block
+    (300, 200, 1000),     # ragged everything
+    (32, 2048, 15808),    # fc weight gradient shape class (M_out = padded vocabulary)
+    (1280, 32, 30000),    # conv weight gradient (transposed form): long K, narrow N
+    (3072, 480, 15808),   # layer-0 dW_ih: CTA-pair kernel, split chosen by the library
+    (2048, 1024, 15744),  # dW_hh (r,z rows)
+])
+@pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
+def test_gemm_mn_major_operands_bit_identical_to_k_major(cuda_lib, M, N, K, a_mn, b_mn):
+    """MN-major UMMA operands (the contraction runs over the ROWS of the matrix in memory) must
+    give exactly the K-major result: same k order, same accumulator, only the shared-memory layout
+    and the descriptors differ.  The transposed operands are strided views of wider matrices, as
+    the weight-gradient call sites pass them."""
+    from speech_b200 import ops
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    Mp, Np = (M + 7) // 8 * 8 + 8, (N + 7) // 8 * 8 + 16
+    At = torch.zeros(K, Mp, device="cuda", dtype=torch.bfloat16)
+    At[:, 8:8 + M] = A.t()
+    Bt = torch.zeros(K, Np, device="cuda", dtype=torch.bfloat16)
+    Bt[:, 8:8 + N] = B.t()
+    a = At[:, 8:8 + M] if a_mn else A
+    b = Bt[:, 8:8 + N] if b_mn else B
+    # plain GEMM
+    ref = ops.gemm_bf16_tn(A, B)
+    out = ops.gemm_bf16_tn(a, b, a_mn=a_mn, b_mn=b_mn)
+    torch.cuda.synchronize()
+    assert torch.equal(ref, out)
+    f32 = A.float() @ B.float().t()
+    assert ((out - f32).abs().max() / f32.abs().max()).item() < 1e-4
+    # accumulating (split-K) GEMM: reduce-add order is not deterministic, compare numerically
+    acc = torch.zeros(M, N, device="cuda")
+    ops.gemm_bf16_tn(a, b, out=acc, accumulate=True, a_mn=a_mn, b_mn=b_mn)
+    torch.cuda.synchronize()
+    assert ((acc - f32).abs().max() / f32.abs().max()).item() < 1e-4

@@ -83,6 +83,7 @@ def test_gru_large_per_gpu_batch(cuda_lib, B, H):
 def test_gru_wgrad_accumulates_into_existing_grad(cuda_lib):
     """With .grad already allocated (FlatSGD / zero_grad(set_to_none=False)) the weight-gradient
     GEMMs reduce-add straight into it; two backward passes must give exactly 2x one pass."""
+    from speech_b200 import ops
     from speech_b200.ops import gru_stack
     torch.manual_seed(3)
     rnn = torch.nn.GRU(64, 128, 2, batch_first=True, bidirectional=True).cuda()
@@ -91,6 +92,7 @@ def test_gru_wgrad_accumulates_into_existing_grad(cuda_lib):
     ref = [p.grad.clone() for p in rnn.parameters()]
     for p in rnn.parameters():
         p.grad.zero_()
+    ops.set_grad_sink(True)                               # what optim.FlatSGD switches on
     gru_stack(x, rnn).sum().backward()                    # fused accumulation path
     for p, r in zip(rnn.parameters(), ref):
         assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-6)
@@ -110,3 +112,71 @@ def test_gru_minibatch_above_one_launch_is_chunked(cuda_lib):
     for (n, p64), (_, pc) in zip(rnn64.named_parameters(), rnn_c.named_parameters()):
         ref = p64.grad
         assert (pc.grad.double().cpu() - ref).abs().max().item() < 3e-2 * ref.abs().max().item() + 1e-4, n
+
+
+def test_gru_default_path_returns_gradients_to_autograd(cuda_lib):
+    """Without the FlatSGD opt-in the Function has no side effect on .grad: torch.autograd.grad
+    gets every weight gradient even when .grad buffers already exist, and leaves them untouched."""
+    from speech_b200.ops import gru_stack
+    torch.manual_seed(4)
+    rnn = torch.nn.GRU(32, 64, 2, batch_first=True, bidirectional=True).cuda()
+    x = torch.randn(5, 6, 32).cuda()
+    gru_stack(x, rnn).sum().backward()
+    want = [p.grad.clone() for p in rnn.parameters()]
+    for p in rnn.parameters():
+        p.grad.fill_(7.0)
+    got = torch.autograd.grad(gru_stack(x, rnn).sum(), list(rnn.parameters()))
+    for g, w, p in zip(got, want, rnn.parameters()):
+        assert g is not None and torch.allclose(g, w, rtol=1e-5, atol=1e-6)
+        assert torch.all(p.grad == 7.0)
+
+
+@pytest.mark.parametrize("B,T,In,H,L", [(6, 11, 40, 32, 3), (8, 9, 64, 128, 2)])
+def test_gru_inter_layer_dropout_matches_masked_reference(cuda_lib, B, T, In, H, L):
+    """nn.GRU(dropout=p) semantics in training: every layer output but the last is multiplied by
+    a keep mask / (1-p).  The masks are drawn with torch.rand on the device in layer order over
+    the kernels' time-major padded layout (row t*Bp + b), so re-seeding reproduces them for an
+    fp64 layer-by-layer reference; forward and all gradients must match (bf16 operand bars)."""
+    from speech_b200.ops import gru_stack
+    p = 0.3
+    torch.manual_seed(B + T)
+    rnn = torch.nn.GRU(In, H, L, batch_first=True, bidirectional=True, dropout=p).cuda()
+    x = torch.randn(B, T, In).cuda().requires_grad_(True)
+    torch.manual_seed(1234)
+    y = gru_stack(x, rnn, dropout=p)
+    assert y.dtype == torch.float32
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    got = {n: q.grad.double().cpu() for n, q in rnn.named_parameters()}
+    # ---- reference: one fp64 nn.GRU per layer, same masks ----
+    Bp = (B + 7) // 8 * 8
+    torch.manual_seed(1234)
+    masks = [(torch.rand(T * Bp, 2 * H, device="cuda") >= p).double().cpu() / (1.0 - p)
+             for _ in range(L - 1)]
+    h = x.detach().double().cpu().requires_grad_(True)
+    x64 = h
+    layers = []
+    for l in range(L):
+        g = torch.nn.GRU(In if l == 0 else 2 * H, H, 1, batch_first=True, bidirectional=True).double()
+        sd = {}
+        for k, v in rnn.state_dict().items():
+            if "_l%d" % l in k:
+                sd[k.replace("_l%d" % l, "_l0")] = v.double().cpu()
+        g.load_state_dict(sd)
+        layers.append(g)
+        h, _ = g(h)
+        if l + 1 < L:
+            mk = masks[l].view(T, Bp, 2 * H)[:, :B].transpose(0, 1)
+            h = h * mk
+    (h * w.double().cpu()).sum().backward()
+    assert (y.double().cpu() - h.detach()).abs().max().item() < 3e-2
+    assert (x.grad.double().cpu() - x64.grad).abs().max().item() < \
+        3e-2 * x64.grad.abs().max().item() + 1e-4
+    for l, g in enumerate(layers):
+        for k, q in g.named_parameters():
+            name = k.replace("_l0", "_l%d" % l)
+            ref = q.grad
+            assert (got[name] - ref).abs().max().item() < 3e-2 * ref.abs().max().item() + 1e-4, name
+    # dropout really happened, and eval (dropout=0) is deterministic and different
+    y0 = gru_stack(x.detach(), rnn, dropout=0.0)
+    assert not torch.allclose(y0, y.detach(), atol=1e-3)
