@@ -84,34 +84,31 @@ int sb_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, 
  *   gi     [T*Bp][ndir*3H] f32   X W_ih^T + b_ih (forward-direction gates first)
  *   whh    [ndir][3H][H]   bf16  recurrent weights;   bhh [ndir][3H] f32
  *   y      [T*Bp][ndir*H]  f32   h_t (out)
- *   xn     [T*Bp][ndir*H]  bf16  h_t (out; operand of the next projection)
- *   xnT    [ndir*H][(T+2)*Bp] bf16 h_t transposed, column (t+1)*Bp+b; columns of t=-1 and t=T
- *          must be zero on entry (out; may be NULL)
+ *   xn     [T*Bp][ndir*H]  bf16  h_t (out; operand of the next projection and of dW_hh)
  *   gates  [T*Bp][ndir][4][H] f32 saved r,z,n,(W_hn h + b_hn) for backward (out; may be NULL)
- *   barrier [ndir] u32 scratch for the per-direction grid barrier
+ *   workspace  >= sb_gru_fwd_workspace_size bytes, 1024-byte aligned: per-chunk ready counters
+ *          and the double-buffered exchange tiles of h_t (zeroed by the call itself)
  * Constraints: H % 16 == 0, Bp % 8 == 0, Bp <= 128, ndir*H/16 <= number of SMs.
  * ------------------------------------------------------------------------------------- */
+int sb_gru_fwd_workspace_size(int Bp, int H, int ndir, size_t* bytes);
 int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bhh, float* y, void* xn_bf16,
-               void* xnT_bf16, float* gates, unsigned int* barrier, int T, int Bp, int H, int ndir,
-               void* stream);
+               float* gates, void* workspace, size_t workspace_bytes, int T, int Bp, int H,
+               int ndir, void* stream);
 
 /* Backward through the recurrence.
  *   dy     [T*Bp][ndir*H] f32  gradient w.r.t. y
  *   whhT   [ndir][H][3H] bf16  W_hh transposed
- *   dgi    [T*Bp][ndir*3H] bf16 (out) gradient w.r.t. gi        -> dX = dgi * W_ih
- *   dgiT   [ndir*3H][T*Bp] bf16 (out) same, transposed          -> dW_ih, dW_hh (r,z rows)
- *   dghnT  [ndir][H][T*Bp] bf16 (out) r * dn_pre, transposed    -> dW_hh (n rows)
- *          (dgiT and dghnT may both be NULL: the weight gradients then contract the token-major
- *           dgi / dghn directly with SB_GEMM_A_MN | SB_GEMM_B_MN)
- *   dghn   [T*Bp][ndir*H] bf16 (out) r * dn_pre, token-major    -> dW_hh (n rows); may be NULL
- *          when dghnT is given
+ *   dgi    [T*Bp][ndir*3H] bf16 (out) gradient w.r.t. gi  -> dX = dgi * W_ih, dW_ih, dW_hh (r,z)
+ *   dghn   [T*Bp][ndir*H] bf16 (out) r * dn_pre            -> dW_hh (n rows)
+ *          (the weight gradients contract these token-major operands directly with
+ *           SB_GEMM_A_MN | SB_GEMM_B_MN; no transposed copies exist)
  *   dbih, dbhh [ndir*3H] f32 accumulated (+=)
+ *   workspace  >= sb_gru_bwd_workspace_size bytes, 1024-byte aligned (zeroed by the call itself)
  */
 int sb_gru_bwd_workspace_size(int Bp, int H, int ndir, size_t* bytes);
 int sb_gru_bwd(const float* dy, const float* y, const float* gates, const void* whhT_bf16,
-               void* dgi_bf16, void* dgiT_bf16, void* dghnT_bf16, void* dghn_bf16, float* dbih,
-               float* dbhh, void* workspace, size_t workspace_bytes, unsigned int* barrier, int T,
-               int Bp, int H, int ndir, void* stream);
+               void* dgi_bf16, void* dghn_bf16, float* dbih, float* dbhh, void* workspace,
+               size_t workspace_bytes, int T, int Bp, int H, int ndir, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * CTC prefix beam search, one CTA per utterance.

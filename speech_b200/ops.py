@@ -111,11 +111,6 @@ def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=N
     return out
 
 
-# Weight-gradient GEMMs contract the token-major activations directly (MN-major UMMA operands,
-# SB_GEMM_A_MN | SB_GEMM_B_MN): no transposed copies (xnT / dgiT / dghnT) are produced at all.
-# False restores the K-major path over transposed copies (developer knob, SB_WGRAD_MN=0).
-USE_MN = __import__("os").environ.get("SB_WGRAD_MN", "1") != "0"
-
 _grad_ready_hook = None
 _announce = True
 _grad_sink_enabled = False
@@ -171,12 +166,11 @@ def _grad_sink(param, rows=None):
     return g if rows is None else g[rows[0]:rows[1]]
 
 
-def _wgrad_split(M, N, K):
-    """split-K factor for the K = T*B weight-gradient contractions (few output tiles, long K)."""
-    tiles = ((M + 127) // 128) * ((N + 255) // 256)
-    kb = (K + 63) // 64
-    s = max(1, min(kb // 8, (2 * 148) // max(tiles, 1)))
-    return int(s)
+def _workspace(nbytes, dev):
+    """1024-byte aligned scratch for one recurrence launch (counters + exchange tiles)"""
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
 
 
 class GRUStackFunction(torch.autograd.Function):
@@ -212,7 +206,9 @@ class GRUStackFunction(torch.autograd.Function):
             X = torch.zeros(T, Bp, Inp, dtype=torch.bfloat16, device=dev)
             X[:, :B, :In] = x.transpose(0, 1)
             X = X.view(M, Inp)
-        barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.sb_gru_fwd_workspace_size(Bp, H, ndir, ctypes.byref(nbytes)), "ws")
+        ws = _workspace(nbytes.value, dev)
         saved = []
         y = None
         for l in range(L):
@@ -235,18 +231,14 @@ class GRUStackFunction(torch.autograd.Function):
             gi = gemm_bf16_tn(X, wih_cat, bias=bih_cat)
             y = torch.empty(M, D, dtype=torch.float32, device=dev)
             xn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
-            xnT = gates = None
+            gates = None
             if need_grad:
-                if not USE_MN:
-                    xnT = torch.empty(D, (T + 2) * Bp, dtype=torch.bfloat16, device=dev)
-                    xnT[:, :Bp].zero_()                     # h_{-1} = 0 (forward direction)
-                    xnT[:, (T + 1) * Bp:].zero_()           # h_{T}  = 0 (backward direction)
                 gates = torch.empty(M, ndir, 4, H, dtype=torch.float32, device=dev)
             sp = _lib.stream_ptr()
             _launch("gru_fwd", 2.0 * M * 3 * H * H * ndir,
                     lambda: lib.sb_gru_fwd(gi.data_ptr(), whh.data_ptr(), bhh.data_ptr(),
-                                           y.data_ptr(), xn.data_ptr(), _lib.ptr(xnT),
-                                           _lib.ptr(gates), barrier.data_ptr(), T, Bp, H, ndir, sp))
+                                           y.data_ptr(), xn.data_ptr(), _lib.ptr(gates),
+                                           ws.data_ptr(), nbytes.value, T, Bp, H, ndir, sp))
             mask = None
             hb = xn                                     # bf16 h_t (un-masked): dW_hh operand
             if dropout > 0.0 and l + 1 < L:
@@ -256,7 +248,7 @@ class GRUStackFunction(torch.autograd.Function):
                 # fp32 state and round once
                 xn = (y * mask).to(torch.bfloat16)
             if need_grad:
-                saved.append((X, y, gates, xnT, mask, wih_cat, whh, hb))
+                saved.append((X, y, gates, mask, wih_cat, whh, hb))
             X = xn
         ctx.saved = saved
         ctx.announce = _announce
@@ -301,13 +293,8 @@ class GRUStackFunction(torch.autograd.Function):
                 wT[d * H:(d + 1) * H, :V] = w.t()
             dY = gemm_bf16_tn(dl, wT)                                         # [M][D] f32
             dw2 = torch.zeros(Vp, D, dtype=torch.float32, device=dev)
-            if USE_MN:
-                gemm_bf16_tn(dl, Xtop, out=dw2, accumulate=True, split_k=_wgrad_split(Vp, D, M),
-                             a_mn=True, b_mn=True)
-            else:
-                top_xnT = ctx.saved[L - 1][3]
-                gemm_bf16_tn(dl.t().contiguous(), top_xnT[:, Bp:Bp + M], out=dw2, accumulate=True,
-                             split_k=_wgrad_split(Vp, D, M))
+            # dW (Vp x D) = dl^T Xtop, both operands read token-major (MN-major UMMA)
+            gemm_bf16_tn(dl, Xtop, out=dw2, accumulate=True, a_mn=True, b_mn=True)
             dfc_w = dw2[:V, :H] if ndir == 1 else dw2[:V, :H] + dw2[:V, H:]
             dfc_b = dout.sum((0, 1))
         elif B == Bp:
@@ -317,13 +304,12 @@ class GRUStackFunction(torch.autograd.Function):
             dY = torch.zeros(T, Bp, D, dtype=torch.float32, device=dev)
             dY[:, :B] = dout.transpose(0, 1)
             dY = dY.view(M, D)
-        barrier = torch.zeros(2, dtype=torch.int32, device=dev)
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.sb_gru_bwd_workspace_size(Bp, H, ndir, ctypes.byref(nbytes)), "ws")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        ws = _workspace(nbytes.value, dev)
         grads = [None] * len(weights)
         for l in reversed(range(L)):
-            X, y, gates, xnT, mask, wih_cat, whh, hb = ctx.saved[l]
+            X, y, gates, mask, wih_cat, whh, hb = ctx.saved[l]
             if mask is not None:
                 dY = dY * mask
             wl = weights[l * 4 * ndir:(l + 1) * 4 * ndir]
@@ -333,51 +319,42 @@ class GRUStackFunction(torch.autograd.Function):
             for d in range(ndir):
                 _transpose_bf16(whh[d], out=whhT[d])
             dgi = torch.empty(M, ndir * K3, dtype=torch.bfloat16, device=dev)
-            dgiT = dghnT = dghn = None
-            if USE_MN:
-                dghn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
-            else:
-                dgiT = torch.empty(ndir * K3, M, dtype=torch.bfloat16, device=dev)
-                dghnT = torch.empty(ndir, H, M, dtype=torch.bfloat16, device=dev)
+            dghn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
             dbih = torch.zeros(ndir * K3, dtype=torch.float32, device=dev)
             dbhh = torch.zeros(ndir * K3, dtype=torch.float32, device=dev)
             sp = _lib.stream_ptr()
             _launch("gru_bwd", 2.0 * M * 3 * H * H * ndir,
                     lambda dY=dY: lib.sb_gru_bwd(dY.data_ptr(), y.data_ptr(), gates.data_ptr(),
-                                                 whhT.data_ptr(), dgi.data_ptr(), _lib.ptr(dgiT),
-                                                 _lib.ptr(dghnT), _lib.ptr(dghn), dbih.data_ptr(),
-                                                 dbhh.data_ptr(), ws.data_ptr(), nbytes.value,
-                                                 barrier.data_ptr(), T, Bp, H, ndir, sp))
+                                                 whhT.data_ptr(), dgi.data_ptr(), dghn.data_ptr(),
+                                                 dbih.data_ptr(), dbhh.data_ptr(), ws.data_ptr(),
+                                                 nbytes.value, T, Bp, H, ndir, sp))
             base = l * 4 * ndir
-            if USE_MN:
-                # ---- weight gradients: contract the token-major operands over their rows ----
-                Ms = M - Bp                      # tokens that have a predecessor in the recurrence
-                for d in range(ndir):
-                    # dW_ih[d] (3H x In_l) = dgi[:, d]^T X
-                    sink = _grad_sink(wl[d * 4])
-                    dwih = sink if sink is not None else \
-                        torch.zeros(K3, In_l, dtype=torch.float32, device=dev)
-                    gemm_bf16_tn(dgi[:, d * K3:(d + 1) * K3], X[:, :In_l], out=dwih,
-                                 accumulate=True, a_mn=True, b_mn=True)
-                    # dW_hh[d] = [dgi_r | dgi_z | dghn]^T h_prev: h_prev of token (t, b) is token
-                    # (t-1, b) in the forward direction and (t+1, b) in the reverse one, so the
-                    # shift is a row offset of Bp on one of the two operands
-                    sink_hh = _grad_sink(wl[d * 4 + 1])
-                    dwhh = sink_hh if sink_hh is not None else \
-                        torch.zeros(K3, H, dtype=torch.float32, device=dev)
-                    if Ms > 0:
-                        ga, hp = (slice(Bp, M), slice(0, Ms)) if d == 0 else \
-                            (slice(0, Ms), slice(Bp, M))
-                        gemm_bf16_tn(dgi[ga, d * K3:d * K3 + 2 * H], hb[hp, d * H:(d + 1) * H],
-                                     out=dwhh[:2 * H], accumulate=True, a_mn=True, b_mn=True)
-                        gemm_bf16_tn(dghn[ga, d * H:(d + 1) * H], hb[hp, d * H:(d + 1) * H],
-                                     out=dwhh[2 * H:], accumulate=True, a_mn=True, b_mn=True)
-                    grads[base + d * 4 + 0] = None if sink is not None else dwih
-                    grads[base + d * 4 + 1] = None if sink_hh is not None else dwhh
-                    grads[base + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
-                    grads[base + d * 4 + 3] = dbhh[d * K3:(d + 1) * K3]
-            else:
-                _wgrad_kmajor(ctx, l, X, xnT, dgiT, dghnT, dbih, dbhh, wl, grads, dev)
+            # ---- weight gradients: contract the token-major operands over their rows ----
+            Ms = M - Bp                      # tokens that have a predecessor in the recurrence
+            for d in range(ndir):
+                # dW_ih[d] (3H x In_l) = dgi[:, d]^T X
+                sink = _grad_sink(wl[d * 4])
+                dwih = sink if sink is not None else \
+                    torch.zeros(K3, In_l, dtype=torch.float32, device=dev)
+                gemm_bf16_tn(dgi[:, d * K3:(d + 1) * K3], X[:, :In_l], out=dwih,
+                             accumulate=True, a_mn=True, b_mn=True)
+                # dW_hh[d] = [dgi_r | dgi_z | dghn]^T h_prev: h_prev of token (t, b) is token
+                # (t-1, b) in the forward direction and (t+1, b) in the reverse one, so the
+                # shift is a row offset of Bp on one of the two operands
+                sink_hh = _grad_sink(wl[d * 4 + 1])
+                dwhh = sink_hh if sink_hh is not None else \
+                    torch.zeros(K3, H, dtype=torch.float32, device=dev)
+                if Ms > 0:
+                    ga, hp = (slice(Bp, M), slice(0, Ms)) if d == 0 else \
+                        (slice(0, Ms), slice(Bp, M))
+                    gemm_bf16_tn(dgi[ga, d * K3:d * K3 + 2 * H], hb[hp, d * H:(d + 1) * H],
+                                 out=dwhh[:2 * H], accumulate=True, a_mn=True, b_mn=True)
+                    gemm_bf16_tn(dghn[ga, d * H:(d + 1) * H], hb[hp, d * H:(d + 1) * H],
+                                 out=dwhh[2 * H:], accumulate=True, a_mn=True, b_mn=True)
+                grads[base + d * 4 + 0] = None if sink is not None else dwih
+                grads[base + d * 4 + 1] = None if sink_hh is not None else dwhh
+                grads[base + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
+                grads[base + d * 4 + 3] = dbhh[d * K3:(d + 1) * K3]
             if _grad_ready_hook is not None and ctx.announce:
                 base = l * 4 * ndir
                 if all(grads[base + d * 4 + k] is None for d in range(ndir) for k in (0, 1)):
@@ -395,62 +372,13 @@ class GRUStackFunction(torch.autograd.Function):
                         _grad_ready_hook(list(wl))
             # ---- gradient w.r.t. the layer input ----
             if l > 0 or ctx.needs_input_grad[0]:
-                if USE_MN:
-                    dY = gemm_bf16_tn(dgi, wih_cat, b_mn=True)            # [M][Kl] f32
-                else:
-                    wihT = _transpose_bf16(wih_cat)                       # [Kl][ndir*3H]
-                    dY = gemm_bf16_tn(dgi, wihT)                          # [M][Kl] f32
+                # dX = dgi W_ih: W_ih (3H x In) is the [K][N] form of the B operand
+                dY = gemm_bf16_tn(dgi, wih_cat, b_mn=True)                # [M][Kl] f32
         dx = None
         if ctx.needs_input_grad[0]:
             dx = dY.view(T, Bp, -1)[:, :B, :In].transpose(0, 1).contiguous()
         ctx.saved = None
         return (dx, None, None, None, dfc_w, dfc_b) + tuple(grads)
-
-def _wgrad_kmajor(ctx, l, X, xnT, dgiT, dghnT, dbih, dbhh, wl, grads, dev):
-    """Weight gradients of layer l over TRANSPOSED copies (K-major operands): the path used before
-    the MN-major operand support; kept behind SB_WGRAD_MN=0 as a cross-check."""
-    B, T, In, Bp, H, ndir, L = ctx.dims
-    M = T * Bp
-    K3 = 3 * H
-    In_l = wl[0].shape[1]
-    if l > 0 and ctx.saved[l - 1][4] is None:
-        XT = ctx.saved[l - 1][3][:, Bp:Bp + M]                   # [In_l][M] view
-    else:
-        XT = X.t().contiguous()                                   # [Kl][M]
-    sinks_ih = [_grad_sink(wl[d * 4]) if XT.shape[0] == In_l else None for d in range(ndir)]
-    if all(g is not None for g in sinks_ih):
-        for d in range(ndir):
-            gemm_bf16_tn(dgiT[d * K3:(d + 1) * K3], XT, out=sinks_ih[d], accumulate=True,
-                         split_k=_wgrad_split(K3, In_l, M))
-        dwih = None
-    else:
-        sk = _wgrad_split(ndir * K3, XT.shape[0], M)
-        if sk == 1:
-            dwih = gemm_bf16_tn(dgiT, XT)
-        else:
-            dwih = torch.zeros(ndir * K3, XT.shape[0], dtype=torch.float32, device=dev)
-            gemm_bf16_tn(dgiT, XT, out=dwih, accumulate=True, split_k=sk)
-    for d in range(ndir):
-        hprevT = xnT[d * H:(d + 1) * H, (0 if d == 0 else 2 * Bp):][:, :M]
-        sk = _wgrad_split(2 * H, H, M)
-        sink = _grad_sink(wl[d * 4 + 1])
-        if sink is not None:
-            dwhh = sink
-            acc = True
-        elif sk == 1:
-            dwhh = torch.empty(K3, H, dtype=torch.float32, device=dev)
-            acc = False
-        else:
-            dwhh = torch.zeros(K3, H, dtype=torch.float32, device=dev)
-            acc = True
-        gemm_bf16_tn(dgiT[d * K3:d * K3 + 2 * H], hprevT, out=dwhh[:2 * H],
-                     accumulate=acc, split_k=sk)
-        gemm_bf16_tn(dghnT[d], hprevT, out=dwhh[2 * H:], accumulate=acc, split_k=sk)
-        grads[l * 4 * ndir + d * 4 + 0] = None if dwih is None else \
-            dwih[d * K3:(d + 1) * K3, :In_l]
-        grads[l * 4 * ndir + d * 4 + 1] = None if sink is not None else dwhh
-        grads[l * 4 * ndir + d * 4 + 2] = dbih[d * K3:(d + 1) * K3]
-        grads[l * 4 * ndir + d * 4 + 3] = dbhh[d * K3:(d + 1) * K3]
 
 
 def _gru_weights(rnn):
@@ -598,23 +526,13 @@ class ConvStackFunction(torch.autograd.Function):
                                                  db.data_ptr(), B, To, Fo, Co, sp))
             grads[2 * l + 1] = db
             # weight gradient: contraction over the M = B*To*Fo patch rows (split-K over all SMs)
-            if USE_MN:
-                # dWp^T [Kp][Co] = A^T dC with both operands read token-major (MN-major UMMA)
-                dWpT = torch.zeros(Kp, Co, dtype=torch.float32, device=dev)
-                gemm_bf16_tn(A, dC, out=dWpT, accumulate=True, a_mn=True, b_mn=True)
-                dWp = dWpT.t()
-            else:
-                dCT = _transpose_bf16(dC)
-                AT = _transpose_bf16(A)
-                dWp = torch.zeros(Co, Kp, dtype=torch.float32, device=dev)
-                gemm_bf16_tn(dCT, AT, out=dWp, accumulate=True, split_k=_wgrad_split(Co, Kp, M))
+            # dWp^T [Kp][Co] = A^T dC with both operands read token-major (MN-major UMMA)
+            dWpT = torch.zeros(Kp, Co, dtype=torch.float32, device=dev)
+            gemm_bf16_tn(A, dC, out=dWpT, accumulate=True, a_mn=True, b_mn=True)
+            dWp = dWpT.t()
             grads[2 * l] = dWp[:, :K].reshape(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
             if l > 0:
-                if USE_MN:
-                    dA = gemm_bf16_tn(dC, Wp, b_mn=True)        # [M][Kp] f32 patch gradient
-                else:
-                    WpT = Wp.t().contiguous()                   # [Kp][Co]
-                    dA = gemm_bf16_tn(dC, WpT)                  # [M][Kp] f32 patch gradient
+                dA = gemm_bf16_tn(dC, Wp, b_mn=True)            # [M][Kp] f32 patch gradient
                 Mp = B * Ti * Fi
                 dCp = torch.empty(Mp, Ci, dtype=torch.bfloat16, device=dev)
                 db = torch.zeros(Ci, dtype=torch.float32, device=dev)

@@ -230,27 +230,25 @@ def test_stage_inputs_routes_to_the_device_assembler_when_the_model_is_on_a_gpu(
     assert x.shape == (4, 77, 40) and y.dtype == torch.int32
 
 
-def test_conv_stack_uses_the_nn_modules_when_backward_is_not_covered():
-    """The TIMIT recipes' second conv layer [*, 5, 32, 1] needs a 5 x 32 tap gather in backward,
-    beyond the unrolled col2im kernel: with gradients enabled conv_stack must take the nn-module
-    route (runs anywhere, hence testable here); the shipped WSJ / north-star stack must not."""
+def test_conv_stack_has_no_library_fallback():
+    """Every stack the reference can express runs on the package's own kernels, training included
+    (the TIMIT recipes' second layer [*, 5, 32, 1] used to fall back to nn.Conv2d for backward):
+    on a CPU tensor conv_stack must therefore raise instead of silently taking an nn-module route,
+    and a stack the kernels do not cover (padding) must raise too."""
     from speech_b200 import _lib, ops
     from speech_b200.models import CTC
     timit = {"dropout": 0.0, "encoder": {"conv": [[8, 5, 32, 2], [8, 5, 32, 1]],
                                          "rnn": {"dim": 16, "bidirectional": True, "layers": 1}}}
     m = CTC(161, 10, timit)
     x = torch.randn(2, 40, 161)
-    y = ops.conv_stack(x, m.conv, True)                 # no CUDA needed: nn route
-    ref = m.conv(x.unsqueeze(1))
-    b, c, t, f = ref.shape
-    assert torch.equal(y, ref.transpose(1, 2).reshape(b, t, c * f))
-    y.sum().backward()
-    assert m.conv[0].weight.grad is not None and m.conv[2].weight.grad is not None
-    # the kernels' own route is chosen for the supported stack (and therefore demands CUDA) ...
+    with pytest.raises(_lib.SpeechB200Error):
+        ops.conv_stack(x, m.conv, True)
     wsj = CTC(80, 10, WSJ)
     with pytest.raises(_lib.SpeechB200Error):
         ops.conv_stack(torch.randn(2, 40, 80), wsj.conv, True)
-    # ... and for the TIMIT stack when no gradient is needed (inference)
     with torch.no_grad(), pytest.raises(_lib.SpeechB200Error):
         ops.conv_stack(x, m.conv, False)
-    assert ops._col2im_taps_ok(wsj.conv[0]) and not ops._col2im_taps_ok(m.conv[2])
+    padded = torch.nn.Sequential(torch.nn.Conv2d(1, 8, (5, 8), stride=(2, 2), padding=1),
+                                 torch.nn.ReLU())
+    with pytest.raises(_lib.SpeechB200Error):
+        ops.conv_stack(torch.randn(2, 40, 80), padded, False)

@@ -7,6 +7,9 @@ lib = _lib.load()
 if len(sys.argv) > 1:
     lib.sb_debug_gru_cluster(int(sys.argv[1]))
     print("cluster size preference:", sys.argv[1])
+if len(sys.argv) > 3:
+    lib.sb_debug_gru_flags(int(sys.argv[3]))      # 32: version-1 forward kernel
+    print("flags:", sys.argv[3])
 torch.manual_seed(0)
 B, T, In, H = 64, 64, 2048, 1024
 rnn = torch.nn.GRU(In, H, 1, batch_first=True, bidirectional=True).cuda()
@@ -33,8 +36,9 @@ else:
     lib.sb_debug_gru_timeline(None)
 print("mode:", MODE)
 d = dbg.cpu().numpy().reshape(64, 16)
-names = ["P:grid_wait done", "P:tma issued", "M:all mma committed", "E:accfull", "E:tmem loaded",
-         "E:xn stored", "E:proxy fence", "E:epi barrier", None, "E:arrived", "E:offpath done"]
+names = ["P:chunk 0 ready seen", "P:last chunk copy issued", "M:all mma committed", "E:accfull",
+         "E:tmem loaded", "E:exchange stored", "E:proxy fence", "E:before arrive", None,
+         "E:arrived", "E:offpath done"]
 for step in (11, 40):
     base = d[step - 1][9]   # previous step's arrival by this CTA
     print("step %d (ns since this CTA's previous arrive):" % step)
