@@ -203,6 +203,59 @@ int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
                     int T, int U1, int V, int blank, float* costs, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* Compact-lattice form of the same loss: `lat` / `garc` are (T, B, U1, 2), TIME-major nodes
+ * n = (t*B + b)*U1 + u, = {log p(blank), log p(label of arc u -> u+1)} per node (what
+ * sb_rnnt_joint_fwd writes) and the gradients w.r.t. them. */
+int sb_rnnt_fwd_bwd_compact(const float* lat, float* garc, const int* labels,
+                            const int* label_offsets, const int* label_lens, const int* act_lens,
+                            int B, int T, int U1, int blank, float* costs, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused RNN-T joint network: relu(fx[b,t,:] + fy[b,u,:]) -> fc2 -> log-softmax per lattice node,
+ * the (B, T', U+1, H) intermediate never exists (it lives as 16 KB operand tiles in shared memory).
+ * Replaces: the broadcast add + ReLU + LinearND + log_softmax of Transducer.decode,
+ *           speech/models/transducer_model.py:71-76 (fc1 shared by both streams, :73).
+ *   fx [B*T][H] f32 = fc1(encoder states), fy [B*U1][H] f32 = fc1(prediction network) (biases in)
+ *   w2 [V1][H] bf16, b2 [V1] f32: fc2;  ymat [B][U1-1] int32 end-padded labels
+ *   node order of lat / garc / dlogits: TIME-major, n = (t*B + b)*U1 + u (frames t0..t0+Tc-1
+ *   are one contiguous slab of rows)
+ *   sb_rnnt_joint_fwd:      lat [nodes][2] (out), lp_full (B, T, U1, V1) batch-first (out, may be
+ *                           NULL: only `infer` needs every class)
+ *   sb_rnnt_joint_dlogits:  backward recompute pass: garc [nodes][2] (gradient w.r.t. lat) ->
+ *                           dlogits [nodes][NV] bf16 (NV = 32 if V1 <= 32 else 64), db2 [V1] +=
+ *   sb_rnnt_joint_build_slab / _reduce_slab: the hidden activations of Tc <= 8 frames
+ *                           (z [B*Tc*U1][H] bf16) for the weight-gradient GEMMs, and the masked
+ *                           reduction of dz [B*Tc*U1][H] f32 into dfx (=) and dfy (+=)
+ * Constraints: H % 8 == 0, V1 <= 64.
+ * ------------------------------------------------------------------------------------- */
+int sb_rnnt_joint_fwd(const float* fx, const float* fy, const void* w2_bf16, const float* b2,
+                      const int* ymat, float* lat, float* lp_full, int B, int T, int U1, int H,
+                      int V1, int blank, void* stream);
+int sb_rnnt_joint_dlogits(const float* fx, const float* fy, const void* w2_bf16, const float* b2,
+                          const int* ymat, const float* garc, void* dlogits_bf16, float* db2, int B,
+                          int T, int U1, int H, int V1, int blank, void* stream);
+int sb_rnnt_joint_build_slab(const float* fx, const float* fy, void* z_bf16, int B, int T, int U1,
+                             int H, int t0, int Tc, void* stream);
+int sb_rnnt_joint_reduce_slab(const float* dz, const void* z_bf16, float* dfx, float* dfy, int B,
+                              int T, int U1, int H, int t0, int Tc, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Transducer beam search over a precomputed (teacher-forced) lattice, one CTA per utterance.
+ * Replaces: transducer.decoders.decode_static(lp, beam_size, blank) of the un-vendored
+ *           awni/transducer, called per utterance on a host array at
+ *           speech/models/transducer_model.py:92-101.
+ *   lp       (B, T, U1, V) f32 log-probabilities (device)
+ *   tlens    (B) frames searched per utterance, ulens (B) lattice rows (labels + 1)
+ *   out_labels (B, U1) int32, out_lens (B), out_scores (B) f64 log-probability of the best
+ *   workspace >= sb_rnnt_decode_static_workspace_size bytes;  beam_size <= 32
+ * ------------------------------------------------------------------------------------- */
+int sb_rnnt_decode_static_workspace_size(int B, int T, int U1, int beam_size, size_t* bytes);
+int sb_rnnt_decode_static(const float* lp, const int* tlens, const int* ulens, int B, int T, int U1,
+                          int V, int beam_size, int blank, int* out_labels, int* out_lens,
+                          double* out_scores, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Scoring, HOST function: Levenshtein distance of two int32 token
  * sequences; replaces `editdistance.eval` in speech/utils/score.py:15-16.  Returns -1 on invalid

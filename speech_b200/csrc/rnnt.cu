@@ -38,6 +38,8 @@ struct RnntParams {
   float* costs;           // (B)
   double* ws;             // (B, 2, T, U1) alpha, beta
   int B, T, U1, V, blank;
+  int compact;            // lp / grads are (T, B, U1, 2), TIME-major nodes (t*B + b)*U1 + u:
+                          // {blank, label of arc u -> u+1}
 };
 
 SB_DEVINL double lse2dd(double a, double b) {
@@ -59,7 +61,8 @@ __global__ void __launch_bounds__(2 * RNNT_SIDE, 1) rnnt_fwd_bwd_kernel(const Rn
   const int U = min(p.label_lens[b], p.U1 - 1);      // labels of this utterance
   const int U1 = p.U1, V = p.V;
   const int* lab = p.labels + p.label_off[b];
-  const float* lp = p.lp + (size_t)b * p.T * U1 * V;
+  const float* lp = p.compact ? p.lp + (size_t)b * U1 * 2 : p.lp + (size_t)b * p.T * U1 * V;
+  const size_t tstr = p.compact ? (size_t)p.B * U1 : (size_t)U1;   // nodes between two frames
   double* alpha = p.ws + (size_t)b * 2 * p.T * U1;
   double* beta = alpha + (size_t)p.T * U1;
 
@@ -77,7 +80,11 @@ __global__ void __launch_bounds__(2 * RNNT_SIDE, 1) rnnt_fwd_bwd_kernel(const Rn
     const int u = i + RNNT_SIDE * q;
     ylab[q] = (u < U) ? lab[u] : p.blank;
   }
-  auto LP = [&](int t, int u, int k) -> double { return (double)__ldg(lp + ((size_t)t * U1 + u) * V + k); };
+  // (in the compact form the only label ever asked for at node u is the one of arc u -> u+1)
+  auto LP = [&](int t, int u, int k) -> double {
+    const size_t node = (size_t)t * tstr + u;
+    return (double)__ldg(p.compact ? lp + node * 2 + (k == p.blank ? 0 : 1) : lp + node * V + k);
+  };
 
   double own[NS];   // this thread's previous cell in column u
 #pragma unroll
@@ -130,18 +137,21 @@ __global__ void __launch_bounds__(2 * RNNT_SIDE, 1) rnnt_fwd_bwd_kernel(const Rn
   __syncthreads();
   const double logp = s_logp;
   if (p.grads == nullptr || logp == -INFINITY) return;
-  float* g = p.grads + (size_t)b * p.T * U1 * V;
+  const int gstride = p.compact ? 2 : V;
+  float* g = p.compact ? p.grads + (size_t)b * U1 * 2 : p.grads + (size_t)b * p.T * U1 * V;
   for (int c = tid; c < T * (U + 1); c += 2 * RNNT_SIDE) {
     const int t = c / (U + 1), u = c % (U + 1);
     const double a = alpha[(size_t)t * U1 + u];
     if (a == -INFINITY) continue;
-    const size_t base = ((size_t)t * U1 + u) * V;
+    const size_t base = ((size_t)t * tstr + u) * gstride;
     // blank transition
     double nxt = (t < T - 1) ? beta[(size_t)(t + 1) * U1 + u] : ((u == U) ? 0.0 : -INFINITY);
-    if (nxt != -INFINITY) g[base + p.blank] = -(float)exp(a + LP(t, u, p.blank) + nxt - logp);
+    if (nxt != -INFINITY)
+      g[base + (p.compact ? 0 : p.blank)] = -(float)exp(a + LP(t, u, p.blank) + nxt - logp);
     if (u < U) {
       const double bn = beta[(size_t)t * U1 + u + 1];
-      if (bn != -INFINITY) g[base + lab[u]] = -(float)exp(a + LP(t, u, lab[u]) + bn - logp);
+      if (bn != -INFINITY)
+        g[base + (p.compact ? 1 : lab[u])] = -(float)exp(a + LP(t, u, lab[u]) + bn - logp);
     }
   }
 }
@@ -156,11 +166,10 @@ extern "C" int sb_rnnt_workspace_size(int B, int T, int U1, size_t* bytes) {
   return SB_OK;
 }
 
-extern "C" int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
-                               const int* label_offsets, const int* label_lens,
-                               const int* act_lens, int B, int T, int U1, int V, int blank,
-                               float* costs, void* workspace, size_t workspace_bytes,
-                               void* stream_) {
+static int rnnt_run(const float* log_probs, float* grads, const int* labels,
+                    const int* label_offsets, const int* label_lens, const int* act_lens, int B,
+                    int T, int U1, int V, int blank, int compact, float* costs, void* workspace,
+                    size_t workspace_bytes, void* stream_) {
   if (!log_probs || !labels || !label_offsets || !label_lens || !act_lens || !costs || !workspace)
     return SB_ERR_INVALID;
   if (B <= 0 || T <= 0 || U1 <= 0 || V <= 0 || blank < 0 || blank >= V) return SB_ERR_INVALID;
@@ -172,9 +181,9 @@ extern "C" int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* 
   p.lp = log_probs; p.grads = grads; p.labels = labels; p.label_off = label_offsets;
   p.label_lens = label_lens; p.act_lens = act_lens; p.costs = costs;
   p.ws = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  p.B = B; p.T = T; p.U1 = U1; p.V = V; p.blank = blank;
-  if (grads &&
-      cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)B * T * U1 * V, stream) != cudaSuccess)
+  p.B = B; p.T = T; p.U1 = U1; p.V = V; p.blank = blank; p.compact = compact;
+  if (grads && cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)B * T * U1 * (compact ? 2 : V),
+                               stream) != cudaSuccess)
     return SB_ERR_CUDA;
   const int ns = (U1 + RNNT_SIDE - 1) / RNNT_SIDE;
   if (ns <= 1) rnnt_fwd_bwd_kernel<1><<<B, 2 * RNNT_SIDE, 0, stream>>>(p);
@@ -182,4 +191,24 @@ extern "C" int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* 
   else if (ns <= 4) rnnt_fwd_bwd_kernel<4><<<B, 2 * RNNT_SIDE, 0, stream>>>(p);
   else return SB_ERR_UNSUPPORTED;
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+extern "C" int sb_rnnt_fwd_bwd(const float* log_probs, float* grads, const int* labels,
+                               const int* label_offsets, const int* label_lens,
+                               const int* act_lens, int B, int T, int U1, int V, int blank,
+                               float* costs, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+  return rnnt_run(log_probs, grads, labels, label_offsets, label_lens, act_lens, B, T, U1, V,
+                  blank, 0, costs, workspace, workspace_bytes, stream_);
+}
+
+// Compact lattice (what sb_rnnt_joint_fwd writes): lat / garc are (T, B, U1, 2), time-major, =
+// {log p(blank), log p(label of arc u -> u+1)} per node and the gradients w.r.t. them.
+extern "C" int sb_rnnt_fwd_bwd_compact(const float* lat, float* garc, const int* labels,
+                                       const int* label_offsets, const int* label_lens,
+                                       const int* act_lens, int B, int T, int U1, int blank,
+                                       float* costs, void* workspace, size_t workspace_bytes,
+                                       void* stream_) {
+  return rnnt_run(lat, garc, labels, label_offsets, label_lens, act_lens, B, T, U1, blank + 1,
+                  blank, 1, costs, workspace, workspace_bytes, stream_);
 }

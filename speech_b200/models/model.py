@@ -117,6 +117,11 @@ class LinearND(nn.Module):
         self.fc = nn.Linear(*args)
 
     def forward(self, x):
+        # time-batched projections run on the package's tcgen05 GEMM (forward and backward);
+        # per-token rows of the attention decoder (a handful of rows) stay in fp32
+        _lib.require_cuda(x, "LinearND input")
+        if x.numel() // x.shape[-1] >= 128:
+            return ops.linear(x, self.fc.weight, self.fc.bias)
         lead = x.shape[:-1]
         out = self.fc(x.reshape(-1, x.shape[-1]))
         return out.view(*lead, out.shape[-1])

@@ -111,6 +111,57 @@ def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=N
     return out
 
 
+class LinearFunction(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM (bf16 operands, fp32 accumulate), forward and backward:
+    the arithmetic behind the reference's LinearND / nn.Linear (model.py:115-133).
+    x (N, K) f32, W (O, K), b (O) -> (N, O) f32."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _lib.require_cuda(x, "x")
+        N, K = x.shape
+        Kp = _round_up(K, 8)
+        xb = x.detach().to(torch.bfloat16)
+        wb = w.detach().to(torch.bfloat16)
+        if Kp != K:
+            xb = torch.nn.functional.pad(xb, (0, Kp - K))
+            wb = torch.nn.functional.pad(wb, (0, Kp - K))
+        xb, wb = xb.contiguous(), wb.contiguous()
+        ctx.save_for_backward(xb, wb)
+        ctx.K = K
+        ctx.has_bias = b is not None
+        return gemm_bf16_tn(xb, wb, bias=None if b is None else b.detach().float().contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb = ctx.saved_tensors
+        K = ctx.K
+        O = wb.shape[0]
+        Op = _round_up(O, 8)
+        dyb = dy.detach().to(torch.bfloat16)
+        if Op != O:
+            dyb = torch.nn.functional.pad(dyb, (0, Op - O))
+            wb = torch.nn.functional.pad(wb, (0, 0, 0, Op - O))
+        dyb, wb = dyb.contiguous(), wb.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_bf16_tn(dyb, wb, b_mn=True)[:, :K]          # dY W: W is the [K][N] form
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(Op, xb.shape[1], dtype=torch.float32, device=dy.device)
+            gemm_bf16_tn(dyb, xb, out=dw, accumulate=True, a_mn=True, b_mn=True)   # dY^T X
+            dw = dw[:O, :K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db
+
+
+def linear(x, w, b=None):
+    """nn.Linear semantics over the last dimension of an N-D CUDA tensor, on the tcgen05 GEMM."""
+    lead = x.shape[:-1]
+    out = LinearFunction.apply(x.reshape(-1, x.shape[-1]).float(), w, b)
+    return out.view(*lead, out.shape[-1])
+
+
 _grad_ready_hook = None
 _announce = True
 _grad_sink_enabled = False

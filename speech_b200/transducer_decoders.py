@@ -1,54 +1,60 @@
 """Drop-in for `transducer.decoders` of awni/transducer (imported at
 speech/models/transducer_model.py:10, used at :100 as `td.decode_static(lp, beam_size, blank)[0]`).
 
-The dependency is un-vendored (Makefile:10-12) so its exact algorithm and tie-breaks are
-UNVERIFIABLE; this is the standard transducer beam search (Graves 2012, §3)
-restricted to a STATIC lattice: because `lp[t, u, :]` was computed with teacher forcing, the
-prediction-network state of a hypothesis is simply the number of labels it has emitted, so
-hypotheses are (label prefix, log-probability) pairs advancing through (t, u).
-Returns (labels, log_probability) so that `[0]` is the label list, as the call site expects.
-
-Beam bookkeeping is host-side (a handful of scalars per frame); the lattice stays on the device
-and each frame's (U x V) slice is read back once.
+The beam search runs on the GPU (csrc/tdecode.cu, one CTA per utterance; hypotheses in a canonical
+trie, float64 scores); `decode_static` keeps the reference's per-utterance call signature and
+returns (labels, log_probability) so that `[0]` is the label list, `decode_static_batch` searches
+a whole minibatch of lattices with one launch and one device->host copy (what
+`Transducer.infer` uses).  The dependency is un-vendored (Makefile:10-12), so the algorithm is the
+standard transducer beam search on a static lattice; its CPU restatement and how it is pinned are
+in oracle/decode_static_ref.py (test infrastructure - not imported here).  There is no CPU path.
 """
-import math
+import ctypes
 
 import torch
 
+from . import _lib
 
-def decode_static(lp, beam_size, blank=0, max_symbols_per_frame=None):
+
+def decode_static_batch(lp, tlens, ulens, beam_size, blank):
+    """lp (B, T, U1, V) float32 CUDA log-probabilities; tlens / ulens: frames and lattice rows
+    (labels + 1) of every utterance.  Returns (list of label lists, list of log-probabilities)."""
+    from . import ops
+    _lib.require_cuda(lp, "lp")
+    lib = _lib.load()
+    lp = lp.detach().float().contiguous()
+    B, T, U1, V = lp.shape
+    dev = lp.device
+    lens = torch.tensor([min(int(t), T) for t in tlens] + [min(int(u), U1) for u in ulens],
+                        dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.sb_rnnt_decode_static_workspace_size(B, T, U1, int(beam_size),
+                                                        ctypes.byref(nbytes)), "ws")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    labels = torch.empty(B, U1, dtype=torch.int32, device=dev)
+    olens = torch.empty(B, dtype=torch.int32, device=dev)
+    scores = torch.empty(B, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        sp = _lib.stream_ptr()
+        ops._launch("rnnt_decode_static", 0.0,
+                    lambda: lib.sb_rnnt_decode_static(lp.data_ptr(), lens[:B].data_ptr(),
+                                                      lens[B:].data_ptr(), B, T, U1, V,
+                                                      int(beam_size), int(blank),
+                                                      labels.data_ptr(), olens.data_ptr(),
+                                                      scores.data_ptr(), ws.data_ptr(),
+                                                      nbytes.value, sp))
+    lab = labels.cpu()
+    n = olens.cpu().tolist()
+    sc = scores.cpu().tolist()
+    return [lab[b, :n[b]].tolist() for b in range(B)], sc
+
+
+def decode_static(lp, beam_size, blank=0):
+    """One utterance: lp (T, U, V) log-probabilities (numpy array or tensor; copied to the GPU if
+    it is not there already) -> (labels, log_probability)."""
     lp = torch.as_tensor(lp)
+    if not lp.is_cuda:
+        lp = lp.cuda()
     T, U, V = lp.shape
-    lat = lp.detach().float().cpu().numpy()
-    beam = {(): 0.0}
-    for t in range(T):
-        done = {}
-        frontier = dict(beam)
-        # expand within the frame until every surviving hypothesis has emitted its blank
-        for _ in range(U if max_symbols_per_frame is None else max_symbols_per_frame + 1):
-            nxt = {}
-            for hyp, score in frontier.items():
-                u = len(hyp)
-                if u >= U:
-                    continue
-                row = lat[t, u]
-                b = score + float(row[blank])
-                done[hyp] = _lse(done[hyp], b) if hyp in done else b
-                if u + 1 < U:
-                    for k in range(V):
-                        if k == blank:
-                            continue
-                        h2 = hyp + (k,)
-                        s2 = score + float(row[k])
-                        nxt[h2] = _lse(nxt[h2], s2) if h2 in nxt else s2
-            if not nxt:
-                break
-            frontier = dict(sorted(nxt.items(), key=lambda kv: -kv[1])[:beam_size])
-        beam = dict(sorted(done.items(), key=lambda kv: -kv[1])[:beam_size])
-    best = max(beam.items(), key=lambda kv: kv[1])
-    return list(best[0]), best[1]
-
-
-def _lse(a, b):
-    m = max(a, b)
-    return m + math.log(math.exp(a - m) + math.exp(b - m))
+    labels, scores = decode_static_batch(lp.unsqueeze(0), [T], [U], beam_size, blank)
+    return labels[0], scores[0]
