@@ -97,7 +97,8 @@ int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bhh, float* y
 
 /* Backward through the recurrence.
  *   dy     [T*Bp][ndir*H] f32  gradient w.r.t. y
- *   whhT   [ndir][H][3H] bf16  W_hh transposed
+ *   whh    [ndir][3H][H] bf16  recurrent weights as stored (the same operand sb_gru_fwd takes;
+ *          the kernel transposes its slice while staging it into shared memory)
  *   dgi    [T*Bp][ndir*3H] bf16 (out) gradient w.r.t. gi  -> dX = dgi * W_ih, dW_ih, dW_hh (r,z)
  *   dghn   [T*Bp][ndir*H] bf16 (out) r * dn_pre            -> dW_hh (n rows)
  *          (the weight gradients contract these token-major operands directly with
@@ -106,7 +107,7 @@ int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bhh, float* y
  *   workspace  >= sb_gru_bwd_workspace_size bytes, 1024-byte aligned (zeroed by the call itself)
  */
 int sb_gru_bwd_workspace_size(int Bp, int H, int ndir, size_t* bytes);
-int sb_gru_bwd(const float* dy, const float* y, const float* gates, const void* whhT_bf16,
+int sb_gru_bwd(const float* dy, const float* y, const float* gates, const void* whh_bf16,
                void* dgi_bf16, void* dghn_bf16, float* dbih, float* dbhh, void* workspace,
                size_t workspace_bytes, int T, int Bp, int H, int ndir, void* stream);
 
@@ -162,11 +163,14 @@ int sb_transpose_bf16(const void* src, void* dst, long long R, int C, long long 
  *           (train.py:32-35, 95-97).
  *   sb_sumsq          out[0] = sum(g^2)                       (one pass over the gradient)
  *   sb_sgd_clip_step  c = min(1, max_norm/(sqrt(sumsq)+1e-6)); [m = momentum*m + c*g]; p -= lr*(m|c*g)
- *                     the clip coefficient is read from device memory (no host sync)
+ *                     the clip coefficient is read from device memory (no host sync);
+ *                     params_bf16 (may be NULL): bf16 copy of the updated parameters, the
+ *                     tensor-core operands of the next step (no per-step cast kernels)
  * ------------------------------------------------------------------------------------- */
 int sb_sumsq(const float* g, long long n, float* out, void* stream);
-int sb_sgd_clip_step(float* params, const float* grads, float* momentum_buf, long long n,
-                     const float* sumsq, float lr, float momentum, float max_norm, void* stream);
+int sb_sgd_clip_step(float* params, const float* grads, float* momentum_buf, void* params_bf16,
+                     long long n, const float* sumsq, float lr, float momentum, float max_norm,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * One decoder step of the additive location-aware attention (forward only, decode path).

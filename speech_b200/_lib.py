@@ -36,7 +36,7 @@ SIGNATURES = {
                                      _c_int, _c_int, _c_int, _c_int, _vp]),
     "sb_transpose_bf16": (_c_int, [_vp, _vp, _c_ll, _c_int, _c_ll, _c_ll, _vp]),
     "sb_sumsq": (_c_int, [_vp, _c_ll, _vp, _vp]),
-    "sb_sgd_clip_step": (_c_int, [_vp, _vp, _vp, _c_ll, _vp, _fl, _fl, _fl, _vp]),
+    "sb_sgd_clip_step": (_c_int, [_vp, _vp, _vp, _vp, _c_ll, _vp, _fl, _fl, _fl, _vp]),
     "sb_attn_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _fl, _c_int, _c_int, _c_int, _c_int,
                               _c_int, _vp, _vp, _vp]),
     "sb_beam_topk": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp]),

@@ -4,7 +4,10 @@
 //   sb_sumsq        : sum of squares of the flat gradient (grid-stride, float4 loads, one atomic
 //                     per CTA) -> the global L2 norm used by the clip
 //   sb_sgd_clip_step: p -= lr * min(1, max_norm / (norm + 1e-6)) * g   (momentum buffer optional),
-//                     the clip coefficient is read from device memory: no host sync in the step
+//                     the clip coefficient is read from device memory: no host sync in the step;
+//                     optionally also writes the bf16 copy of the updated parameters that the
+//                     next step's tensor-core GEMMs / recurrence kernels take as operands, so no
+//                     per-step cast kernels are needed
 // Roofline: HBM (read g once for the norm; read p,g + write p for the update = 16 B/param total).
 #include "common.cuh"
 
@@ -37,8 +40,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 __global__ void __launch_bounds__(256)
 sgd_clip_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom,
-                     long long n, const float* __restrict__ sumsq, float lr, float momentum,
-                     float max_norm) {
+                     __nv_bfloat16* __restrict__ p16, long long n, const float* __restrict__ sumsq,
+                     float lr, float momentum, float max_norm) {
   const float norm = sqrtf(*sumsq);
   const float coef = fminf(1.0f, max_norm / (norm + 1e-6f));   // torch.nn.utils.clip_grad_norm_
   const float scale = coef;
@@ -59,12 +62,15 @@ sgd_clip_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* 
     }
     pv.x -= lr * gv.x; pv.y -= lr * gv.y; pv.z -= lr * gv.z; pv.w -= lr * gv.w;
     p4[i] = pv;
+    if (p16)
+      reinterpret_cast<uint2*>(p16)[i] = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
   }
   for (long long i = (n4 << 2) + blockIdx.x * 256LL + threadIdx.x; i < n;
        i += (long long)gridDim.x * 256) {
     float gv = g[i] * scale;
     if (mom) { mom[i] = momentum * mom[i] + gv; gv = mom[i]; }
     p[i] -= lr * gv;
+    if (p16) p16[i] = __float2bfloat16_rn(p[i]);
   }
 }
 
@@ -82,13 +88,15 @@ extern "C" int sb_sumsq(const float* g, long long n, float* out, void* stream_) 
 }
 
 extern "C" int sb_sgd_clip_step(float* params, const float* grads, float* momentum_buf,
-                                long long n, const float* sumsq, float lr, float momentum,
-                                float max_norm, void* stream_) {
+                                void* params_bf16, long long n, const float* sumsq, float lr,
+                                float momentum, float max_norm, void* stream_) {
   if (!params || !grads || !sumsq || n <= 0) return SB_ERR_INVALID;
   if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)momentum_buf) & 15) return SB_ERR_INVALID;
+  if ((uintptr_t)params_bf16 & 7) return SB_ERR_INVALID;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int grid = device_sm_count() * 4;
-  sgd_clip_step_kernel<<<grid, 256, 0, stream>>>(params, grads, momentum_buf, n, sumsq, lr,
-                                                 momentum, max_norm);
+  sgd_clip_step_kernel<<<grid, 256, 0, stream>>>(params, grads, momentum_buf,
+                                                 reinterpret_cast<__nv_bfloat16*>(params_bf16), n,
+                                                 sumsq, lr, momentum, max_norm);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }

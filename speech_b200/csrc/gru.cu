@@ -62,7 +62,7 @@ struct GruBwdParams {
   const float* dy;     // [T*Bp][ndir*H]   gradient w.r.t. this layer's output
   const float* y;      // [T*Bp][ndir*H]   forward h_t (fp32)
   const float* gates;  // [T*Bp][ndir][4][H]
-  const bf16* whhT;    // [ndir][H][3H]    W_hh^T, bf16
+  const bf16* whh;     // [ndir][3H][H]    W_hh as stored, bf16 (transposed while staging)
   bf16* dgi;           // [T*Bp][ndir*3H]  d(pre-activation) of the input projection, bf16
   bf16* dghn;          // [T*Bp][ndir*H]   dn_pre * r, token-major (wgrad of W_hn)
   bf16* xchg;          // plain kernel: [ndir][2][Bp][3H] per-step exchange of dgh_t;
@@ -775,16 +775,18 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
     reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   {
-    // resident operand: rows = the 16 hidden units k0..k0+15 of W_hh^T, K = 3H
-    const int pieces_per_row = nchunks * 8;
-    for (int k = tid; k < 16 * pieces_per_row; k += GRU_THREADS) {
-      const int r = k / pieces_per_row, pc = k % pieces_per_row;
-      const int col = pc * 8;
-      if (col < K3) {
-        const uint4 v =
-            *reinterpret_cast<const uint4*>(p.whhT + ((long long)dir * H + j0 + r) * K3 + col);
-        *reinterpret_cast<uint4*>(s.wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
-      }
+    // resident operand: rows = the 16 hidden units j0..j0+15 of W_hh^T, K = 3H.  W_hh is read as
+    // stored ([3H][H]: 32 contiguous bytes per k) and transposed on the way into shared memory
+    for (int k = tid; k < K3 * 2; k += GRU_THREADS) {
+      const int kk = k >> 1, half = k & 1;
+      const uint4 v = *reinterpret_cast<const uint4*>(
+          p.whh + ((long long)dir * K3 + kk) * H + j0 + half * 8);
+      const unsigned short* e = reinterpret_cast<const unsigned short*>(&v);
+      uint8_t* chunk = s.wtile + (kk >> 6) * WCHUNK + (kk & 7) * 2;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<unsigned short*>(
+            chunk + sw128_offset((uint32_t)(half * 8 + q), (uint32_t)((kk & 63) >> 3))) = e[q];
     }
   }
   if (tid == 0) {
@@ -1034,13 +1036,19 @@ gru_bwd_ks_kernel(const GruBwdParams p) {
     reinterpret_cast<uint4*>(base)[k] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   {
-    // resident operand: rows = the cluster's 64 units of W_hh^T, columns = this CTA's K quarter
-    const int pieces_per_row = nchunks * 8;
-    for (int k = tid; k < 64 * pieces_per_row; k += GRU_THREADS) {
-      const int r = k / pieces_per_row, pc = k % pieces_per_row;
+    // resident operand: rows = the cluster's 64 units of W_hh^T, columns = this CTA's K quarter.
+    // W_hh is read as stored ([3H][H]: the cluster's 64 units are 128 contiguous bytes of row k)
+    // and transposed on the way into shared memory (once per launch)
+    for (int k = tid; k < KQ * 8; k += GRU_THREADS) {
+      const int kl = k >> 3, piece = k & 7;       // local k, 8-unit piece of the 64 units
       const uint4 v = *reinterpret_cast<const uint4*>(
-          p.whhT + ((long long)dir * H + k0c + r) * K3 + (long long)crank * KQ + pc * 8);
-      *reinterpret_cast<uint4*>(wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+          p.whh + ((long long)dir * K3 + (long long)crank * KQ + kl) * H + k0c + piece * 8);
+      const unsigned short* e = reinterpret_cast<const unsigned short*>(&v);
+      uint8_t* chunk = wtile + (kl >> 6) * WCHUNK + (kl & 7) * 2;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<unsigned short*>(
+            chunk + sw128_offset((uint32_t)(piece * 8 + q), (uint32_t)((kl & 63) >> 3))) = e[q];
     }
   }
   if (tid == 0) {
@@ -1486,12 +1494,12 @@ extern "C" int sb_gru_bwd_workspace_size(int Bp, int H, int ndir, size_t* bytes)
 }
 
 extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
-                          const void* whhT_bf16, void* dgi_bf16, void* dghn_bf16, float* dbih,
+                          const void* whh_bf16, void* dgi_bf16, void* dghn_bf16, float* dbih,
                           float* dbhh, void* workspace, size_t workspace_bytes, int T, int Bp,
                           int H, int ndir, void* stream_) {
   int rc = gru_check(T, Bp, H, ndir);
   if (rc != SB_OK) return rc;
-  if (!dy || !y || !gates || !whhT_bf16 || !dgi_bf16 || !dghn_bf16 || !dbih || !dbhh ||
+  if (!dy || !y || !gates || !whh_bf16 || !dgi_bf16 || !dghn_bf16 || !dbih || !dbhh ||
       !workspace)
     return SB_ERR_INVALID;
   size_t need = 0;
@@ -1501,7 +1509,7 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   GruBwdParams p;
-  p.dy = dy; p.y = y; p.gates = gates; p.whhT = reinterpret_cast<const bf16*>(whhT_bf16);
+  p.dy = dy; p.y = y; p.gates = gates; p.whh = reinterpret_cast<const bf16*>(whh_bf16);
   p.dgi = reinterpret_cast<bf16*>(dgi_bf16);
   p.dghn = reinterpret_cast<bf16*>(dghn_bf16);
   p.barrier = reinterpret_cast<unsigned int*>(ws);

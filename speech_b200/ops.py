@@ -162,6 +162,23 @@ def linear(x, w, b=None):
     return out.view(*lead, out.shape[-1])
 
 
+_gru_operands = {}
+
+
+def register_gru_operands(first_w_ih, entry):
+    """optim.FlatSGD: operands of one GRU layer as views of its flat buffers (see there)."""
+    _gru_operands[id(first_w_ih)] = entry
+
+
+def _cached_gru_operands(w_ih0, Kl):
+    e = _gru_operands.get(id(w_ih0))
+    if e is None or e["wih"].shape[1] != Kl or e["params"][0] is not w_ih0:
+        return None
+    if any(q._version != v for q, v in zip(e["params"], e["versions"])):
+        return None          # modified outside FlatSGD.step(): fall back to casting the fp32 values
+    return e
+
+
 _grad_ready_hook = None
 _announce = True
 _grad_sink_enabled = False
@@ -269,16 +286,22 @@ class GRUStackFunction(torch.autograd.Function):
             b_ih = [wl[d * 4 + 2] for d in range(ndir)]
             b_hh = [wl[d * 4 + 3] for d in range(ndir)]
             Kl = X.shape[1]
-            # bf16 operand copies of the master weights: one fused cast+copy per matrix
             In_l = w_ih[0].shape[1]
-            wih_cat = (torch.empty if Kl == In_l else torch.zeros)(
-                ndir * 3 * H, Kl, dtype=torch.bfloat16, device=dev)
-            whh = torch.empty(ndir, 3 * H, H, dtype=torch.bfloat16, device=dev)
-            for d in range(ndir):
-                wih_cat[d * 3 * H:(d + 1) * 3 * H, :In_l].copy_(w_ih[d].detach())
-                whh[d].copy_(w_hh[d].detach())
-            bih_cat = torch.cat([b.detach() for b in b_ih]).float().contiguous()
-            bhh = torch.stack([b.detach() for b in b_hh]).float().contiguous()
+            cached = _cached_gru_operands(w_ih[0], Kl)
+            if cached is not None:
+                # views of the optimizer's flat buffers (bf16 shadow written by sgd_clip_step)
+                wih_cat, whh = cached["wih"], cached["whh"]
+                bih_cat, bhh = cached["bih"], cached["bhh"]
+            else:
+                # bf16 operand copies of the master weights: one fused cast+copy per matrix
+                wih_cat = (torch.empty if Kl == In_l else torch.zeros)(
+                    ndir * 3 * H, Kl, dtype=torch.bfloat16, device=dev)
+                whh = torch.empty(ndir, 3 * H, H, dtype=torch.bfloat16, device=dev)
+                for d in range(ndir):
+                    wih_cat[d * 3 * H:(d + 1) * 3 * H, :In_l].copy_(w_ih[d].detach())
+                    whh[d].copy_(w_hh[d].detach())
+                bih_cat = torch.cat([b.detach() for b in b_ih]).float().contiguous()
+                bhh = torch.stack([b.detach() for b in b_hh]).float().contiguous()
             gi = gemm_bf16_tn(X, wih_cat, bias=bih_cat)
             y = torch.empty(M, D, dtype=torch.float32, device=dev)
             xn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
@@ -366,9 +389,6 @@ class GRUStackFunction(torch.autograd.Function):
             wl = weights[l * 4 * ndir:(l + 1) * 4 * ndir]
             Kl = X.shape[1]
             In_l = wl[0].shape[1]
-            whhT = torch.empty(ndir, H, K3, dtype=torch.bfloat16, device=dev)   # [ndir][H][3H]
-            for d in range(ndir):
-                _transpose_bf16(whh[d], out=whhT[d])
             dgi = torch.empty(M, ndir * K3, dtype=torch.bfloat16, device=dev)
             dghn = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
             dbih = torch.zeros(ndir * K3, dtype=torch.float32, device=dev)
@@ -376,7 +396,7 @@ class GRUStackFunction(torch.autograd.Function):
             sp = _lib.stream_ptr()
             _launch("gru_bwd", 2.0 * M * 3 * H * H * ndir,
                     lambda dY=dY: lib.sb_gru_bwd(dY.data_ptr(), y.data_ptr(), gates.data_ptr(),
-                                                 whhT.data_ptr(), dgi.data_ptr(), dghn.data_ptr(),
+                                                 whh.data_ptr(), dgi.data_ptr(), dghn.data_ptr(),
                                                  dbih.data_ptr(), dbhh.data_ptr(), ws.data_ptr(),
                                                  nbytes.value, T, Bp, H, ndir, sp))
             base = l * 4 * ndir
