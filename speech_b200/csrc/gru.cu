@@ -65,9 +65,7 @@ struct GruBwdParams {
   const bf16* whh;     // [ndir][3H][H]    W_hh as stored, bf16 (transposed while staging)
   bf16* dgi;           // [T*Bp][ndir*3H]  d(pre-activation) of the input projection, bf16
   bf16* dghn;          // [T*Bp][ndir*H]   dn_pre * r, token-major (wgrad of W_hn)
-  bf16* xchg;          // plain kernel: [ndir][2][Bp][3H] per-step exchange of dgh_t;
-                       // K-split kernel: [ndir][2][3H/64][Bp][64] pre-swizzled exchange tiles
-  unsigned int* ctr;   // K-split kernel: [ndir][32] per-unit-chunk ready counters, 128 B apart
+  bf16* xchg;          // [ndir][2][Bp][3H] per-step exchange of dgh_t (double-buffered)
   float* dbih;         // [ndir*3H] += sum_{t,b} dgi
   float* dbhh;         // [ndir*3H] += sum_{t,b} dgh
   unsigned int* barrier;  // [ndir]
@@ -446,310 +444,6 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
 }
 
 // =============================================================================================
-// forward, version 2: tile-major exchange + bulk copies + per-chunk ready counters
-//
-// Measured on the version above (globaltimer timeline of one CTA, H = 1024, B = 64, 7.36 us/step):
-// 4.4 us from "all CTAs arrived" to "all MMAs retired" - the TMA gather of h_{t-1} as 16 tensor
-// boxes of 64 rows x 128 B picked out of 4 KB-strided token rows, read by 64 CTAs at once;
-// 1.4 us from a CTA's arrive until the single counter is seen complete; 0.8 us inside
-// red.release.gpu after the CTA-wide bar.sync; 0.6 us of gate math on two of the four SM
-// sub-partitions.  Here
-//   * h_t is published into a small double-buffered exchange buffer that is laid out exactly as
-//     the consumers' shared-memory operand: hx[dir][parity][chunk][Bp rows][64] bf16, rows
-//     pre-swizzled (SWIZZLE_128B K-major), so a [Bp x 64] chunk is ONE contiguous Bp*128-byte
-//     block and the gather is nchunks 1-D bulk copies (cp.async.bulk) of whole L2 lines;
-//   * readiness is tracked per chunk: the 4 CTAs that own the 64 units of chunk c arrive (one
-//     red.release.gpu per epilogue WARP, no CTA-wide barrier in front of it) on counter c, and
-//     lane c of the producer warp polls counter c and copies chunk c as soon as its 4 producers
-//     are done - the gather starts while stragglers still compute, and 16 counters take 1/16 of
-//     the atomic traffic each;
-//   * the time-major xn / y / gates stores all happen after the arrive.
-// =============================================================================================
-struct GruFwd2Params {
-  const float* gi;     // [T*Bp][ndir*3H]
-  const bf16* whh;     // [ndir][3H][H]
-  const float* bhh;    // [ndir][3H]
-  float* y;            // [T*Bp][ndir*H]
-  bf16* xn;            // [T*Bp][ndir*H]
-  float* gates;        // [T*Bp][ndir][4][H] or null
-  bf16* hx;            // [ndir][2][nchunks][Bp][64] exchange tiles (zero-initialised)
-  unsigned int* ctr;   // [ndir][32] counters, 128 bytes apart (zero-initialised)
-  unsigned long long* dbg;
-  int T, Bp, H, ndir, ring, gc;
-};
-
-static constexpr int GRU_CTR_STRIDE = 32;   // u32 words between two chunk counters (one L2 line)
-static constexpr int GRU_MAX_CHUNKS = 32;   // one poller lane per chunk
-
-SB_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes),
-        "r"(smem_u32(bar))
-      : "memory");
-}
-SB_DEVINL void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
-                           uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes),
-        "r"(smem_u32(bar)), "h"(mask)
-      : "memory");
-}
-SB_DEVINL void poll_ge(const unsigned int* ctr, unsigned int target) {
-  unsigned int spins = 0;
-  while (ld_acquire_gpu(ctr) < target) {
-    if (++spins > SB_SPIN_LIMIT) __trap();
-  }
-}
-
-// Producer warp of the exchange gather: lane c owns chunk c of every step.  Group g = c / gc
-// shares one full/empty mbarrier pair (slot g % ring); every lane arms its own chunk's bytes.
-// With a cluster, chunk c is copied by the CTA of rank c % cs and multicast to all of them, and a
-// slot is free again when EVERY CTA of the cluster has consumed it (empty barrier count = cs).
-// c: chunk index inside this CTA's operand (lane), nchunks of them; the chunk's tile in the
-// exchange buffer is number src_chunk of src_chunks per parity, its ready counter is `ctr`.
-SB_DEVINL void gather_lane(uint8_t* ring_base, uint64_t* full, uint64_t* empty, const bf16* hx_dir,
-                           const unsigned int* ctr, int c, int nchunks, int src_chunk,
-                           int src_chunks, int chunk_elems, int ring, int gc, int first_step,
-                           int last_step, unsigned int per_step, uint32_t rank, uint32_t cs,
-                           unsigned long long* dbg) {
-  const int ngroups = nchunks / gc;
-  const int upr = ngroups / ring;
-  const int g = c / gc, i = c % gc;
-  const int slot = g % ring;
-  const uint32_t bytes = (uint32_t)chunk_elems * 2u;
-  const bool mine = ((uint32_t)c % cs) == rank;
-  const uint16_t mask = (uint16_t)((1u << cs) - 1u);
-  uint8_t* dst = ring_base + (size_t)(slot * gc + i) * bytes;
-  for (int step = first_step; step < last_step; ++step) {
-    const int k = step - first_step;
-    const unsigned int P = (unsigned int)(k * upr + g / ring);
-    if (P > 0) mbar_wait(&empty[slot], (P - 1u) & 1u);
-    mbar_expect_tx(&full[slot], bytes);
-    if (mine) {
-      // h of the previous step (parity (step-1)&1) is complete when its producers arrived
-      poll_ge(ctr, per_step * (unsigned int)(step - first_step + 1));
-      if (dbg && c == 0 && blockIdx.x == 0 && step < 64) dbg[step * 16 + 0] = gtime();
-      const bf16* src = hx_dir + ((size_t)((step - 1) & 1) * src_chunks + src_chunk) * chunk_elems;
-      if (cs > 1) bulk_g2s_mc(dst, src, bytes, &full[slot], mask);
-      else bulk_g2s(dst, src, bytes, &full[slot]);
-      if (dbg && c == nchunks - 1 && blockIdx.x == 0 && step < 64) dbg[step * 16 + 1] = gtime();
-    }
-  }
-}
-
-// MMA thread of version 2: like mma_consume, but the slot is always handed back (empty barrier)
-template <int N>
-SB_DEVINL void mma_consume2(uint8_t* ring_base, uint8_t* wtile, uint64_t* full, uint64_t* empty,
-                            uint64_t* accfull, uint32_t tmem_d, int nchunks, int wchunk_bytes,
-                            int chunk_bytes, int ring, int gc, int k, uint32_t cs) {
-  constexpr uint32_t idesc = umma_idesc_bf16_f32(128, N);
-  const int ngroups = nchunks / gc;
-  const int upr = ngroups / ring;
-  const uint16_t mask = (uint16_t)((1u << cs) - 1u);
-  for (int g = 0; g < ngroups; ++g) {
-    const int slot = g % ring;
-    const unsigned int P = (unsigned int)(k * upr + g / ring);
-    mbar_wait(&full[slot], P & 1u);
-    tc_fence_after_sync();
-    for (int i = 0; i < gc; ++i) {
-      const int c = g * gc + i;
-      const uint64_t da =
-          umma_desc_sw128_kmajor(smem_u32(ring_base + (size_t)(slot * gc + i) * chunk_bytes));
-      const uint64_t db = umma_desc_sw128_kmajor(smem_u32(wtile + c * wchunk_bytes));
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16_ss(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                     (c > 0 || kk > 0) ? 1u : 0u);
-    }
-    if (cs > 1) umma_commit_mc(&empty[slot], mask);
-    else umma_commit(&empty[slot]);
-  }
-  umma_commit(accfull);
-}
-
-__global__ void __launch_bounds__(GRU_THREADS, 1)
-gru_fwd2_kernel(const GruFwd2Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const int H = p.H, Bp = p.Bp, T = p.T;
-  const int nC = H / GRU_HC;
-  const int dir = blockIdx.x / nC;
-  const int j0 = (blockIdx.x % nC) * GRU_HC;
-  const int nchunks = (H + 63) / 64;
-  constexpr int WCHUNK = 48 * 128;  // 48 rows x 64 bf16
-  const int chunk_bytes = Bp * 128;
-  const int ring_bytes = p.ring * p.gc * chunk_bytes;
-  const int wbytes = max(nchunks * WCHUNK, 16384 - chunk_bytes);
-  const GruSmem s = carve(smem_raw, ring_bytes, wbytes);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int D = p.ndir * H;
-  const uint32_t crank = cluster_rank(), csize = cluster_size();
-
-  for (int k = tid; k < (ring_bytes + wbytes) / 16; k += GRU_THREADS)
-    reinterpret_cast<uint4*>(s.ring)[k] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  {
-    const int pieces_per_row = nchunks * 8;
-    for (int k = tid; k < 48 * pieces_per_row; k += GRU_THREADS) {
-      const int r = k / pieces_per_row, pc = k % pieces_per_row;
-      const int g = r / GRU_HC, jj = r % GRU_HC;
-      const int col = pc * 8;
-      if (col < H) {
-        const uint4 v = *reinterpret_cast<const uint4*>(
-            p.whh + ((long long)dir * 3 * H + g * H + j0 + jj) * H + col);
-        *reinterpret_cast<uint4*>(s.wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
-      }
-    }
-    if (tid < 48) {
-      const int g = tid / GRU_HC, jj = tid % GRU_HC;
-      s.scratch[tid] = p.bhh[dir * 3 * H + g * H + j0 + jj];
-    }
-  }
-  if (tid == 0) {
-    for (int i = 0; i < GRU_MAX_RING; ++i) {
-      mbar_init(&s.full[i], p.gc);      // one arrive.expect_tx per chunk lane of the group
-      mbar_init(&s.empty[i], csize);
-    }
-    mbar_init(s.accfull, 1);
-    mbar_fence_init();
-  }
-  if (warp == 8) tmem_alloc(s.tmem_slot, 64);
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  cluster_sync_all();
-  const uint32_t tmem_base = *s.tmem_slot;
-
-  // epilogue warps that hold real batch rows; each arrives once per step on its chunk counter
-  const int nw_active = 2 * ((Bp + 31) / 32);
-  const int my_chunk = j0 / 64;
-  unsigned int* ctr_dir = p.ctr + dir * GRU_MAX_CHUNKS * GRU_CTR_STRIDE;
-  bf16* hx_dir = p.hx + (size_t)dir * 2 * nchunks * (Bp * 64);
-
-  if (warp == 9) {
-    // ===================== exchange gather: lane c owns chunk c =====================
-    if (lane < nchunks) {
-      const int ctas_c = min(64 / GRU_HC, nC - lane * (64 / GRU_HC));
-      gather_lane(s.ring, s.full, s.empty, hx_dir, ctr_dir + lane * GRU_CTR_STRIDE, lane, nchunks,
-                  lane, nchunks, Bp * 64, p.ring, p.gc, 1, T, (unsigned int)(ctas_c * nw_active),
-                  crank, csize, p.dbg);
-    }
-  } else if (warp == 8) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      for (int step = 1; step < T; ++step) {
-        mma_consume2<48>(s.ring, s.wtile, s.full, s.empty, s.accfull, tmem_base, nchunks, WCHUNK,
-                         chunk_bytes, p.ring, p.gc, step - 1, csize);
-        GRU_STAMP(2);
-      }
-    }
-  } else {
-    // ===================== epilogue: thread = (batch row, half of the 16 units) ==============
-    const int row = (warp & 3) * 32 + lane;
-    const int uh = warp >> 2;
-    const int ju = j0 + uh * GRU_UPT;
-    float hprev[GRU_UPT];
-#pragma unroll
-    for (int jj = 0; jj < GRU_UPT; ++jj) hprev[jj] = 0.f;
-    float bias[3][GRU_UPT];
-#pragma unroll
-    for (int g = 0; g < 3; ++g)
-#pragma unroll
-      for (int jj = 0; jj < GRU_UPT; ++jj) bias[g][jj] = s.scratch[g * 16 + uh * GRU_UPT + jj];
-    const bool active = row < Bp;
-    const bool warp_active = (warp & 3) * 32 < Bp;
-    unsigned int* my_ctr = ctr_dir + my_chunk * GRU_CTR_STRIDE;
-    // this thread's 16-byte piece inside its chunk tile: row `row`, 16-byte column (j0%64)/8 + uh
-    const uint32_t piece = sw128_offset((uint32_t)row, (uint32_t)((j0 % 64) / 8 + uh));
-    for (int step = 0; step < T; ++step) {
-      const int t = dir == 0 ? step : (T - 1 - step);
-      float gi[3][GRU_UPT];
-      if (active) {
-        const float* g = p.gi + ((long long)t * Bp + row) * (p.ndir * 3 * H) + dir * 3 * H + ju;
-#pragma unroll
-        for (int gg = 0; gg < 3; ++gg) ld8(g + gg * H, gi[gg]);
-      }
-      float acc[3][GRU_UPT];
-      if (step > 0) {
-        mbar_wait(s.accfull, (step - 1) & 1);
-        if (tid == 0) GRU_STAMP(3);
-        tc_fence_after_sync();
-        uint32_t v[3][8];
-#pragma unroll
-        for (int gg = 0; gg < 3; ++gg)
-          tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + gg * 16 + uh * GRU_UPT,
-                            v[gg]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int gg = 0; gg < 3; ++gg)
-#pragma unroll
-          for (int jj = 0; jj < GRU_UPT; ++jj) acc[gg][jj] = __uint_as_float(v[gg][jj]);
-        tc_fence_before_sync();
-        if (tid == 0) GRU_STAMP(4);
-      } else {
-#pragma unroll
-        for (int gg = 0; gg < 3; ++gg)
-#pragma unroll
-          for (int jj = 0; jj < GRU_UPT; ++jj) acc[gg][jj] = 0.f;
-      }
-      const long long m = (long long)t * Bp + row;
-      float hn[GRU_UPT], rr[GRU_UPT], zz[GRU_UPT], nn[GRU_UPT];
-      if (active) {
-#pragma unroll
-        for (int jj = 0; jj < GRU_UPT; ++jj) {
-          rr[jj] = fast_sigmoid(gi[0][jj] + acc[0][jj] + bias[0][jj]);
-          zz[jj] = fast_sigmoid(gi[1][jj] + acc[1][jj] + bias[1][jj]);
-          hn[jj] = acc[2][jj] + bias[2][jj];
-          nn[jj] = fast_tanh(gi[2][jj] + rr[jj] * hn[jj]);
-          hprev[jj] = (1.f - zz[jj]) * nn[jj] + zz[jj] * hprev[jj];
-        }
-      }
-      if (step + 1 < T) {
-        if (active) {
-          // critical path: this thread's 16 bytes of the exchange tile of parity step&1
-          uint8_t* tile = reinterpret_cast<uint8_t*>(
-              hx_dir + ((size_t)(step & 1) * nchunks + my_chunk) * (Bp * 64));
-          *reinterpret_cast<uint4*>(tile + piece) = pack8(hprev);
-          if (tid == 0) GRU_STAMP(5);
-          fence_proxy_async_global();   // generic writes -> other CTAs' bulk-copy (async proxy) reads
-          if (tid == 0) GRU_STAMP(6);
-        }
-        __syncwarp();
-        if (warp_active && lane == 0) {
-          if (tid == 0) GRU_STAMP(7);
-          red_release_gpu_add(my_ctr, 1u);   // release: cumulative over the warp's writes
-          if (tid == 0) GRU_STAMP(9);
-        }
-      }
-      // off the critical path: bf16 operand of the next projection, fp32 state, saved gates
-      if (active) {
-        st_stream_u4(p.xn + m * D + dir * H + ju, pack8(hprev));
-        st8(p.y + m * D + dir * H + ju, hprev);
-        if (p.gates) {
-          float* go = p.gates + ((m * p.ndir + dir) * 4) * H + ju;
-          st8(go, rr);
-          st8(go + H, zz);
-          st8(go + 2 * H, nn);
-          st8(go + 3 * H, hn);
-        }
-      }
-      if (tid == 0) GRU_STAMP(10);
-    }
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 8) {
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 64);
-  }
-}
-
-// =============================================================================================
 // backward (reverse of the forward time order of each direction)
 // =============================================================================================
 __global__ void __launch_bounds__(GRU_THREADS, 1)
@@ -999,7 +693,8 @@ SB_DEVINL void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(GRU_THREADS, 1)
-gru_bwd_ks_kernel(const GruBwdParams p) {
+gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
+                  const __grid_constant__ CUtensorMap tm_d1, const GruBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int H = p.H, Bp = p.Bp, T = p.T;
   const int nC = H / GRU_HC;
@@ -1023,12 +718,12 @@ gru_bwd_ks_kernel(const GruBwdParams p) {
   float* recv = reinterpret_cast<float*>(wtile + wbytes);          // [KS][Bp][16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(recv + KS * Bp * 16);
   uint64_t* full = bars;          // [4] groups
-  uint64_t* empty = bars + 4;     // [4]
-  uint64_t* accfull = bars + 8;
-  uint64_t* recvbar = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* accfull = bars + 4;
+  uint64_t* recvbar = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = p.ndir * H;
+  const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
   const int gc = (nchunks % 4 == 0) ? 4 : ((nchunks % 3 == 0) ? 3 : ((nchunks % 2 == 0) ? 2 : 1));
   const int ngroups = nchunks / gc;                   // <= 4 for H <= 1024 ... checked on host
 
@@ -1052,13 +747,11 @@ gru_bwd_ks_kernel(const GruBwdParams p) {
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], gc);      // one arrive.expect_tx per chunk lane of the group
-      mbar_init(&empty[i], 1);
-    }
+    for (int i = 0; i < 4; ++i) mbar_init(&full[i], 1);
     mbar_init(accfull, 1);
     mbar_init(recvbar, (KS - 1) * (GRU_EPI / 32));   // one arrive per epilogue warp of every peer
     mbar_fence_init();
+    tma_prefetch_desc(tm);
   }
   if (warp == 8) tmem_alloc(tmem_slot, 64);
   fence_proxy_async_smem();
@@ -1067,26 +760,40 @@ gru_bwd_ks_kernel(const GruBwdParams p) {
   tc_fence_after_sync();
   cluster_sync_all();
   const uint32_t tmem_base = *tmem_slot;
-  // exchange: dgh_t lives in pre-swizzled [Bp x 64] tiles, chunk kc = gate * (H/64) + unit chunk;
-  // the 4 CTAs owning unit chunk uc arrive (once per epilogue warp and step) on counter uc
-  const int nchH = H / 64;
-  const int nw_active = 2 * ((Bp + 31) / 32);
-  unsigned int* ctr_dir = p.ctr + dir * GRU_MAX_CHUNKS * GRU_CTR_STRIDE;
-  bf16* dgx_dir = p.xchg + (size_t)dir * 2 * (3 * nchH) * (Bp * 64);
+  unsigned int* ctr = p.barrier + dir;
 
   if (warp == 9) {
-    if (lane < nchunks) {
-      const int kc = (int)crank * nchunks + lane;      // this lane's chunk of the K = 3H dimension
-      gather_lane(ring, full, empty, dgx_dir, ctr_dir + (kc % nchH) * GRU_CTR_STRIDE, lane,
-                  nchunks, kc, 3 * nchH, Bp * 64, ngroups, gc, 1, T,
-                  (unsigned int)((64 / GRU_HC) * nw_active), 0u, 1u, p.dbg);
+    if (lane == 0) {
+      for (int step = 0; step + 1 < T; ++step) {
+        grid_wait(ctr, (unsigned int)nC * (step + 1));   // dgh of this step is complete
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_expect_tx(&full[g], (uint32_t)(stride * gc));
+          for (int i = 0; i < gc; ++i) {
+            const int c = g * gc + i;
+            tma_load_2d(ring + c * stride, tm, &full[g], (int)crank * KQ + c * 64,
+                        (step & 1) * Bp);
+          }
+        }
+      }
     }
   } else if (warp == 8) {
     if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 64);
       for (int step = 0; step + 1 < T; ++step) {
-        mma_consume2<64>(ring, wtile, full, empty, accfull, tmem_base, nchunks, WCHUNK, stride,
-                         ngroups, gc, step, 1u);
-        GRU_STAMP(2);
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&full[g], step & 1);
+          tc_fence_after_sync();
+          for (int i = 0; i < gc; ++i) {
+            const int c = g * gc + i;
+            const uint64_t da = umma_desc_sw128_kmajor(smem_u32(ring + c * stride));
+            const uint64_t db = umma_desc_sw128_kmajor(smem_u32(wtile + c * WCHUNK));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ss(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                           (c > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(accfull);
       }
     }
   } else {
@@ -1104,15 +811,12 @@ gru_bwd_ks_kernel(const GruBwdParams p) {
     const uint32_t my_slot = smem_u32(recv + ((size_t)crank * Bp + (active ? row : 0)) * 16 +
                                       uh * GRU_UPT);
     const uint32_t my_bar = smem_u32(recvbar);
-    const bool warp_active = (warp & 3) * 32 < Bp;
-    unsigned int* my_ctr = ctr_dir + (j0 / 64) * GRU_CTR_STRIDE;
-    // this thread's 16-byte piece inside a chunk tile: row `row`, 16-byte column (j0%64)/8 + uh
-    const uint32_t piece = sw128_offset((uint32_t)(active ? row : 0), (uint32_t)((j0 % 64) / 8 + uh));
 
     for (int step = 0; step < T; ++step) {
       const int t = dir == 0 ? (T - 1 - step) : step;
       const int tp = dir == 0 ? t - 1 : t + 1;
       const bool has_prev = dir == 0 ? (t > 0) : (t < T - 1);
+      bf16* xb = p.xchg + ((long long)(dir * 2 + (step & 1)) * Bp) * K3;
       const long long m = (long long)t * Bp + row;
       float rr[GRU_UPT], zz[GRU_UPT], nn[GRU_UPT], hn[GRU_UPT], dh[GRU_UPT], hp[GRU_UPT];
       if (active) {
@@ -1195,24 +899,21 @@ gru_bwd_ks_kernel(const GruBwdParams p) {
           db_hn[jj] += dnr[jj];
         }
         if (step + 1 < T) {
-          // critical path: the tiles [dr | dz | dn*r] the cluster peers of every unit chunk gather
-          uint8_t* tiles = reinterpret_cast<uint8_t*>(
-              dgx_dir + ((size_t)(step & 1) * (3 * nchH) + j0 / 64) * (Bp * 64));
-          const size_t gate_stride = (size_t)nchH * stride;
-          *reinterpret_cast<uint4*>(tiles + piece) = pack8(dr);
-          *reinterpret_cast<uint4*>(tiles + gate_stride + piece) = pack8(dz);
-          *reinterpret_cast<uint4*>(tiles + 2 * gate_stride + piece) = pack8(dnr);
+          bf16* x = xb + (long long)row * K3 + ju;
+          *reinterpret_cast<uint4*>(x) = pack8(dr);
+          *reinterpret_cast<uint4*>(x + H) = pack8(dz);
+          *reinterpret_cast<uint4*>(x + 2 * H) = pack8(dnr);
           if (tid == 0) GRU_STAMP(5);
           fence_proxy_async_global();
           if (tid == 0) GRU_STAMP(6);
         }
       }
       if (step + 1 < T) {
-        __syncwarp();
-        if (warp_active && lane == 0) {
-          if (tid == 0) GRU_STAMP(7);
-          red_release_gpu_add(my_ctr, 1u);
-          if (tid == 0) GRU_STAMP(9);
+        epi_barrier();
+        if (tid == 0) {
+          GRU_STAMP(7);
+          grid_arrive(ctr);
+          GRU_STAMP(9);
         }
       }
       if (active) {
@@ -1248,6 +949,261 @@ gru_bwd_ks_kernel(const GruBwdParams p) {
   if (warp == 8) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// =============================================================================================
+// forward, K-split variant: the 4 CTAs of a cluster jointly own 64 hidden units.
+//
+// Measured on gru_fwd_kernel (globaltimer timeline, H = 1024, B = 64, 7.4 us/step): 3.5 us pass
+// between "h_{t-1} is complete" and "all MMAs retired", for a gather of 128 KB per CTA - the same
+// ~30 B/ns per SM whether it is fetched as tensor boxes or as contiguous bulk copies, with or
+// without cluster multicast: 128 CTAs x 128 KB = 16 MB of L2->SM traffic per step is the bound,
+// next to 480 KB of shared-memory traffic (TMA writes + MMA operand reads of a 128-row A tile).
+// Here CTA r of a cluster contracts only the r-th QUARTER of K = H for all 64 units of its
+// cluster and all three gates,
+//     D_r[batch x 192] = h_{t-1}[:, quarter r] * W_hh[(r|z|n) x 64 units, quarter r]^T,
+// i.e. it gathers 32 KB instead of 128 KB (the whole quarter stays resident: no ring) and issues
+// 16 MMAs of N = 192 instead of 64 of N = 48; the four partial products are reduce-scattered
+// through distributed shared memory exactly as in gru_bwd_ks_kernel (each CTA receives the
+// 3 x 16 columns of its own units from its three peers: 36 KB per CTA and step).
+// Requires cluster size 4, H % 256 == 0, Bp <= 64.
+// =============================================================================================
+__global__ void __launch_bounds__(GRU_THREADS, 1)
+gru_fwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
+                  const __grid_constant__ CUtensorMap tm_d1, const GruFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int H = p.H, Bp = p.Bp, T = p.T;
+  const int nC = H / GRU_HC;
+  const int dir = blockIdx.x / nC;
+  const int cta_in_dir = blockIdx.x % nC;
+  const int j0 = cta_in_dir * GRU_HC;                 // own 16 units (gate math, stores)
+  const uint32_t crank = cluster_rank();              // == cta_in_dir % 4
+  const int k0c = (cta_in_dir / KS) * (KS * GRU_HC);  // first of the cluster's 64 units
+  const int KQ = H / KS;                              // this CTA's share of the contraction
+  const int nchunks = KQ / 64;
+  constexpr int NCOL = 3 * KS * GRU_HC;               // 192 accumulator columns: gate x 64 units
+  constexpr int WCHUNK = NCOL * 128;                  // 192 rows x 64 bf16
+  constexpr int RW = 3 * GRU_HC;                      // 48 floats received per row and peer
+  const int stride = Bp * 128;
+  const int ring_bytes = nchunks * stride;            // the whole quarter is resident
+  const int wbytes = nchunks * WCHUNK;
+  // carve: ring | weights | recv | barriers.  (The 128-row A read of the last chunk runs past the
+  // ring into the weights: finite data, rows >= Bp are never used.)
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* ring = base;
+  uint8_t* wtile = ring + ring_bytes;
+  float* recv = reinterpret_cast<float*>(wtile + wbytes);          // [KS][Bp][48]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(recv + KS * Bp * RW);
+  uint64_t* full = bars;
+  uint64_t* accfull = bars + 1;
+  uint64_t* recvbar = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* bias_s = reinterpret_cast<float*>(bars + 4);             // [48]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = p.ndir * H;
+  const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
+
+  for (int k = tid; k < (ring_bytes + wbytes + KS * Bp * RW * 4) / 16; k += GRU_THREADS)
+    reinterpret_cast<uint4*>(base)[k] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    // resident operand: rows = (gate, unit of the cluster), columns = this CTA's K quarter
+    const int pieces_per_row = nchunks * 8;
+    for (int k = tid; k < NCOL * pieces_per_row; k += GRU_THREADS) {
+      const int r = k / pieces_per_row, pc = k % pieces_per_row;
+      const int g = r / (KS * GRU_HC), u = r % (KS * GRU_HC);
+      const uint4 v = *reinterpret_cast<const uint4*>(
+          p.whh + ((long long)dir * 3 * H + (long long)g * H + k0c + u) * H + (long long)crank * KQ +
+          pc * 8);
+      *reinterpret_cast<uint4*>(wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+    }
+    if (tid < RW) {
+      const int g = tid / GRU_HC, jj = tid % GRU_HC;
+      bias_s[tid] = p.bhh[dir * 3 * H + g * H + j0 + jj];
+    }
+  }
+  if (tid == 0) {
+    mbar_init(full, 1);
+    mbar_init(accfull, 1);
+    mbar_init(recvbar, (KS - 1) * (GRU_EPI / 32));   // one arrive per epilogue warp of every peer
+    mbar_fence_init();
+    tma_prefetch_desc(tm);
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  cluster_sync_all();
+  const uint32_t tmem_base = *tmem_slot;
+  unsigned int* ctr = p.barrier + dir;
+
+  if (warp == 9) {
+    // ===================== TMA producer: this CTA's K quarter of h_{t-1} =====================
+    if (lane == 0) {
+      for (int step = 1; step < T; ++step) {
+        const int t = dir == 0 ? step : (T - 1 - step);
+        const int tp = dir == 0 ? t - 1 : t + 1;
+        grid_wait(ctr, (unsigned int)nC * step);       // all CTAs published h_{tp}
+        GRU_STAMP(0);
+        mbar_expect_tx(full, (uint32_t)(stride * nchunks));
+        for (int c = 0; c < nchunks; ++c)
+          tma_load_2d(ring + c * stride, tm, full, (int)crank * KQ + c * 64, tp * Bp);
+        GRU_STAMP(1);
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NCOL);
+      for (int step = 1; step < T; ++step) {
+        mbar_wait(full, (step - 1) & 1);
+        tc_fence_after_sync();
+        for (int c = 0; c < nchunks; ++c) {
+          const uint64_t da = umma_desc_sw128_kmajor(smem_u32(ring + c * stride));
+          const uint64_t db = umma_desc_sw128_kmajor(smem_u32(wtile + c * WCHUNK));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ss(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                         (c > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(accfull);
+        GRU_STAMP(2);
+      }
+    }
+  } else {
+    // ===================== epilogue: thread = (batch row, half of the CTA's 16 units) ==========
+    const int row = (warp & 3) * 32 + lane;
+    const int uh = warp >> 2;
+    const int ju = j0 + uh * GRU_UPT;
+    const bool active = row < Bp;
+    float hprev[GRU_UPT];
+#pragma unroll
+    for (int jj = 0; jj < GRU_UPT; ++jj) hprev[jj] = 0.f;
+    float bias[3][GRU_UPT];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int jj = 0; jj < GRU_UPT; ++jj) bias[g][jj] = bias_s[g * GRU_HC + uh * GRU_UPT + jj];
+    // where this thread's slices land in each peer: recv[src = my rank][row][gate*16 + uh*8 ..]
+    const uint32_t my_slot =
+        smem_u32(recv + ((size_t)crank * Bp + (active ? row : 0)) * RW + uh * GRU_UPT);
+    const uint32_t my_bar = smem_u32(recvbar);
+
+    for (int step = 0; step < T; ++step) {
+      const int t = dir == 0 ? step : (T - 1 - step);
+      float gi[3][GRU_UPT];
+      if (active) {
+        const float* g = p.gi + ((long long)t * Bp + row) * (p.ndir * 3 * H) + dir * 3 * H + ju;
+#pragma unroll
+        for (int gg = 0; gg < 3; ++gg) ld8(g + gg * H, gi[gg]);
+      }
+      float acc[3][GRU_UPT];
+#pragma unroll
+      for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+        for (int jj = 0; jj < GRU_UPT; ++jj) acc[gg][jj] = 0.f;
+      if (step > 0) {
+        mbar_wait(accfull, (step - 1) & 1);
+        if (tid == 0) GRU_STAMP(3);
+        tc_fence_after_sync();
+        // ---- reduce-scatter of the four partial products: one peer's 3 x 8 columns at a time ----
+#pragma unroll
+        for (int pr = 0; pr < KS; ++pr) {
+          uint32_t v[3][8];
+#pragma unroll
+          for (int gg = 0; gg < 3; ++gg)
+            tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
+                                  gg * (KS * GRU_HC) + pr * GRU_HC + uh * GRU_UPT, v[gg]);
+          tmem_ld_wait();
+          if ((uint32_t)pr == crank) {
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+              for (int jj = 0; jj < GRU_UPT; ++jj) acc[gg][jj] = __uint_as_float(v[gg][jj]);
+          } else if (active) {
+            const uint32_t ra = mapa_shared(my_slot, (uint32_t)pr);
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) {
+              st_cluster_f4(ra + gg * (GRU_HC * 4),
+                            make_float4(__uint_as_float(v[gg][0]), __uint_as_float(v[gg][1]),
+                                        __uint_as_float(v[gg][2]), __uint_as_float(v[gg][3])));
+              st_cluster_f4(ra + gg * (GRU_HC * 4) + 16,
+                            make_float4(__uint_as_float(v[gg][4]), __uint_as_float(v[gg][5]),
+                                        __uint_as_float(v[gg][6]), __uint_as_float(v[gg][7])));
+            }
+          }
+        }
+        // one release-arrive per warp and peer (see gru_bwd_ks_kernel)
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int pr = 0; pr < KS; ++pr)
+            if ((uint32_t)pr != crank) mbar_arrive_remote_release(mapa_shared(my_bar, (uint32_t)pr));
+        }
+        tc_fence_before_sync();
+        if (tid == 0) GRU_STAMP(4);
+        mbar_wait_acquire_cluster(recvbar, (step - 1) & 1);
+        if (active) {
+#pragma unroll
+          for (int src = 0; src < KS; ++src) {
+            if ((uint32_t)src == crank) continue;
+            const float* rp = recv + ((size_t)src * Bp + row) * RW + uh * GRU_UPT;
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) {
+              const float4 a = *reinterpret_cast<const float4*>(rp + gg * GRU_HC);
+              const float4 b = *reinterpret_cast<const float4*>(rp + gg * GRU_HC + 4);
+              acc[gg][0] += a.x; acc[gg][1] += a.y; acc[gg][2] += a.z; acc[gg][3] += a.w;
+              acc[gg][4] += b.x; acc[gg][5] += b.y; acc[gg][6] += b.z; acc[gg][7] += b.w;
+            }
+          }
+        }
+      }
+      const long long m = (long long)t * Bp + row;
+      float hn[GRU_UPT], rr[GRU_UPT], zz[GRU_UPT], nn[GRU_UPT];
+      if (active) {
+#pragma unroll
+        for (int jj = 0; jj < GRU_UPT; ++jj) {
+          rr[jj] = fast_sigmoid(gi[0][jj] + acc[0][jj] + bias[0][jj]);
+          zz[jj] = fast_sigmoid(gi[1][jj] + acc[1][jj] + bias[1][jj]);
+          hn[jj] = acc[2][jj] + bias[2][jj];
+          nn[jj] = fast_tanh(gi[2][jj] + rr[jj] * hn[jj]);
+          hprev[jj] = (1.f - zz[jj]) * nn[jj] + zz[jj] * hprev[jj];
+        }
+        // critical path: only the bf16 h_t that the other CTAs gather next step
+        *reinterpret_cast<uint4*>(p.xn + m * D + dir * H + ju) = pack8(hprev);
+        if (tid == 0) GRU_STAMP(5);
+        fence_proxy_async_global();   // generic writes -> other CTAs' TMA reads
+        if (tid == 0) GRU_STAMP(6);
+      }
+      epi_barrier();
+      if (tid == 0) {
+        GRU_STAMP(7);
+        grid_arrive(ctr);
+        GRU_STAMP(9);
+      }
+      if (active) {
+        st8(p.y + m * D + dir * H + ju, hprev);
+        if (p.gates) {
+          float* go = p.gates + ((m * p.ndir + dir) * 4) * H + ju;
+          st8(go, rr);
+          st8(go + H, zz);
+          st8(go + 2 * H, nn);
+          st8(go + 3 * H, hn);
+        }
+      }
+      if (tid == 0) GRU_STAMP(10);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -1412,16 +1368,17 @@ static int gru_check(int T, int Bp, int H, int ndir) {
   return SB_OK;
 }
 
-// workspace of one recurrence launch: [0,1024) legacy per-direction grid-barrier words,
-// [1024, 1024 + ndir*32*128) per-chunk ready counters (one L2 line each), then the exchange tiles
+// workspace of one recurrence launch: [0,1024) the per-direction grid-barrier words, then the
+// exchange buffers of the backward kernels
 static size_t gru_ws_counters_bytes(int ndir) {
-  return 1024 + (size_t)ndir * GRU_MAX_CHUNKS * GRU_CTR_STRIDE * sizeof(unsigned int);
+  (void)ndir;
+  return 1024;
 }
 
 extern "C" int sb_gru_fwd_workspace_size(int Bp, int H, int ndir, size_t* bytes) {
   if (!bytes || Bp <= 0 || H <= 0 || (ndir != 1 && ndir != 2)) return SB_ERR_INVALID;
-  const int nchunks = (H + 63) / 64;
-  *bytes = gru_ws_counters_bytes(ndir) + (size_t)ndir * 2 * nchunks * Bp * 128 + 1024;
+  (void)Bp;
+  *bytes = gru_ws_counters_bytes(ndir);      // the forward kernels exchange h_t through xn itself
   return SB_OK;
 }
 
@@ -1447,24 +1404,31 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
       gru_ring_slots(std::max(nchunks * 48 * 128, 16384 - Bp * 128), Bp, nchunks, &gc, &smem);
   if (ring < 0) return SB_ERR_UNSUPPORTED;
 
-  if (!(g_gru_ablate & 32) && nchunks <= GRU_MAX_CHUNKS) {
-    GruFwd2Params q;
-    q.gi = gi; q.whh = reinterpret_cast<const bf16*>(whh_bf16); q.bhh = bhh; q.y = y;
-    q.xn = reinterpret_cast<bf16*>(xn_bf16); q.gates = gates;
-    q.ctr = reinterpret_cast<unsigned int*>(ws + 1024);
-    q.hx = reinterpret_cast<bf16*>(ws + gru_ws_counters_bytes(ndir));
-    q.dbg = g_gru_dbg;
-    q.T = T; q.Bp = Bp; q.H = H; q.ndir = ndir; q.ring = ring; q.gc = gc;
-    void* args[] = {(void*)&q};
-    // clusters only buy the multicast of the gather; shrink until the whole grid is co-resident
-    for (int cs = gru_cluster_size(nC); cs >= 1; cs >>= 1) {
-      rc = gru_launch_exact((const void*)gru_fwd2_kernel, ndir * nC, cs, smem, args, stream);
+  // ---- preferred: K-split over 4-CTA clusters (H % 256 == 0, batch rows <= 64) ----
+  if (!(g_gru_ablate & 32) && H % 256 == 0 && nC % KS == 0 && Bp <= 64) {
+    const int nq = H / KS / 64;
+    const size_t ks_smem = (size_t)nq * Bp * 128 + (size_t)nq * 192 * 128 +
+                           (size_t)KS * Bp * 48 * 4 + 1024 + 512;
+    if (ks_smem <= 227 * 1024) {
+      GruFwdParams q;
+      q.gi = gi; q.whh = reinterpret_cast<const bf16*>(whh_bf16); q.bhh = bhh; q.y = y;
+      q.xn = reinterpret_cast<bf16*>(xn_bf16); q.xnT = nullptr; q.gates = gates;
+      q.barrier = barrier; q.T = T; q.Bp = Bp; q.H = H; q.ndir = ndir;
+      q.dbg = g_gru_dbg; q.ablate = 0; q.ring = nq; q.gc = 1;
+      CUtensorMap tq[2];
+      for (int d = 0; d < 2; ++d) {
+        const int dd = d < ndir ? d : 0;
+        rc = make_tmap_bf16_2d(&tq[d], q.xn + (size_t)dd * H, (long long)T * Bp, H,
+                               (long long)ndir * H, Bp);
+        if (rc != SB_OK) return rc;
+      }
+      void* kargs[] = {(void*)&tq[0], (void*)&tq[1], (void*)&q};
+      rc = gru_launch_exact((const void*)gru_fwd_ks_kernel, ndir * nC, KS, ks_smem, kargs, stream);
       if (rc == SB_OK) return SB_OK;
     }
-    return rc;
   }
 
-  // ---- version 1 (tensor-map gather, one counter per direction): developer comparison only ----
+  // ---- every other shape: each CTA gathers all of h_{t-1} (tensor-map TMA, cluster multicast) ----
   GruFwdParams p;
   p.gi = gi; p.whh = reinterpret_cast<const bf16*>(whh_bf16); p.bhh = bhh; p.y = y;
   p.xn = reinterpret_cast<bf16*>(xn_bf16); p.xnT = nullptr;
@@ -1513,7 +1477,6 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   p.dgi = reinterpret_cast<bf16*>(dgi_bf16);
   p.dghn = reinterpret_cast<bf16*>(dghn_bf16);
   p.barrier = reinterpret_cast<unsigned int*>(ws);
-  p.ctr = reinterpret_cast<unsigned int*>(ws + 1024);
   p.xchg = reinterpret_cast<bf16*>(ws + gru_ws_counters_bytes(ndir));
   p.dbih = dbih; p.dbhh = dbhh; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
   p.dbg = g_gru_dbg;
@@ -1530,8 +1493,14 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
     const size_t ks_smem = (size_t)nq * Bp * 128 + (size_t)nq * 64 * 128 + (size_t)KS * Bp * 64 +
                            1024 + 256;
     if (ks_smem <= 227 * 1024) {
+      CUtensorMap tq[2];
+      for (int d = 0; d < 2; ++d) {
+        const int dd = d < ndir ? d : 0;
+        rc = make_tmap_bf16_2d(&tq[d], p.xchg + (size_t)dd * 2 * Bp * K3, 2LL * Bp, K3, K3, Bp);
+        if (rc != SB_OK) return rc;
+      }
       p.ring = nq; p.gc = 1;
-      void* kargs[] = {(void*)&p};
+      void* kargs[] = {(void*)&tq[0], (void*)&tq[1], (void*)&p};
       rc = gru_launch_exact((const void*)gru_bwd_ks_kernel, ndir * nC_, KS, ks_smem, kargs, stream);
       if (rc == SB_OK) return SB_OK;
     }

@@ -36,8 +36,8 @@ else:
     lib.sb_debug_gru_timeline(None)
 print("mode:", MODE)
 d = dbg.cpu().numpy().reshape(64, 16)
-names = ["P:chunk 0 ready seen", "P:last chunk copy issued", "M:all mma committed", "E:accfull",
-         "E:tmem loaded", "E:exchange stored", "E:proxy fence", "E:before arrive", None,
+names = ["P:grid_wait done", "P:tma issued", "M:all mma committed", "E:accfull",
+         "E:tmem loaded (+reduce-scatter)", "E:xn stored", "E:proxy fence", "E:epi barrier", None,
          "E:arrived", "E:offpath done"]
 for step in (11, 40):
     base = d[step - 1][9]   # previous step's arrival by this CTA
