@@ -173,17 +173,57 @@ int sb_sgd_clip_step(float* params, const float* grads, float* momentum_buf, voi
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * One decoder step of the additive location-aware attention (forward only, decode path).
- * Replaces: NNAttention.forward (speech/models/seq2seq.py:344-360) inside Seq2Seq.decode_step
- *           (:114-137), i.e. infer (:162-178) and beam_search (:180-227).
- *   eh (B,T,H) encoder states; dhx (B,H) decoder state; ax_prev (B,T) previous alignment or NULL
- *   conv_w (H,Kc), conv_b (H): Conv1d(1,H,Kc,'same') over ax_prev; lin_w (H), lin_b: Linear(H,1)
- *   log_t != 0: scores are multiplied by log(T) before the softmax
- *   out: sx (B,H) = sum_t ax_t eh_t ; ax (B,T) = softmax over time
+ * Attention decoder step of the sequence-to-sequence model (csrc/s2s.cu), fp32.
+ * Replaces: the per-token chain nn.Embedding + nn.GRUCell + NNAttention (Conv1d, broadcast add,
+ *           ReLU, Linear, softmax, weighted sum) + LinearND of Seq2Seq.decode / decode_step
+ *           (speech/models/seq2seq.py:78-137, 344-360) and the host loops of infer (:145-178) and
+ *           beam_search (:180-227).
+ *   sb_s2s_cell_fwd   ix = emb[tok[b*tok_stride]] + sx_prev (NULL at the first step);
+ *                     hx = GRUCell(ix, hx_prev); optionally saves ix and the gates (r, z, n, hn)
+ *   sb_s2s_attn_fwd   attention of every row over eh (eh_bcast: all rows attend over utterance
+ *                     0 - beam search), sx (B,H) / ax (B,T); with fc_w: logits = fc(hx + sx) written
+ *                     at logits[b*logit_stride + c], optional log-softmax, arg-max, greedy history
+ *                     and end-token count; `done` (device int, may be NULL): != 0 -> no-op
+ *   sb_attn_step      the attention alone (NNAttention.forward on the decode path)
+ *   sb_s2s_attn_bwd / sb_s2s_cell_bwd   gradients of one step (see csrc/s2s.cu)
+ *   sb_s2s_check_done greedy stop rule: every row emitted end_tok in the same step
+ *   sb_s2s_beam_*     device-side beam bookkeeping with the reference's stable-sort tie order
+ * Constraints: H % 4 == 0, H <= 1024, conv kernel width odd and <= 15, beam <= 32.
  * ------------------------------------------------------------------------------------- */
 int sb_attn_step(const float* eh, const float* dhx, const float* ax_prev, const float* conv_w,
                  const float* conv_b, const float* lin_w, float lin_b, int log_t, int B, int T,
                  int H, int Kc, float* sx, float* ax, void* stream);
+int sb_s2s_cell_fwd(const float* emb, const int* tok, int tok_stride, const float* sx_prev,
+                    const float* hx_prev, const float* w_ih, const float* w_hh, const float* b_ih,
+                    const float* b_hh, float* hx, float* ix_save, float* gates_save,
+                    const int* done, int B, int H, void* stream);
+int sb_s2s_attn_fwd(const float* eh, int eh_bcast, const float* hx, const float* ax_prev,
+                    const float* conv_w, const float* conv_b, const float* lin_w, float lin_b,
+                    int log_t, int B, int T, int H, int Kc, float* sx, float* ax,
+                    const float* fc_w, const float* fc_b, int C, float* logits,
+                    long long logit_stride, float* logp, int* argmax, int* history,
+                    int hist_stride, int hist_col, int* end_count, int end_tok, const int* done,
+                    void* stream);
+int sb_s2s_attn_bwd(const float* eh, const float* hx, const float* hx_prev, const float* ax_prev,
+                    const float* ax, const float* sx, const float* conv_w, const float* conv_b,
+                    const float* lin_w, float lin_b, const float* fc_w, const float* dlogits,
+                    long long dl_stride, const float* d_ix_next, const float* d_ax_next,
+                    const float* d_hx_next, const float* gates, float* d_eh, float* d_ax_prev,
+                    float* d_gi, float* d_gh, float* d_hx_direct, float* o_save, float* g_conv_w,
+                    float* g_conv_b, float* g_lin_w, float* g_lin_b, int log_t, int B, int T, int H,
+                    int Kc, int C, void* stream);
+int sb_s2s_cell_bwd(const float* d_gi, const float* d_gh, const float* d_hx_direct,
+                    const float* w_ih, const float* w_hh, float* d_ix, float* d_hx_prev, int B,
+                    int H, void* stream);
+int sb_s2s_check_done(const int* end_count, int B, int* done, int* nsteps, int step1, void* stream);
+int sb_s2s_beam_state_size(size_t* bytes);
+int sb_s2s_beam_init(void* state, int* nodes, int* tok_next, int start_tok, void* stream);
+int sb_s2s_beam_select(const float* logp, void* state, double* c_scores, int* nodes,
+                       int* parent_row, int* tok_next, int* out_tokens, int K, int C, int end_tok,
+                       int step, int max_len, int node_cap, int c_cap, void* stream);
+int sb_s2s_beam_gather(const float* hx_in, const float* sx_in, const float* ax_in, float* hx_out,
+                       float* sx_out, float* ax_out, const int* parent_row, const void* state,
+                       int K, int H, int T, void* stream);
 
 /* Beam expand/prune of Seq2Seq.beam_search (speech/models/seq2seq.py:200-212): indices and values
  * of the k best of n float64 scores, ordered by (score descending, index ascending) - the order of

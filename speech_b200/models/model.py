@@ -120,7 +120,7 @@ class LinearND(nn.Module):
         # time-batched projections run on the package's tcgen05 GEMM (forward and backward);
         # per-token rows of the attention decoder (a handful of rows) stay in fp32
         _lib.require_cuda(x, "LinearND input")
-        if x.numel() // x.shape[-1] >= 128:
+        if x.numel() // x.shape[-1] >= 128 and self.fc.out_features >= 8:
             return ops.linear(x, self.fc.weight, self.fc.bias)
         lead = x.shape[:-1]
         out = self.fc(x.reshape(-1, x.shape[-1]))

@@ -3,8 +3,9 @@
 
 The encoder runs on the sm_100a kernels (ops.conv_stack / ops.gru_stack).  The per-token decoder
 (embedding + GRUCell + NNAttention + fc, seq2seq.py:92-108,114-137) keeps the reference's module
-structure and state_dict names; in round 1 its small per-step ops are torch calls, the beam
-expand/prune runs on the device (ops.beam_topk) with the reference's tie order.
+structure and state_dict names (the nn modules are parameter containers); its arithmetic is two
+kernels per token, forward and backward (functions/s2s.py -> csrc/s2s.cu), and both the greedy
+loop and the beam search run device-resident: one device->host copy per decode.
 Reference quirks kept on purpose: end-padding is part of the loss (:58-63), `hx` starts at zero,
 scheduled sampling draws from Python's `random` (:94), `beam_search` handles one utterance (:197)
 and needs the py3 fix list(filter(...)) (:211) - applied here.
@@ -71,48 +72,29 @@ class Seq2Seq(model.Model):
             return self.forward_impl(x, y)[0]
 
     def decode(self, x, y):
-        """Teacher-forced decode (:78-112).  x (B, T', H); y (B, U) -> logits (B, U-1, V-1)."""
-        inputs = self.embedding(y[:, :-1])
-        out, aligns = [], []
-        hx = torch.zeros((x.shape[0], x.shape[2]), device=x.device, dtype=x.dtype)
-        ax = sx = None
-        for t in range(y.shape[1] - 1):
-            if out and self.scheduled_sampling and random.random() < self.sample_prob:
-                ix = self.embedding(torch.max(out[-1], dim=2)[1])
-            else:
-                ix = inputs[:, t:t + 1, :]
-            if sx is not None:
-                ix = ix + sx
-            hx = self.dec_rnn(ix.squeeze(dim=1), hx)
-            ox = hx.unsqueeze(dim=1)
-            sx, ax = self.attend(x, ox, ax)
-            aligns.append(ax)
-            out.append(self.fc(ox + sx))
-        return torch.cat(out, dim=1), torch.stack(aligns, dim=1)
+        """Teacher-forced decode (:78-112).  x (B, T', H); y (B, U) -> logits (B, U-1, V-1),
+        alignments (B, U-1, T').  The scheduled-sampling coin flips are drawn here from Python's
+        `random` in the reference's order (:93-94: one draw per step after the first, only while
+        sampling is on); the steps themselves run on the device."""
+        from ..functions import s2s
+        steps = y.shape[1] - 1
+        flags = [False] * max(steps, 1)
+        if self.scheduled_sampling:
+            for t in range(1, steps):
+                flags[t] = random.random() < self.sample_prob
+        return s2s.decode(self, x, y, flags)
 
     def decode_step(self, x, y, state=None, softmax=False):
         """One decoder step (:114-137).  y (B, 1) -> (logits (B, V-1), (hx, ax, sx))."""
-        if state is None:
-            hx = torch.zeros((x.shape[0], x.shape[2]), device=x.device, dtype=x.dtype)
-            ax = sx = None
-        else:
-            hx, ax, sx = state
-        ix = self.embedding(y)
-        if sx is not None:
-            ix = ix + sx
-        hx = self.dec_rnn(ix.squeeze(dim=1), hx)
-        ox = hx.unsqueeze(dim=1)
-        sx, ax = self.attend(x, ox, ax=ax)
-        out = self.fc((ox + sx).squeeze(dim=1))
-        if softmax:
-            out = nn.functional.log_softmax(out, dim=1)
-        return out, (hx, ax, sx)
+        from ..functions import s2s
+        return s2s.decode_step(self, x, y, state, softmax)
 
     def predict(self, batch):
         probs = self(batch)
         return [seq.tolist() for seq in torch.max(probs, dim=2)[1].cpu().numpy()]
 
     def infer_decode(self, x, y, end_tok, max_len):
+        """(:145-160) kept for API parity: per-step logits and the arg-max tokens."""
         probs, argmaxs, state = [], [y], None
         for _ in range(max_len):
             out, state = self.decode_step(x, y, state=state)
@@ -124,54 +106,27 @@ class Seq2Seq(model.Model):
         return torch.cat(probs), torch.cat(argmaxs, dim=1)
 
     def infer(self, batch, max_len=200):
-        """Greedy decode (:162-178): the start token, then arg-max until every row emitted end."""
+        """Greedy decode (:162-178): the start token, then arg-max until every row emitted end in
+        the same step; device-resident (functions/s2s.py: greedy)."""
+        from ..functions import s2s
         x, y = self.collate(*batch)
         end_tok = int(y[0, -1])
         x, y = self._to_dev(x, y)
         with torch.no_grad():
             x = self.encode(x)
-            _, argmaxs = self.infer_decode(x, y[:, 0:1], end_tok, max_len)
-        return [seq.tolist() for seq in argmaxs.cpu().numpy()]
+            return s2s.greedy(self, x, y[:, 0], end_tok, max_len)
 
     def beam_search(self, batch, beam_size=10, max_len=200):
-        """Beam search for ONE utterance (:180-227).  Hypothesis scores are sums of
-        log-softmax; pruning is the reference's stable descending sort, i.e. ties keep
-        (beam index, then vocabulary index) order - reproduced on the device by ops.beam_topk."""
-        from .. import ops
+        """Beam search for ONE utterance (:180-227).  Hypothesis scores are sums of log-softmax
+        (float64); pruning is the reference's stable descending sort, i.e. ties keep (beam index,
+        then vocabulary index) order; device-resident (functions/s2s.py: beam_search)."""
+        from ..functions import s2s
         x, y = self.collate(*batch)
         start_tok, end_tok = int(y[0, 0]), int(y[0, -1])
         x, y = self._to_dev(x, y)
         with torch.no_grad():
             x = self.encode(x)
-            y = y[:, 0:1].clone()
-            beam = [((start_tok,), 0.0, None)]
-            complete = []
-            for _ in range(max_len):
-                rows, scores = [], []
-                states = []
-                for hyp, score, state in beam:
-                    y[0] = hyp[-1]
-                    out, state = self.decode_step(x, y, state=state, softmax=True)
-                    rows.append(out.reshape(-1).double() + score)
-                    states.append(state)
-                cand = torch.stack(rows)                     # (beam, V-1) float64 like the ref
-                nv = cand.shape[1]
-                k = min(cand.numel(), 2 * beam_size)         # enough to fill the live beam
-                idx, val = ops.beam_topk(cand, k)
-                new_beam = [(beam[i // nv][0] + (i % nv,), v, states[i // nv])
-                            for i, v in zip(idx, val)]
-                for c in new_beam[:beam_size]:
-                    if c[0][-1] == end_tok:
-                        complete.append(c)
-                beam = [c for c in new_beam if c[0][-1] != end_tok][:beam_size]
-                if len(beam) == 0:
-                    break
-                if sum(c[1] > beam[0][1] for c in complete) >= beam_size:
-                    break
-            complete = sorted(complete, key=lambda c: c[1], reverse=True)
-            if len(complete) == 0:
-                complete = beam
-            return [complete[0][0]]
+            return [s2s.beam_search(self, x, start_tok, end_tok, beam_size, max_len)]
 
     def collate(self, inputs, labels):
         return self.stage_inputs(inputs), torch.from_numpy(end_pad_concat(labels))
@@ -194,7 +149,7 @@ class NNAttention(nn.Module):
 
     def forward(self, eh, dhx, ax=None):
         if eh.is_cuda and not torch.is_grad_enabled():
-            # decode path: fused single-pass kernel (csrc/attn.cu)
+            # stand-alone decode-path call: fused single-pass kernel (csrc/s2s.cu)
             from .. import ops
             return ops.attn_step(eh, dhx, ax, self.conv, self.nn[1].fc, self.log_t)
         pax = eh + dhx
