@@ -847,36 +847,37 @@ gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
         if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
         float own[GRU_UPT];
-        uint32_t v[KS][8];
         if (tid == 0) mbar_expect_tx(recvbar, (uint32_t)((KS - 1) * Bp * 16 * 4));
-#pragma unroll
-        for (int pr = 0; pr < KS; ++pr)
+        // the peers' slices first, each staged and sent as soon as it is complete (see
+        // gru_fwd_ks_kernel); the own slice last
+#pragma unroll 1
+        for (int q = 1; q <= KS; ++q) {
+          const uint32_t pr = (crank + (uint32_t)q) % KS;      // q == KS: own slice
+          uint32_t v[8];
           tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + pr * 16 +
-                                uh * GRU_UPT, v[pr]);
-        tmem_ld_wait();
+                                uh * GRU_UPT, v);
+          tmem_ld_wait();
+          if (q == KS) {
 #pragma unroll
-        for (int pr = 0; pr < KS; ++pr) {
-          if ((uint32_t)pr == crank) {
-#pragma unroll
-            for (int jj = 0; jj < GRU_UPT; ++jj) own[jj] = __uint_as_float(v[pr][jj]);
-          } else if (active) {
-            // stage the slice that belongs to peer `pr` (its 16 units) in local shared memory
-            float4* sp = reinterpret_cast<float4*>(stage + ((size_t)pr * Bp + row) * 16 + uh * GRU_UPT);
-            sp[0] = make_float4(__uint_as_float(v[pr][0]), __uint_as_float(v[pr][1]),
-                                __uint_as_float(v[pr][2]), __uint_as_float(v[pr][3]));
-            sp[1] = make_float4(__uint_as_float(v[pr][4]), __uint_as_float(v[pr][5]),
-                                __uint_as_float(v[pr][6]), __uint_as_float(v[pr][7]));
+            for (int jj = 0; jj < GRU_UPT; ++jj) own[jj] = __uint_as_float(v[jj]);
+          } else {
+            if (active) {
+              float4* sp = reinterpret_cast<float4*>(stage + ((size_t)pr * Bp + row) * 16 +
+                                                     uh * GRU_UPT);
+              sp[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]),
+                                  __uint_as_float(v[2]), __uint_as_float(v[3]));
+              sp[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]),
+                                  __uint_as_float(v[6]), __uint_as_float(v[7]));
+            }
+            fence_proxy_async_smem();
+            epi_barrier();
+            if (tid == 0)
+              bulk_s2peer(mapa_shared(smem_u32(recv + (size_t)crank * Bp * 16), pr),
+                          stage + (size_t)pr * Bp * 16, (uint32_t)(Bp * 16 * 4),
+                          mapa_shared(smem_u32(recvbar), pr));
           }
         }
-        fence_proxy_async_smem();     // generic st.shared -> the copy engine's (async proxy) reads
         tc_fence_before_sync();
-        epi_barrier();                // all slices staged
-        if (warp == 0 && lane < KS && (uint32_t)lane != crank) {
-          // one bulk copy per peer: my slice for it lands in ITS recv[src = my rank]
-          bulk_s2peer(mapa_shared(smem_u32(recv + (size_t)crank * Bp * 16), (uint32_t)lane),
-                      stage + (size_t)lane * Bp * 16, (uint32_t)(Bp * 16 * 4),
-                      mapa_shared(smem_u32(recvbar), (uint32_t)lane));
-        }
         if (tid == 0) GRU_STAMP(4);
         mbar_wait(recvbar, (step - 1) & 1);
 #pragma unroll
@@ -1116,43 +1117,46 @@ gru_fwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
         mbar_wait(accfull, (step - 1) & 1);
         if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
-        // ---- reduce-scatter of the four partial products: one peer's 3 x 8 columns at a time ----
+        // ---- reduce-scatter of the four partial products.  The three slices that belong to
+        // the peers go first, one at a time: TMEM -> registers -> local staging -> (named barrier)
+        // -> ONE bulk copy into the peer's receive buffer, so the first copy is in flight while
+        // the next slice is still being staged; the CTA's own slice is read last ----
         if (tid == 0) mbar_expect_tx(recvbar, (uint32_t)((KS - 1) * Bp * RW * 4));
-#pragma unroll
-        for (int pr = 0; pr < KS; ++pr) {
+#pragma unroll 1
+        for (int q = 1; q <= KS; ++q) {
+          const uint32_t pr = (crank + (uint32_t)q) % KS;      // q == KS: own slice
           uint32_t v[3][8];
 #pragma unroll
           for (int gg = 0; gg < 3; ++gg)
             tmem_ld_32x32b_x8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
                                   gg * (KS * GRU_HC) + pr * GRU_HC + uh * GRU_UPT, v[gg]);
           tmem_ld_wait();
-          if ((uint32_t)pr == crank) {
+          if (q == KS) {
 #pragma unroll
             for (int gg = 0; gg < 3; ++gg)
 #pragma unroll
               for (int jj = 0; jj < GRU_UPT; ++jj) acc[gg][jj] = __uint_as_float(v[gg][jj]);
-          } else if (active) {
-            // stage the slice that belongs to peer `pr` (gate-major 3 x 16) in local shared memory
-            float* sp = stage + ((size_t)pr * Bp + row) * RW + uh * GRU_UPT;
+          } else {
+            if (active) {
+              float* sp = stage + ((size_t)pr * Bp + row) * RW + uh * GRU_UPT;
 #pragma unroll
-            for (int gg = 0; gg < 3; ++gg) {
-              float4* q = reinterpret_cast<float4*>(sp + gg * GRU_HC);
-              q[0] = make_float4(__uint_as_float(v[gg][0]), __uint_as_float(v[gg][1]),
-                                 __uint_as_float(v[gg][2]), __uint_as_float(v[gg][3]));
-              q[1] = make_float4(__uint_as_float(v[gg][4]), __uint_as_float(v[gg][5]),
-                                 __uint_as_float(v[gg][6]), __uint_as_float(v[gg][7]));
+              for (int gg = 0; gg < 3; ++gg) {
+                float4* o = reinterpret_cast<float4*>(sp + gg * GRU_HC);
+                o[0] = make_float4(__uint_as_float(v[gg][0]), __uint_as_float(v[gg][1]),
+                                   __uint_as_float(v[gg][2]), __uint_as_float(v[gg][3]));
+                o[1] = make_float4(__uint_as_float(v[gg][4]), __uint_as_float(v[gg][5]),
+                                   __uint_as_float(v[gg][6]), __uint_as_float(v[gg][7]));
+              }
             }
+            fence_proxy_async_smem();   // generic st.shared -> the copy engine's (async proxy) reads
+            epi_barrier();              // this peer's slice is completely staged
+            if (tid == 0)
+              bulk_s2peer(mapa_shared(smem_u32(recv + (size_t)crank * Bp * RW), pr),
+                          stage + (size_t)pr * Bp * RW, (uint32_t)(Bp * RW * 4),
+                          mapa_shared(smem_u32(recvbar), pr));
           }
         }
-        fence_proxy_async_smem();     // generic st.shared -> the copy engine's (async proxy) reads
         tc_fence_before_sync();
-        epi_barrier();                // all slices staged
-        if (warp == 0 && lane < KS && (uint32_t)lane != crank) {
-          // one bulk copy per peer: my slice for it lands in ITS recv[src = my rank]
-          bulk_s2peer(mapa_shared(smem_u32(recv + (size_t)crank * Bp * RW), (uint32_t)lane),
-                      stage + (size_t)lane * Bp * RW, (uint32_t)(Bp * RW * 4),
-                      mapa_shared(smem_u32(recvbar), (uint32_t)lane));
-        }
         if (tid == 0) GRU_STAMP(4);
         mbar_wait(recvbar, (step - 1) & 1);
         if (active) {

@@ -39,6 +39,7 @@ _knobs_applied = False
 
 # ---- optional per-kernel timing (CUDA events on the launching stream; used by bench.py) ----
 _prof = None
+_prof_detail = False      # developer: one profile class per GEMM shape (tools/debug_step.py)
 
 
 def profile_begin():
@@ -104,7 +105,11 @@ def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=N
     if accumulate:
         flags |= GEMM_ACCUMULATE
     sp = _lib.stream_ptr()
-    _launch("gemm_bf16_tn", 2.0 * M * N * K,
+    name = "gemm_bf16_tn"
+    if _prof_detail:
+        name = "gemm %dx%dx%d%s%s%s" % (M, N, K, " aT" if a_mn else "", " bT" if b_mn else "",
+                                       " acc" if accumulate else "")
+    _launch(name, 2.0 * M * N * K,
             lambda: lib.sb_gemm_bf16_tn(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
                                         out.data_ptr(), out.stride(0), _lib.ptr(bias), M, N, K,
                                         flags, split_k, rB, rT, vB, sp))
@@ -516,11 +521,28 @@ def _transpose_bf16(src, rows_pad=8, out=None):
     return dst[:, :R]
 
 
+CONV_CHUNK_BYTES = 40 << 20     # patch-matrix bytes handled per launch group (stays in the 126 MB L2)
+
+
+def _conv_chunks(B, per_utt_bytes):
+    """utterances per launch group: the patch matrix of a group (bf16 forward / wgrad operand,
+    fp32 patch gradient) is produced and consumed while it is still L2-resident."""
+    nb = max(1, min(B, CONV_CHUNK_BYTES // max(per_utt_bytes, 1)))
+    return [(b0, min(B, b0 + nb)) for b0 in range(0, B, nb)]
+
+
 class ConvStackFunction(torch.autograd.Function):
     """Conv2d+ReLU stack as im2col + tcgen05 GEMM (csrc/conv.cu, csrc/gemm.cu).
 
     forward(x (B,T,F) f32, specs ((kh,kw,s),...), w0, b0, w1, b1, ...) -> (B, T', C*F') f32 with
-    the reference's channel-major feature order (model.py:66-71)."""
+    the reference's channel-major feature order (model.py:66-71).
+
+    The patch (im2col) matrix of the north-star second layer is 607 MB in bf16 and its gradient
+    1.2 GB in fp32; neither ever exists: the minibatch is processed in groups of utterances whose
+    patch matrix fits the L2 (produced by one kernel, consumed by the next), and the backward pass
+    RE-BUILDS the patches of a group from the saved layer input instead of reading a stored copy.
+    Measured on the r01 form (whole-batch matrices): 455 us im2col + 403 us transposes + 950 us
+    patch gradient + col2im, ~15x the algorithmic HBM traffic."""
 
     @staticmethod
     def forward(ctx, x, specs, dropout, *params):
@@ -546,21 +568,30 @@ class ConvStackFunction(torch.autograd.Function):
             Kp = _round_up(K, 8)
             To, Fo = (Ti - kh) // s_ + 1, (Fi - kw) // s_ + 1
             M = B * To * Fo
-            A = torch.empty(M, Kp, dtype=torch.bfloat16, device=dev)
-            src = cur
-            mprev = masks[l - 1] if l > 0 else None
-            _launch("conv_im2col", 0.0,
-                    lambda: lib.sb_conv_im2col(src.data_ptr(), _lib.ptr(mprev), mscale, A.data_ptr(), B, Ti,
-                                               Fi, Ci, kh, kw, s_, Kp, 1 if l > 0 else 0, sp))
+            rows = To * Fo                         # patch rows per utterance
             Wp = torch.zeros(Co, Kp, dtype=torch.bfloat16, device=dev)
             Wp[:, :K] = w.detach().permute(0, 2, 3, 1).reshape(Co, K)
-            C = gemm_bf16_tn(A, Wp, bias=b.detach().float().contiguous())
+            bias = b.detach().float().contiguous()
+            C = torch.empty(M, Co, dtype=torch.float32, device=dev)
+            mprev = masks[l - 1] if l > 0 else None
+            chunks = _conv_chunks(B, rows * Kp * 2)
+            A = torch.empty((chunks[0][1] - chunks[0][0]) * rows, Kp, dtype=torch.bfloat16, device=dev)
+            src = cur
+            for b0, b1 in chunks:
+                nb = b1 - b0
+                soff = b0 * Ti * Fi * Ci
+                _launch("conv_im2col", 0.0,
+                        lambda: lib.sb_conv_im2col(src.data_ptr() + 4 * soff,
+                                                   None if mprev is None else mprev.data_ptr() + soff,
+                                                   mscale, A.data_ptr(), nb, Ti, Fi, Ci, kh, kw, s_,
+                                                   Kp, 1 if l > 0 else 0, sp))
+                gemm_bf16_tn(A[:nb * rows], Wp, out=C[b0 * rows:b1 * rows], bias=bias)
             mask = None
             if dropout > 0.0:
                 mask = (torch.rand(M, Co, device=dev) >= dropout).to(torch.uint8)
             masks.append(mask)
             if need_grad:
-                saved.append((A, cur, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp)))
+                saved.append((cur, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp)))
             cur, Ti, Fi, Ci = C, To, Fo, Co
         out = torch.empty(B, Ti, Ci * Fi, dtype=torch.float32, device=dev)
         _launch("conv_relu_to_bct", 0.0,
@@ -584,8 +615,9 @@ class ConvStackFunction(torch.autograd.Function):
         dY = dY.contiguous().float()
         dC = None
         for l in reversed(range(ctx.nl)):
-            A, Pprev, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp) = ctx.saved[l]
+            Pprev, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp) = ctx.saved[l]
             M = B * To * Fo
+            rows = To * Fo
             if dC is None:
                 dC = torch.empty(M, Co, dtype=torch.bfloat16, device=dev)
                 db = torch.zeros(Co, dtype=torch.float32, device=dev)
@@ -596,25 +628,41 @@ class ConvStackFunction(torch.autograd.Function):
                                                  dCl.data_ptr(),
                                                  db.data_ptr(), B, To, Fo, Co, sp))
             grads[2 * l + 1] = db
-            # weight gradient: contraction over the M = B*To*Fo patch rows (split-K over all SMs)
-            # dWp^T [Kp][Co] = A^T dC with both operands read token-major (MN-major UMMA)
+            mprev = ctx.masks[l - 1] if l > 0 else None
+            # per group of utterances: rebuild the patches (bf16), contract them with dC for the
+            # weight gradient (dWp^T [Kp][Co] += A^T dC, both operands token-major = MN-major
+            # UMMA, split-K over all SMs), and - below the top layer - form the patch gradient
+            # dA = dC Wp (fp32) and gather it back onto the layer input (col2im + ReLU mask)
+            chunks = _conv_chunks(B, rows * Kp * (4 if l > 0 else 2))
+            nb0 = chunks[0][1] - chunks[0][0]
+            A = torch.empty(nb0 * rows, Kp, dtype=torch.bfloat16, device=dev)
             dWpT = torch.zeros(Kp, Co, dtype=torch.float32, device=dev)
-            gemm_bf16_tn(A, dC, out=dWpT, accumulate=True, a_mn=True, b_mn=True)
+            if l > 0:
+                dA = torch.empty(nb0 * rows, Kp, dtype=torch.float32, device=dev)
+                dCp = torch.empty(B * Ti * Fi, Ci, dtype=torch.bfloat16, device=dev)
+                dbp = torch.zeros(Ci, dtype=torch.float32, device=dev)
+            for b0, b1 in chunks:
+                nb = b1 - b0
+                soff = b0 * Ti * Fi * Ci
+                _launch("conv_im2col", 0.0,
+                        lambda: lib.sb_conv_im2col(Pprev.data_ptr() + 4 * soff,
+                                                   None if mprev is None else mprev.data_ptr() + soff,
+                                                   ctx.mscale, A.data_ptr(), nb, Ti, Fi, Ci, kh, kw,
+                                                   s_, Kp, 1 if l > 0 else 0, sp))
+                dCc = dC[b0 * rows:b1 * rows]
+                gemm_bf16_tn(A[:nb * rows], dCc, out=dWpT, accumulate=True, a_mn=True, b_mn=True)
+                if l > 0:
+                    gemm_bf16_tn(dCc, Wp, out=dA[:nb * rows], b_mn=True)   # patch gradient, f32
+                    _launch("conv_col2im_relu", 0.0,
+                            lambda: lib.sb_conv_col2im_relu(
+                                dA.data_ptr(), dA.stride(0), Pprev.data_ptr() + 4 * soff,
+                                None if mprev is None else mprev.data_ptr() + soff, ctx.mscale,
+                                dCp.data_ptr() + 2 * soff, dbp.data_ptr(), nb, Ti, Fi, Ci, kh, kw,
+                                s_, sp))
             dWp = dWpT.t()
             grads[2 * l] = dWp[:, :K].reshape(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
             if l > 0:
-                dA = gemm_bf16_tn(dC, Wp, b_mn=True)            # [M][Kp] f32 patch gradient
-                Mp = B * Ti * Fi
-                dCp = torch.empty(Mp, Ci, dtype=torch.bfloat16, device=dev)
-                db = torch.zeros(Ci, dtype=torch.float32, device=dev)
-                _launch("conv_col2im_relu", 0.0,
-                        lambda: lib.sb_conv_col2im_relu(dA.data_ptr(), dA.stride(0),
-                                                        Pprev.data_ptr(),
-                                                        _lib.ptr(ctx.masks[l - 1]), ctx.mscale,
-                                                        dCp.data_ptr(),
-                                                        db.data_ptr(), B, Ti, Fi, Ci, kh, kw, s_,
-                                                        sp))
-                dC = dCp
+                dC, db = dCp, dbp
         ctx.saved = None
         ctx.masks = None
         return (None, None, None) + tuple(grads)

@@ -99,7 +99,8 @@ def test_teacher_forced_decode_forward_and_backward(cuda_lib, B, T, H, V, U, log
             continue
         ref = rp[name].grad
         got = p.grad.double().cpu().reshape(ref.shape)
-        tol = 2e-2 if name.endswith("weight") and ("dec_rnn" in name or name.startswith("fc"))             else 2e-3
+        # time-batched on the tcgen05 GEMM (bf16 operands): cell weights and the output projection
+        tol = 2e-2 if name in ("dec_rnn.weight_ih", "dec_rnn.weight_hh", "fc.fc.weight") else 2e-3
         assert (got - ref).abs().max().item() < tol * ref.abs().max().item() + 1e-6, name
 
 

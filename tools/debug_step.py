@@ -25,6 +25,7 @@ x, y, xl, yl = m.collate(inputs, labels)
 x = x.cuda()
 tick("batch on gpu", t0)
 for it in range(3):
+    ops._prof_detail = (it == 2)
     ops.profile_begin()
     c = ops.conv_stack(x, m.conv, True)
     tick("conv", t0)
@@ -35,5 +36,5 @@ for it in range(3):
     tick("fc+ctc loss=%.3f" % loss.item(), t0)
     loss.backward()
     tick("backward", t0)
-    for k, v in ops.profile_end().items():
-        print("    %-14s n=%3d  %.3f ms  %.1f TFLOP/s" % (k, v[0], v[1], v[2] / 1e9 / max(v[1], 1e-9)))
+    for k, v in sorted(ops.profile_end().items(), key=lambda kv: -kv[1][1]):
+        print("    %-34s n=%3d  %.3f ms  %.1f TFLOP/s" % (k, v[0], v[1], v[2] / 1e9 / max(v[1], 1e-9)))
