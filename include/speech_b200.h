@@ -95,6 +95,14 @@ int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bhh, float* y
                float* gates, void* workspace, size_t workspace_bytes, int T, int Bp, int H,
                int ndir, void* stream);
 
+/* "Parity mode" forward recurrence: the same time loop in plain fp32 on CUDA cores (fp32 weights
+ * [ndir][3H][H], fp32 state, no bf16 rounding anywhere), csrc/gru_f32.cu.  It exists to measure
+ * the bf16 tensor-core path against, not to be fast.
+ *   barrier: ndir u32 words (zeroed by the call).  Constraints: H % 4 == 0, Bp <= 128,
+ *   H/8 <= number of SMs. */
+int sb_gru_fwd_f32(const float* gi, const float* whh_f32, const float* bhh, float* y,
+                   unsigned int* barrier, int T, int Bp, int H, int ndir, void* stream);
+
 /* Backward through the recurrence.
  *   dy     [T*Bp][ndir*H] f32  gradient w.r.t. y
  *   whh    [ndir][3H][H] bf16  recurrent weights as stored (the same operand sb_gru_fwd takes;

@@ -39,6 +39,10 @@ class CTC(model.Model):
         bf16 top-layer output (same math as model.py:75-77 followed by ctc_model.py:29)."""
         from .. import _lib, ops
         _lib.require_cuda(x, "forward_impl() input")
+        if getattr(self, "parity_mode", False) and not torch.is_grad_enabled():
+            # reference-precision forward (split-bf16 GEMMs, fp32 recurrence): a measuring stick
+            # for the bf16 operand path, see ops.encode_logits_parity
+            return ops.encode_logits_parity(x, self.conv, self.rnn, self.fc.fc)
         x = ops.conv_stack(x, self.conv, self.training)
         p = self.rnn.dropout if self.training else 0.0
         return ops.gru_stack_logits(x, self.rnn, self.fc.fc, dropout=p)

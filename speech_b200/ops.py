@@ -116,6 +116,98 @@ def gemm_bf16_tn(A, B, out=None, bias=None, accumulate=False, split_k=1, remap=N
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# "Parity mode" (SURVEY.md section 7): the forward pass of the encoder in reference precision, to
+# measure the bf16 tensor-core path against.  Dense contractions run as 3-pass split-bf16 GEMMs
+# (x = hi + lo with hi = bf16(x), lo = bf16(x - hi): hi*hi + hi*lo + lo*hi on the tensor cores,
+# relative error ~2^-16), the recurrence in plain fp32 (csrc/gru_f32.cu).  No autograd.
+# ------------------------------------------------------------------------------------------------
+def _split_bf16(t, Kp):
+    t = t.detach().float()
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    if Kp != t.shape[1]:
+        hi = torch.nn.functional.pad(hi, (0, Kp - t.shape[1]))
+        lo = torch.nn.functional.pad(lo, (0, Kp - t.shape[1]))
+    return hi.contiguous(), lo.contiguous()
+
+
+def gemm_split(A, B, bias=None, remap=None):
+    """A (M,K) f32 @ B (N,K)^T f32 -> (M,N) f32 with split-bf16 operands (3 tensor-core passes)."""
+    Kp = _round_up(A.shape[1], 8)
+    a_hi, a_lo = _split_bf16(A, Kp)
+    b_hi, b_lo = _split_bf16(B, Kp)
+    out = gemm_bf16_tn(a_hi, b_hi, bias=bias, remap=remap)
+    gemm_bf16_tn(a_hi, b_lo, out=out, accumulate=True, remap=remap)
+    gemm_bf16_tn(a_lo, b_hi, out=out, accumulate=True, remap=remap)
+    return out
+
+
+def encode_logits_parity(x, conv, rnn, fc):
+    """Reference-precision forward of conv stack -> GRU stack -> halves-sum -> fc (no grad):
+    x (B,T,F) -> logits (B,T',V).  Same kernels' layouts, split-bf16 GEMMs, fp32 recurrence."""
+    _lib.require_cuda(x, "x")
+    lib = _lib.load()
+    dev = x.device
+    B, Ti, Fi = x.shape
+    sp = _lib.stream_ptr()
+    cur = x.detach().float().contiguous()              # (B, Ti, Fi, Ci) channels-last, Ci = 1
+    Ci = 1
+    for l, c in enumerate(m for m in conv.children() if isinstance(m, torch.nn.Conv2d)):
+        kh, kw, s_ = c.kernel_size[0], c.kernel_size[1], c.stride[0]
+        Co = c.out_channels
+        K = kh * kw * Ci
+        Kp = _round_up(K, 8)
+        To, Fo = (Ti - kh) // s_ + 1, (Fi - kw) // s_ + 1
+        M = B * To * Fo
+        r = cur if l == 0 else torch.relu(cur)
+        r_hi = r.to(torch.bfloat16).float()
+        parts = []
+        for src in (r_hi, r - r_hi):                   # im2col of the hi and lo halves (exact)
+            A = torch.empty(M, Kp, dtype=torch.bfloat16, device=dev)
+            _launch("conv_im2col", 0.0,
+                    lambda: lib.sb_conv_im2col(src.data_ptr(), None, 1.0, A.data_ptr(), B, Ti, Fi,
+                                               Ci, kh, kw, s_, Kp, 0, sp))
+            parts.append(A)
+        W = torch.zeros(Co, Kp, dtype=torch.float32, device=dev)
+        W[:, :K] = c.weight.detach().float().permute(0, 2, 3, 1).reshape(Co, K)
+        w_hi, w_lo = _split_bf16(W, Kp)
+        C = gemm_bf16_tn(parts[0], w_hi, bias=c.bias.detach().float().contiguous())
+        gemm_bf16_tn(parts[0], w_lo, out=C, accumulate=True)
+        gemm_bf16_tn(parts[1], w_hi, out=C, accumulate=True)
+        cur, Ti, Fi, Ci = C, To, Fo, Co
+    feats = torch.empty(B, Ti, Ci * Fi, dtype=torch.float32, device=dev)
+    _launch("conv_relu_to_bct", 0.0,
+            lambda: lib.sb_conv_relu_to_bct(cur.data_ptr(), None, 1.0, feats.data_ptr(), B, Ti, Fi,
+                                            Ci, sp))
+    ndir, weights = _gru_weights(rnn)
+    H = rnn.hidden_size
+    T = Ti
+    Bp = _round_up(B, 8)
+    M = T * Bp
+    X = torch.zeros(T, Bp, feats.shape[2], dtype=torch.float32, device=dev)
+    X[:, :B] = feats.transpose(0, 1)
+    X = X.view(M, -1)
+    barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+    for l in range(rnn.num_layers):
+        wl = weights[l * 4 * ndir:(l + 1) * 4 * ndir]
+        w_ih = torch.cat([wl[d * 4].detach().float() for d in range(ndir)])
+        b_ih = torch.cat([wl[d * 4 + 2].detach().float() for d in range(ndir)]).contiguous()
+        w_hh = torch.stack([wl[d * 4 + 1].detach().float() for d in range(ndir)]).contiguous()
+        b_hh = torch.stack([wl[d * 4 + 3].detach().float() for d in range(ndir)]).contiguous()
+        gi = gemm_split(X, w_ih, bias=b_ih)
+        y = torch.empty(M, ndir * H, dtype=torch.float32, device=dev)
+        _launch("gru_fwd_f32", 2.0 * M * 3 * H * H * ndir,
+                lambda: lib.sb_gru_fwd_f32(gi.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
+                                           y.data_ptr(), barrier.data_ptr(), T, Bp, H, ndir, sp))
+        X = y
+    w = fc.weight.detach().float()
+    wcat = torch.cat([w, w], 1) if ndir == 2 else w
+    V = w.shape[0]
+    return gemm_split(X, wcat, bias=fc.bias.detach().float().contiguous(),
+                      remap=(Bp, T, B)).view(B, T, V)
+
+
 class LinearFunction(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 GEMM (bf16 operands, fp32 accumulate), forward and backward:
     the arithmetic behind the reference's LinearND / nn.Linear (model.py:115-133).
@@ -521,28 +613,11 @@ def _transpose_bf16(src, rows_pad=8, out=None):
     return dst[:, :R]
 
 
-CONV_CHUNK_BYTES = 40 << 20     # patch-matrix bytes handled per launch group (stays in the 126 MB L2)
-
-
-def _conv_chunks(B, per_utt_bytes):
-    """utterances per launch group: the patch matrix of a group (bf16 forward / wgrad operand,
-    fp32 patch gradient) is produced and consumed while it is still L2-resident."""
-    nb = max(1, min(B, CONV_CHUNK_BYTES // max(per_utt_bytes, 1)))
-    return [(b0, min(B, b0 + nb)) for b0 in range(0, B, nb)]
-
-
 class ConvStackFunction(torch.autograd.Function):
     """Conv2d+ReLU stack as im2col + tcgen05 GEMM (csrc/conv.cu, csrc/gemm.cu).
 
     forward(x (B,T,F) f32, specs ((kh,kw,s),...), w0, b0, w1, b1, ...) -> (B, T', C*F') f32 with
-    the reference's channel-major feature order (model.py:66-71).
-
-    The patch (im2col) matrix of the north-star second layer is 607 MB in bf16 and its gradient
-    1.2 GB in fp32; neither ever exists: the minibatch is processed in groups of utterances whose
-    patch matrix fits the L2 (produced by one kernel, consumed by the next), and the backward pass
-    RE-BUILDS the patches of a group from the saved layer input instead of reading a stored copy.
-    Measured on the r01 form (whole-batch matrices): 455 us im2col + 403 us transposes + 950 us
-    patch gradient + col2im, ~15x the algorithmic HBM traffic."""
+    the reference's channel-major feature order (model.py:66-71)."""
 
     @staticmethod
     def forward(ctx, x, specs, dropout, *params):
@@ -568,30 +643,21 @@ class ConvStackFunction(torch.autograd.Function):
             Kp = _round_up(K, 8)
             To, Fo = (Ti - kh) // s_ + 1, (Fi - kw) // s_ + 1
             M = B * To * Fo
-            rows = To * Fo                         # patch rows per utterance
+            A = torch.empty(M, Kp, dtype=torch.bfloat16, device=dev)
+            src = cur
+            mprev = masks[l - 1] if l > 0 else None
+            _launch("conv_im2col", 0.0,
+                    lambda: lib.sb_conv_im2col(src.data_ptr(), _lib.ptr(mprev), mscale, A.data_ptr(), B, Ti,
+                                               Fi, Ci, kh, kw, s_, Kp, 1 if l > 0 else 0, sp))
             Wp = torch.zeros(Co, Kp, dtype=torch.bfloat16, device=dev)
             Wp[:, :K] = w.detach().permute(0, 2, 3, 1).reshape(Co, K)
-            bias = b.detach().float().contiguous()
-            C = torch.empty(M, Co, dtype=torch.float32, device=dev)
-            mprev = masks[l - 1] if l > 0 else None
-            chunks = _conv_chunks(B, rows * Kp * 2)
-            A = torch.empty((chunks[0][1] - chunks[0][0]) * rows, Kp, dtype=torch.bfloat16, device=dev)
-            src = cur
-            for b0, b1 in chunks:
-                nb = b1 - b0
-                soff = b0 * Ti * Fi * Ci
-                _launch("conv_im2col", 0.0,
-                        lambda: lib.sb_conv_im2col(src.data_ptr() + 4 * soff,
-                                                   None if mprev is None else mprev.data_ptr() + soff,
-                                                   mscale, A.data_ptr(), nb, Ti, Fi, Ci, kh, kw, s_,
-                                                   Kp, 1 if l > 0 else 0, sp))
-                gemm_bf16_tn(A[:nb * rows], Wp, out=C[b0 * rows:b1 * rows], bias=bias)
+            C = gemm_bf16_tn(A, Wp, bias=b.detach().float().contiguous())
             mask = None
             if dropout > 0.0:
                 mask = (torch.rand(M, Co, device=dev) >= dropout).to(torch.uint8)
             masks.append(mask)
             if need_grad:
-                saved.append((cur, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp)))
+                saved.append((A, cur, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp)))
             cur, Ti, Fi, Ci = C, To, Fo, Co
         out = torch.empty(B, Ti, Ci * Fi, dtype=torch.float32, device=dev)
         _launch("conv_relu_to_bct", 0.0,
@@ -615,9 +681,8 @@ class ConvStackFunction(torch.autograd.Function):
         dY = dY.contiguous().float()
         dC = None
         for l in reversed(range(ctx.nl)):
-            Pprev, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp) = ctx.saved[l]
+            A, Pprev, C, Wp, (Ti, Fi, Ci, kh, kw, s_, To, Fo, Co, K, Kp) = ctx.saved[l]
             M = B * To * Fo
-            rows = To * Fo
             if dC is None:
                 dC = torch.empty(M, Co, dtype=torch.bfloat16, device=dev)
                 db = torch.zeros(Co, dtype=torch.float32, device=dev)
@@ -628,41 +693,25 @@ class ConvStackFunction(torch.autograd.Function):
                                                  dCl.data_ptr(),
                                                  db.data_ptr(), B, To, Fo, Co, sp))
             grads[2 * l + 1] = db
-            mprev = ctx.masks[l - 1] if l > 0 else None
-            # per group of utterances: rebuild the patches (bf16), contract them with dC for the
-            # weight gradient (dWp^T [Kp][Co] += A^T dC, both operands token-major = MN-major
-            # UMMA, split-K over all SMs), and - below the top layer - form the patch gradient
-            # dA = dC Wp (fp32) and gather it back onto the layer input (col2im + ReLU mask)
-            chunks = _conv_chunks(B, rows * Kp * (4 if l > 0 else 2))
-            nb0 = chunks[0][1] - chunks[0][0]
-            A = torch.empty(nb0 * rows, Kp, dtype=torch.bfloat16, device=dev)
+            # weight gradient: contraction over the M = B*To*Fo patch rows (split-K over all SMs)
+            # dWp^T [Kp][Co] = A^T dC with both operands read token-major (MN-major UMMA)
             dWpT = torch.zeros(Kp, Co, dtype=torch.float32, device=dev)
-            if l > 0:
-                dA = torch.empty(nb0 * rows, Kp, dtype=torch.float32, device=dev)
-                dCp = torch.empty(B * Ti * Fi, Ci, dtype=torch.bfloat16, device=dev)
-                dbp = torch.zeros(Ci, dtype=torch.float32, device=dev)
-            for b0, b1 in chunks:
-                nb = b1 - b0
-                soff = b0 * Ti * Fi * Ci
-                _launch("conv_im2col", 0.0,
-                        lambda: lib.sb_conv_im2col(Pprev.data_ptr() + 4 * soff,
-                                                   None if mprev is None else mprev.data_ptr() + soff,
-                                                   ctx.mscale, A.data_ptr(), nb, Ti, Fi, Ci, kh, kw,
-                                                   s_, Kp, 1 if l > 0 else 0, sp))
-                dCc = dC[b0 * rows:b1 * rows]
-                gemm_bf16_tn(A[:nb * rows], dCc, out=dWpT, accumulate=True, a_mn=True, b_mn=True)
-                if l > 0:
-                    gemm_bf16_tn(dCc, Wp, out=dA[:nb * rows], b_mn=True)   # patch gradient, f32
-                    _launch("conv_col2im_relu", 0.0,
-                            lambda: lib.sb_conv_col2im_relu(
-                                dA.data_ptr(), dA.stride(0), Pprev.data_ptr() + 4 * soff,
-                                None if mprev is None else mprev.data_ptr() + soff, ctx.mscale,
-                                dCp.data_ptr() + 2 * soff, dbp.data_ptr(), nb, Ti, Fi, Ci, kh, kw,
-                                s_, sp))
+            gemm_bf16_tn(A, dC, out=dWpT, accumulate=True, a_mn=True, b_mn=True)
             dWp = dWpT.t()
             grads[2 * l] = dWp[:, :K].reshape(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
             if l > 0:
-                dC, db = dCp, dbp
+                dA = gemm_bf16_tn(dC, Wp, b_mn=True)            # [M][Kp] f32 patch gradient
+                Mp = B * Ti * Fi
+                dCp = torch.empty(Mp, Ci, dtype=torch.bfloat16, device=dev)
+                db = torch.zeros(Ci, dtype=torch.float32, device=dev)
+                _launch("conv_col2im_relu", 0.0,
+                        lambda: lib.sb_conv_col2im_relu(dA.data_ptr(), dA.stride(0),
+                                                        Pprev.data_ptr(),
+                                                        _lib.ptr(ctx.masks[l - 1]), ctx.mscale,
+                                                        dCp.data_ptr(),
+                                                        db.data_ptr(), B, Ti, Fi, Ci, kh, kw, s_,
+                                                        sp))
+                dC = dCp
         ctx.saved = None
         ctx.masks = None
         return (None, None, None) + tuple(grads)

@@ -85,3 +85,41 @@ def test_all_parameter_gradients_at_northstar_depth(cuda_lib):
     worst_cos = min(r[2] for r in rows)
     assert worst_cos > 0.999, rows
     assert worst_rel < 5e-2, rows
+
+
+def test_parity_mode_loss_matches_fp32_reference_at_northstar_depth(cuda_lib):
+    """`model.parity_mode = True` (inference only): split-bf16 3-pass GEMMs + the fp32 recurrence
+    kernel (csrc/gru_f32.cu).  The CTC loss of the north-star model must then agree with the fp32
+    CPU reference to 1e-5 relative and the logits to 5e-4 absolute - the bf16 operand path is
+    held to 1e-4 / ~1e-2; this is the measuring stick SURVEY.md section 7 asks for."""
+    import bench
+    m, ref, inputs, labels = _northstar(4)
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    x = torch.from_numpy(np.stack(inputs))
+    flat = torch.tensor([t for l in labels for t in l], dtype=torch.int32)
+    lens = torch.tensor([len(l) for l in labels], dtype=torch.int32)
+    with torch.no_grad():
+        ref_logits = ref.logits(x)
+        ref_loss = float(ref.loss(x, flat, lens).item())
+    m.cuda()
+    m.set_eval()
+    batch = (tuple(inputs), tuple(labels))
+    with torch.no_grad():
+        bf16_logits = m(batch)
+        bf16_loss = float(m.loss(batch).item())
+        m.parity_mode = True
+        par_logits = m(batch)
+        par_loss = float(m.loss(batch).item())
+    e_bf16 = (bf16_logits.cpu() - ref_logits).abs().max().item()
+    e_par = (par_logits.cpu() - ref_logits).abs().max().item()
+    d = os.path.join(ROOT, "gpurun_out")
+    msg = ("north-star model, 4 utterances: |logits - fp32 ref| max: bf16 path %.3e, parity mode %.3e; "
+           "CTC loss rel delta: bf16 path %.3e, parity mode %.3e"
+           % (e_bf16, e_par, abs(bf16_loss - ref_loss) / ref_loss, abs(par_loss - ref_loss) / ref_loss))
+    print(msg)
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_mode.txt"), "w") as fh:
+            fh.write(msg + "\n")
+    assert e_par < 5e-4, msg
+    assert abs(par_loss - ref_loss) / ref_loss < 1e-5, msg
+    assert abs(bf16_loss - ref_loss) / ref_loss < 1e-4, msg
