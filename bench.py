@@ -355,6 +355,7 @@ def run_ours(args):
     # gradient must equal the single-rank gradient of the global batch ----
     dp = dp_check(model, opt, dev, world, rank) if world > 1 else None
     weak = weak_scaling(model, opt, world, rank, dev, timed) if world > 1 else None
+    rnnt_dp = rnnt_dp_measurement(world, rank, timed) if world in (2, 4) else None
 
     if rank == 0:
         utt = GLOBAL_B * args.steps
@@ -417,6 +418,8 @@ def run_ours(args):
             line["dp_check"] = dp
         if weak is not None:
             line["secondary"] = {"weak_scaling": weak}
+        if rnnt_dp is not None:
+            line["secondary"]["rnnt_dp"] = rnnt_dp
         if world == 1 and not args.no_secondary:
             line["secondary"] = secondary_measurements(model, batch, dev)
         if world == 1 and not args.no_cpu_baseline:
@@ -481,6 +484,31 @@ def dp_check(model, opt, dev, world, rank):
     return out
 
 
+def rnnt_dp_measurement(world, rank, timed):
+    """BASELINE.json configs[4] data-parallel: the B=32 RNN-T minibatch sharded over the ranks,
+    gradients all-reduced by FlatSGD (same machinery as the headline step)."""
+    from speech_b200 import ops
+    from speech_b200.optim import FlatSGD
+    per = 32 // world
+    m, batch = rnnt_workload(per, rank * per)
+    m.set_train()
+    ops.set_grad_ready_hook(None)
+    opt = FlatSGD(m, lr=1e-4, momentum=0.0, max_grad_norm=200.0, world_size=world)
+
+    def step():
+        opt.zero_grad()
+        loss = m.loss(batch)
+        loss.backward()
+        opt.step()
+        return loss
+
+    steps = 3
+    ms = timed(step, steps, 2)
+    ops.set_grad_ready_hook(None)
+    return {"global_batch": 32, "world": world, "ms_per_step": ms / steps,
+            "utt_per_s": 32 * steps / (ms * 1e-3)}
+
+
 def weak_scaling(model, opt, world, rank, dev, timed):
     """N > 1 only: B=64 per rank (global batch 64 N), same step otherwise: shows the gradient
     all-reduce overlap separately from the chain-bound strong-scaling number."""
@@ -539,6 +567,20 @@ def secondary_measurements(model, batch, dev):
     # lr 1e-3 drive the recurrent weights up, which amplifies the bf16 operand rounding) ----
     t_ours, t_ref, _, _, _ = loss_pair(model)
     out["ctc_loss_rel_delta_after_timed_steps"] = abs(t_ours - t_ref) / abs(t_ref)
+    # ---- the same loss in PARITY MODE (split-bf16 GEMMs + fp32 recurrence, inference only): the
+    # measuring stick for the bf16 operand path, on the trained weights as well ----
+    for tag, mm in (("seed0", None), ("after_timed_steps", model)):
+        if mm is None:
+            torch.manual_seed(0)
+            mm = CTC(F_IN, VOCAB, MODEL_CFG).cuda()
+        was = mm.training
+        mm.set_eval()
+        mm.parity_mode = True
+        p_ours, p_ref, _, _, _ = loss_pair(mm)
+        mm.parity_mode = False
+        if was:
+            mm.set_train()
+        out["ctc_loss_rel_delta_parity_mode_" + tag] = abs(p_ours - p_ref) / abs(p_ref)
     # ---- kernel-only delta on our logits ----
     lg = logits.detach().double().cpu()
     lp = torch.log_softmax(lg, 2).transpose(0, 1)
@@ -605,7 +647,106 @@ def secondary_measurements(model, batch, dev):
                                      "features out"}
     except Exception as e:      # never let a secondary number take the bench line down
         out["featuriser"] = {"error": repr(e)}
+    try:
+        out["other_configs"] = other_config_measurements(dev)
+    except Exception as e:
+        out["other_configs"] = {"error": repr(e)}
     return out
+
+
+def _time_train_steps(m, batch, steps=3, warm=2):
+    """utt/s of zero_grad -> loss -> backward -> clip + SGD on one GPU (device events)"""
+    from speech_b200.optim import FlatSGD
+    m.set_train()
+    opt = FlatSGD(m, lr=1e-4, momentum=0.0, max_grad_norm=200.0)
+
+    def step():
+        opt.zero_grad()
+        loss = m.loss(batch)
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "utt_per_s": len(batch[0]) / (ms * 1e-3), "loss": float(loss.item())}
+
+
+WSJ_CONV = [[32, 5, 8, 2], [32, 5, 8, 2]]
+
+
+def other_config_measurements(dev):
+    """The other workloads BASELINE.json `configs` names (synthetic data, random-init weights,
+    1 GPU; outside the timed regions of the headline metric):
+      [1] TIMIT CTC: 4-layer biGRU-512, 80 features, 61 phones, B=32 (training step)
+      [3] WSJ attention model: conv + 3x biGRU-512 encoder (training step B=16; greedy and beam-8
+          decode through the device-resident loops)
+      [4] RNN-Transducer: 3x biGRU-1024 encoder + GRU-1024 prediction net (the reference class
+          ties both dims, transducer_model.py:20-25), B=32, fused joint + lattice loss"""
+    from speech_b200.models import CTC, Seq2Seq, Transducer
+    out = {}
+    rng = np.random.RandomState(2)
+    # ---- configs[1]: TIMIT CTC ----
+    torch.manual_seed(0)
+    cfg = {"dropout": 0.0, "encoder": {"conv": WSJ_CONV,
+                                       "rnn": {"dim": 512, "bidirectional": True, "layers": 4}}}
+    m = CTC(F_IN, 61, cfg).cuda()
+    batch = (tuple(rng.randn(300, F_IN).astype(np.float32) for _ in range(32)),
+             tuple(rng.randint(0, 61, size=rng.randint(20, 40)).tolist() for _ in range(32)))
+    out["timit_ctc_bigru512x4_B32_T300"] = _time_train_steps(m, batch)
+    del m
+    # ---- configs[3]: WSJ attention model ----
+    torch.manual_seed(0)
+    cfg = {"dropout": 0.0, "encoder": {"conv": WSJ_CONV,
+                                       "rnn": {"dim": 512, "bidirectional": True, "layers": 3}},
+           "decoder": {"embedding_dim": 512, "layers": 1, "log_t": True}}
+    V = 32
+    m = Seq2Seq(F_IN, V, cfg).cuda()
+    lab = lambda: [V - 1] + rng.randint(0, V - 2, size=rng.randint(60, 100)).tolist() + [V - 2]
+    batch = (tuple(rng.randn(800, F_IN).astype(np.float32) for _ in range(16)),
+             tuple(lab() for _ in range(16)))
+    res = _time_train_steps(m, batch)
+    m.set_eval()
+    m.infer(batch, max_len=100)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m.infer(batch, max_len=100)
+    torch.cuda.synchronize()
+    res["greedy_decode_utt_per_s_B16_100steps"] = 16 / (time.perf_counter() - t0)
+    one = ((batch[0][0],), (batch[1][0],))
+    m.beam_search(one, beam_size=8, max_len=100)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for e in range(4):
+        m.beam_search(((batch[0][e],), (batch[1][e],)), beam_size=8, max_len=100)
+    torch.cuda.synchronize()
+    res["beam8_decode_utt_per_s_100steps"] = 4 / (time.perf_counter() - t0)
+    out["wsj_seq2seq_bigru512x3_B16_T800"] = res
+    del m
+    # ---- configs[4]: RNN-Transducer ----
+    out["rnnt_bigru1024x3_pred1024_B32_T1000"] = _time_train_steps(*rnnt_workload(32, 0))
+    return out
+
+
+def rnnt_workload(nutt, first):
+    """(model, batch) of the RNN-T configuration, utterances first .. first+nutt of a B=32 batch"""
+    from speech_b200.models import Transducer
+    torch.manual_seed(0)
+    cfg = {"dropout": 0.0, "encoder": {"conv": WSJ_CONV,
+                                       "rnn": {"dim": 1024, "bidirectional": True, "layers": 3}},
+           "decoder": {"embedding_dim": 256, "layers": 1}}
+    m = Transducer(F_IN, VOCAB, cfg).cuda()
+    rng = np.random.RandomState(3)
+    inputs = [rng.randn(T_IN, F_IN).astype(np.float32) for _ in range(32)]
+    labels = [rng.randint(0, VOCAB, size=rng.randint(40, 100)).tolist() for _ in range(32)]
+    return m, (tuple(inputs[first:first + nutt]), tuple(labels[first:first + nutt]))
 
 
 def main():
