@@ -1060,6 +1060,7 @@ gru_fwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
         const int tp = dir == 0 ? t - 1 : t + 1;
         grid_wait(ctr, (unsigned int)nC * step);       // all CTAs published h_{tp}
         GRU_STAMP(0);
+        if (p.dbg && step == 21) p.dbg[1024 + 256 + blockIdx.x] = gtime();   // skew probe
         mbar_expect_tx(full, (uint32_t)(stride * nchunks));
         for (int c = 0; c < nchunks; ++c)
           tma_load_2d(ring + c * stride, tm, full, (int)crank * KQ + c * 64, tp * Bp);
@@ -1194,6 +1195,7 @@ gru_fwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
       epi_barrier();
       if (tid == 0) {
         GRU_STAMP(7);
+        if (p.dbg && step == 20) p.dbg[1024 + blockIdx.x] = gtime();         // skew probe
         grid_arrive(ctr);
         GRU_STAMP(9);
       }
