@@ -1,0 +1,8 @@
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
+tail -c 400 gpurun_out/bench_n8.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_n8.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches')}, 'e2e', d['e2e']['value'])
+print(d.get('dp_check')); print(d.get('secondary'))
+PY
