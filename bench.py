@@ -69,9 +69,9 @@ def synth_batch(nutt, seed=0):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the committed
-# `ncu --set full` captures of this same workload (profiles/r01_summary.md; B=64 per GPU)
-NCU_TRAFFIC_BYTES = {"gru_bwd": 795.84e6 + 406.26e6, "gru_fwd": 406.82e6 + 725.97e6,
-                     "gemm_bf16_tn": 124.46e6 + 343.93e6, "ctc_fwd_bwd": 3.13e6}
+# `ncu --set full` captures of this same workload (profiles/r02_summary.md; B=64 per GPU)
+NCU_TRAFFIC_BYTES = {"gru_bwd": 793.56e6 + 215.58e6, "gru_fwd": 409.71e6 + 661.25e6,
+                     "gemm_bf16_tn": 172.35e6 + 353.05e6, "ctc_fwd_bwd": 3.13e6}
 
 
 def flops_per_step(nutt):
@@ -388,7 +388,7 @@ def run_ours(args):
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "traffic": NCU_TRAFFIC_BYTES.get(dom) if nutt == GLOBAL_B else None,
-                    "traffic_source": "profiles/r01_summary.md (ncu --set full, bytes per launch)",
+                    "traffic_source": "profiles/r02_summary.md (ncu --set full, bytes per launch)",
                     "peak_source": peak_src,
                     "avg_launch_ms": ms / n if n else None,
                     "note": "per-step latency-bound recurrence (see DESIGN.md 4.2): tensor pipe "

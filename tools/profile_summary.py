@@ -3,7 +3,7 @@
 import collections, csv, io, subprocess, sys
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
 out = []
-out.append("# Round 1 profile summaries (1x B200, Nsight Compute, `--clock-control none`)\n")
+out.append("# Round %s profile summaries (1x B200, Nsight Compute, `--clock-control none`)\n" % R[1:].lstrip("0"))
 out.append("Launch list: `ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv "
            "--log-file gpurun_out/launches_%s.csv python bench.py --profile --steps 1 --warmup 1` "
            "(ONE full training step of the north-star config: B=64, T=1000, F=80, conv [[32,5,8,2]]x2, 5x biGRU-1024; "
@@ -40,9 +40,14 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__grid_size", "launch__cluster_dim_x", "launch__shared_mem_per_block_dynamic",
         "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__cycles_elapsed.max"]
-for k in ["gru_bwd_ks_kernel", "gru_fwd_kernel", "gemm_bf16_tn_pair_kernel", "gemm_bf16_tn_kernel",
-          "ctc_fwd_bwd_kernel"]:
+        "sm__cycles_elapsed.max", "sm__inst_executed_pipe_xu.sum", "smsp__inst_executed.sum"]
+KERNELS = {"r01": ["gru_bwd_ks_kernel", "gru_fwd_kernel", "gemm_bf16_tn_pair_kernel",
+                   "gemm_bf16_tn_kernel", "ctc_fwd_bwd_kernel"]}.get(
+    R, ["gru_fwd_ks_kernel", "gru_bwd_ks_kernel", "gemm_bf16_tn_pair_kernel", "im2col_kernel",
+        "col2im_relu_kernel", "ctc_fwd_bwd_kernel", "sgd_clip_step_kernel", "joint_kernel",
+        "rnnt_fwd_bwd_kernel", "rnnt_decode_static_kernel", "s2s_cell_fwd_kernel",
+        "s2s_attn_fwd_kernel", "s2s_attn_bwd_kernel", "s2s_cell_bwd_kernel"])
+for k in KERNELS:
     txt = subprocess.run(["ncu", "-i", "gpurun_out/prof_%s_%s.ncu-rep" % (R, k), "--page", "raw", "--csv"],
                          capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(txt)))
@@ -51,10 +56,10 @@ for k in ["gru_bwd_ks_kernel", "gru_fwd_kernel", "gemm_bf16_tn_pair_kernel", "ge
     h, u, v = rr[0], rr[1], rr[2]
     kname = v[h.index("Kernel Name")] if "Kernel Name" in h else k
     out.append("## `%s` - one launch, `ncu --set full --import-source on -k regex:%s -c 1`\n" % (kname[:90], k))
-    if k == "gemm_bf16_tn_kernel":
+    if k == "gemm_bf16_tn_kernel" and R == "r01":
         out.append("(capture of the single-CTA 128x256 kernel taken BEFORE the CTA-pair kernel replaced it on "
                    "the large GEMMs; kept for comparison - same shape class, gi of layer 1.)\n")
-    if k == "ctc_fwd_bwd_kernel":
+    if k == "ctc_fwd_bwd_kernel" and R == "r01":
         out.append("(capture from the earlier profiling pass of this round; the kernel has not changed since.)\n")
     out.append("| metric | value |\n|---|---|")
     for w in want:
