@@ -314,7 +314,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   tc_fence_after_sync();
   cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   const uint32_t tmem_base = *s.tmem_slot;
-  unsigned int* ctr = p.barrier + dir;
+  unsigned int* ctr = p.barrier + dir * 32;   // one L2 line per direction
 
   if (warp == 9) {
     // ===================== TMA producer =====================
@@ -502,7 +502,7 @@ gru_bwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
   tc_fence_after_sync();
   cluster_sync_all();
   const uint32_t tmem_base = *s.tmem_slot;
-  unsigned int* ctr = p.barrier + dir;
+  unsigned int* ctr = p.barrier + dir * 32;   // one L2 line per direction
 
   if (warp == 9) {
     if (lane == 0) {
@@ -775,7 +775,7 @@ gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
   tc_fence_after_sync();
   cluster_sync_all();
   const uint32_t tmem_base = *tmem_slot;
-  unsigned int* ctr = p.barrier + dir;
+  unsigned int* ctr = p.barrier + dir * 32;   // one L2 line per direction
 
   if (warp == 9) {
     if (lane == 0) {
@@ -1053,7 +1053,7 @@ gru_fwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
   tc_fence_after_sync();
   cluster_sync_all();
   const uint32_t tmem_base = *tmem_slot;
-  unsigned int* ctr = p.barrier + dir;
+  unsigned int* ctr = p.barrier + dir * 32;   // one L2 line per direction
 
   if (warp == 9) {
     // ===================== TMA producer: this CTA's K quarter of h_{t-1} =====================
