@@ -10,7 +10,6 @@ Reference quirks kept on purpose: end-padding is part of the loss (:58-63), `hx`
 scheduled sampling draws from Python's `random` (:94), `beam_search` handles one utterance (:197)
 and needs the py3 fix list(filter(...)) (:211) - applied here.
 """
-import math
 import random
 
 import numpy as np
@@ -148,16 +147,11 @@ class NNAttention(nn.Module):
         self.log_t = log_t
 
     def forward(self, eh, dhx, ax=None):
-        if eh.is_cuda and not torch.is_grad_enabled():
-            # stand-alone decode-path call: fused single-pass kernel (csrc/s2s.cu)
-            from .. import ops
-            return ops.attn_step(eh, dhx, ax, self.conv, self.nn[1].fc, self.log_t)
-        pax = eh + dhx
-        if ax is not None:
-            pax = pax + self.conv(ax.unsqueeze(dim=1)).transpose(1, 2)
-        pax = self.nn(pax).squeeze(dim=2)
-        if self.log_t:
-            pax = math.log(pax.shape[1]) * pax
-        ax = nn.functional.softmax(pax, dim=1)
-        sx = torch.sum(eh * ax.unsqueeze(2), dim=1, keepdim=True)
-        return sx, ax
+        """(sx (B,1,H), ax (B,T)) of one attention step on the fused kernel (csrc/s2s.cu).  The
+        module is a parameter container for the decoder: training differentiates the whole
+        decode through functions/s2s.py, so this stand-alone call carries no autograd."""
+        from .. import ops
+        if torch.is_grad_enabled() and (eh.requires_grad or dhx.requires_grad):
+            raise RuntimeError("NNAttention.forward is inference-only; gradients flow through "
+                               "Seq2Seq.decode (speech_b200.functions.s2s)")
+        return ops.attn_step(eh, dhx, ax, self.conv, self.nn[1].fc, self.log_t)

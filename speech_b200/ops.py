@@ -298,9 +298,10 @@ def set_grad_ready_hook(fn, guard=None):
     gradients of one layer's parameters are final in their .grad buffers (all producing kernels
     enqueued on the current stream).  Used by optim.FlatSGD to start that layer's all-reduce
     while the layers below are still being differentiated.  None disables.
-    guard() (optional) runs at the START of every announcing backward pass, before any gradient
-    buffer is touched: it raises if an earlier backward of the same step already announced
-    (a second pass would add local gradients into slices that are being all-reduced)."""
+    guard(parameters) (optional) runs at the START of every announcing backward of a GRU stack,
+    before any gradient buffer is touched: it raises if gradients of these parameters were
+    already announced in this step (a second backward pass would add local gradients into
+    slices that are being all-reduced)."""
     global _grad_ready_hook, _grad_guard
     _grad_ready_hook = fn
     _grad_guard = guard if fn is not None else None
@@ -445,7 +446,7 @@ class GRUStackFunction(torch.autograd.Function):
         B, T, In, Bp, H, ndir, L = ctx.dims
         weights = ctx.weights
         if _grad_ready_hook is not None and ctx.announce and _grad_guard is not None:
-            _grad_guard()
+            _grad_guard(list(weights))
         dev = dout.device
         M = T * Bp
         D = ndir * H

@@ -116,8 +116,13 @@ class FlatSGD:
         for e in self._op_entries:
             e["versions"] = [q._version for q in e["params"]]
 
-    def _guard_second_backward(self):
-        if self.reducer.pending:
+    def _guard_second_backward(self, params):
+        spans = [self.spans.get(id(p)) for p in params]
+        spans = [sp for sp in spans if sp is not None]
+        if not spans:
+            return
+        lo, hi = min(sp[0] for sp in spans), max(sp[1] for sp in spans)
+        if any(plo < hi and lo < phi for plo, phi, _ in self.reducer.pending):
             raise RuntimeError(
                 "FlatSGD(overlap=True): a second backward pass before step() would add local "
                 "gradients into slices that are already being all-reduced; use overlap=False "

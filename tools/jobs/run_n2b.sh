@@ -1,0 +1,9 @@
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+tail -c 300 gpurun_out/bench_n2.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches')}, 'e2e', d['e2e']['value'])
+print(d.get('dp_check')); print(d.get('secondary'))
+for k,v in sorted(d['kernels'].items(), key=lambda kv:-kv[1]['ms_per_step'])[:4]: print('  %-18s n=%5.1f %.3f ms'%(k,v['launches_per_step'],v['ms_per_step']))
+PY

@@ -4,5 +4,6 @@ python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench_n8.json').read().strip().splitlines()[-1])
 print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches')}, 'e2e', d['e2e']['value'])
-print(d.get('dp_check')); print(d.get('secondary'))
+print(d.get("dp_check")); print(d.get("secondary"))
+for k,v in sorted(d["kernels"].items(), key=lambda kv:-kv[1]["ms_per_step"])[:4]: print("  %-18s n=%5.1f %.3f ms"%(k,v["launches_per_step"],v["ms_per_step"]))
 PY
