@@ -169,13 +169,16 @@ int sb_transpose_bf16(const void* src, void* dst, long long R, int C, long long 
  * Tail of the training step over flat fp32 buffers.
  * Replaces: nn.utils.clip_grad_norm(model.parameters(), 200) + torch.optim.SGD.step()
  *           (train.py:32-35, 95-97).
- *   sb_sumsq          out[0] = sum(g^2)                       (one pass over the gradient)
+ *   sb_sumsq          out[0] = sum(g^2), one pass over the gradient; per-CTA partials combined in
+ *                     a fixed order (bit-reproducible: data-parallel replicas stay identical);
+ *                     workspace: sb_sumsq_workspace_size bytes, zeroed once by the caller
  *   sb_sgd_clip_step  c = min(1, max_norm/(sqrt(sumsq)+1e-6)); [m = momentum*m + c*g]; p -= lr*(m|c*g)
  *                     the clip coefficient is read from device memory (no host sync);
  *                     params_bf16 (may be NULL): bf16 copy of the updated parameters, the
  *                     tensor-core operands of the next step (no per-step cast kernels)
  * ------------------------------------------------------------------------------------- */
-int sb_sumsq(const float* g, long long n, float* out, void* stream);
+int sb_sumsq_workspace_size(size_t* bytes);
+int sb_sumsq(const float* g, long long n, float* out, void* workspace, void* stream);
 int sb_sgd_clip_step(float* params, const float* grads, float* momentum_buf, void* params_bf16,
                      long long n, const float* sumsq, float lr, float momentum, float max_norm,
                      void* stream);

@@ -35,7 +35,8 @@ SIGNATURES = {
     "sb_conv_col2im_relu": (_c_int, [_vp, _c_ll, _vp, _vp, _fl, _vp, _vp, _c_int, _c_int, _c_int,
                                      _c_int, _c_int, _c_int, _c_int, _vp]),
     "sb_transpose_bf16": (_c_int, [_vp, _vp, _c_ll, _c_int, _c_ll, _c_ll, _vp]),
-    "sb_sumsq": (_c_int, [_vp, _c_ll, _vp, _vp]),
+    "sb_sumsq_workspace_size": (_c_int, [ctypes.POINTER(_c_sz)]),
+    "sb_sumsq": (_c_int, [_vp, _c_ll, _vp, _vp, _vp]),
     "sb_sgd_clip_step": (_c_int, [_vp, _vp, _vp, _vp, _c_ll, _vp, _fl, _fl, _fl, _vp]),
     "sb_attn_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _fl, _c_int, _c_int, _c_int, _c_int,
                               _c_int, _vp, _vp, _vp]),

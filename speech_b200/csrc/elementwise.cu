@@ -1,8 +1,9 @@
 // Flat-buffer optimizer kernels: the tail of the reference's training step
 // (train.py:32-35: clip_grad_norm(model.parameters(), 200) ; optimizer.step() with plain SGD,
 // train.py:95-97) over ONE contiguous fp32 parameter buffer and ONE contiguous gradient buffer.
-//   sb_sumsq        : sum of squares of the flat gradient (grid-stride, float4 loads, one atomic
-//                     per CTA) -> the global L2 norm used by the clip
+//   sb_sumsq        : sum of squares of the flat gradient (grid-stride, float4 loads, per-CTA
+//                     partials combined in a fixed order: bit-reproducible across ranks) -> the
+//                     global L2 norm used by the clip
 //   sb_sgd_clip_step: p -= lr * min(1, max_norm / (norm + 1e-6)) * g   (momentum buffer optional),
 //                     the clip coefficient is read from device memory: no host sync in the step;
 //                     optionally also writes the bf16 copy of the updated parameters that the
@@ -15,8 +16,15 @@
 
 namespace sb {
 
+// DETERMINISTIC: every CTA writes its partial sum to a scratch slot, and the last CTA to finish
+// adds the slots in index order.  With atomics the summation order - hence the last bits of the
+// norm, the clip coefficient and finally the parameters - differed between data-parallel ranks
+// holding bit-identical gradients (bench.py dp_check: replicas drifted apart by 1e-5 in 70 steps).
+static constexpr int SUMSQ_MAX_CTAS = 1024;
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n,
-                                                    float* __restrict__ out) {
+                                                    float* __restrict__ out,
+                                                    float* __restrict__ partial,
+                                                    unsigned int* __restrict__ ticket) {
   float acc = 0.f;
   const long long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -29,12 +37,30 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     acc += g[i] * g[i];
   acc = warp_sum(acc);
   __shared__ float part[8];
+  __shared__ bool last;
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += part[w];
-    atomicAdd(out, t);
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // fixed-order reduction of the gridDim.x partials by the last CTA
+  float s = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) s += __ldcg(partial + i);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    *out = t;
+    *ticket = 0u;
   }
 }
 
@@ -78,12 +104,22 @@ sgd_clip_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* 
 
 using namespace sb;
 
-extern "C" int sb_sumsq(const float* g, long long n, float* out, void* stream_) {
-  if (!g || !out || n <= 0) return SB_ERR_INVALID;
+extern "C" int sb_sumsq_workspace_size(size_t* bytes) {
+  if (!bytes) return SB_ERR_INVALID;
+  *bytes = (SUMSQ_MAX_CTAS + 4) * sizeof(float);
+  return SB_OK;
+}
+
+// workspace: sb_sumsq_workspace_size bytes, ZERO-INITIALISED ONCE by the caller (the kernel leaves
+// its ticket word at zero again); partial sums are combined in a fixed order: bit-reproducible.
+extern "C" int sb_sumsq(const float* g, long long n, float* out, void* workspace, void* stream_) {
+  if (!g || !out || !workspace || n <= 0) return SB_ERR_INVALID;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (cudaMemsetAsync(out, 0, sizeof(float), stream) != cudaSuccess) return SB_ERR_CUDA;
-  const int grid = device_sm_count() * 4;
-  sumsq_kernel<<<grid, 256, 0, stream>>>(g, n, out);
+  int grid = device_sm_count() * 4;
+  if (grid > SUMSQ_MAX_CTAS) grid = SUMSQ_MAX_CTAS;
+  float* partial = reinterpret_cast<float*>(workspace);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + SUMSQ_MAX_CTAS);
+  sumsq_kernel<<<grid, 256, 0, stream>>>(g, n, out, partial, ticket);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 

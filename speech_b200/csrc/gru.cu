@@ -71,6 +71,7 @@ struct GruBwdParams {
   unsigned int* barrier;  // [ndir]
   unsigned long long* dbg;
   int T, Bp, H, ndir, ring, gc;
+  int ablate;          // developer knobs (polling mode bits 64 / 128)
 };
 
 SB_DEVINL unsigned long long gtime() {
@@ -85,14 +86,25 @@ SB_DEVINL unsigned long long gtime() {
 
 // ---- per-direction grid barrier ------------------------------------------------------------
 SB_DEVINL void grid_arrive(unsigned int* ctr) { red_release_gpu_add(ctr, 1u); }
-// (Polling with relaxed loads + one acquire fence was measured SLOWER, 7.8 vs 7.3 us/step: the
-// tighter spin of 128 pollers on the counter's L2 line delays the arriving reductions; the
-// ld.acquire's implied fence throttles the poll rate.)
-SB_DEVINL void grid_wait(const unsigned int* ctr, unsigned int target) {
+// Polling modes of the grid barrier (developer knob sb_debug_gru_flags bits 64 / 128):
+//   0   : ld.acquire.gpu per poll (its implied fence throttles the poll rate)
+//   64  : ld.relaxed.gpu + nanosleep per poll, one fence.acq_rel.gpu when the count is complete
+//   128 : ld.relaxed.gpu + nanosleep per poll, no fence (the TMA reads that follow go to L2)
+// (Un-throttled relaxed polling was measured SLOWER, 7.8 vs 7.3 us/step: the tight spin of 128
+// pollers on the counter's L2 line delays the arriving reductions.)
+SB_DEVINL void grid_wait(const unsigned int* ctr, unsigned int target, int mode = 0) {
   unsigned int spins = 0;
-  while (ld_acquire_gpu(ctr) < target) {
+  if (mode == 0) {
+    while (ld_acquire_gpu(ctr) < target) {
+      if (++spins > SB_SPIN_LIMIT) __trap();
+    }
+    return;
+  }
+  while (ld_relaxed_gpu(ctr) < target) {
+    __nanosleep(64);
     if (++spins > SB_SPIN_LIMIT) __trap();
   }
+  if (mode & 64) fence_acq_rel_gpu();
 }
 SB_DEVINL void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GRU_EPI) : "memory"); }
 
@@ -780,7 +792,7 @@ gru_bwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
   if (warp == 9) {
     if (lane == 0) {
       for (int step = 0; step + 1 < T; ++step) {
-        grid_wait(ctr, (unsigned int)nC * (step + 1));   // dgh of this step is complete
+        grid_wait(ctr, (unsigned int)nC * (step + 1), p.ablate & 192);   // dgh of this step is complete
         for (int g = 0; g < ngroups; ++g) {
           mbar_expect_tx(&full[g], (uint32_t)(stride * gc));
           for (int i = 0; i < gc; ++i) {
@@ -1061,7 +1073,7 @@ gru_fwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
       for (int step = 1; step < T; ++step) {
         const int t = dir == 0 ? step : (T - 1 - step);
         const int tp = dir == 0 ? t - 1 : t + 1;
-        grid_wait(ctr, (unsigned int)nC * step);       // all CTAs published h_{tp}
+        grid_wait(ctr, (unsigned int)nC * step, p.ablate & 192);   // all CTAs published h_{tp}
         GRU_STAMP(0);
         if (p.dbg && step == 21) p.dbg[1024 + 256 + blockIdx.x] = gtime();   // skew probe
         mbar_expect_tx(full, (uint32_t)(stride * nchunks));
@@ -1432,7 +1444,7 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
       q.gi = gi; q.whh = reinterpret_cast<const bf16*>(whh_bf16); q.bhh = bhh; q.y = y;
       q.xn = reinterpret_cast<bf16*>(xn_bf16); q.xnT = nullptr; q.gates = gates;
       q.barrier = barrier; q.T = T; q.Bp = Bp; q.H = H; q.ndir = ndir;
-      q.dbg = g_gru_dbg; q.ablate = 0; q.ring = nq; q.gc = 1;
+      q.dbg = g_gru_dbg; q.ablate = g_gru_ablate & 192; q.ring = nq; q.gc = 1;
       CUtensorMap tq[2];
       for (int d = 0; d < 2; ++d) {
         const int dd = d < ndir ? d : 0;
@@ -1498,6 +1510,7 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
   p.xchg = reinterpret_cast<bf16*>(ws + gru_ws_counters_bytes(ndir));
   p.dbih = dbih; p.dbhh = dbhh; p.T = T; p.Bp = Bp; p.H = H; p.ndir = ndir;
   p.dbg = g_gru_dbg;
+  p.ablate = g_gru_ablate & 192;
   const int K3 = 3 * H;
   const int nchunks = (K3 + 63) / 64;
   size_t smem = 0;

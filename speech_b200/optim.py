@@ -62,6 +62,10 @@ class FlatSGD:
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.mom = torch.zeros(n, dtype=torch.float32, device=dev) if self.momentum != 0 else None
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        import ctypes
+        nb = ctypes.c_size_t(0)
+        _lib.check(_lib.load().sb_sumsq_workspace_size(ctypes.byref(nb)), "sumsq ws")
+        self.sumsq_ws = torch.zeros(nb.value, dtype=torch.uint8, device=dev)
         self.spans = {}
         self.offs = {}
         for p, o in zip(self.params, offs):
@@ -177,7 +181,8 @@ class FlatSGD:
         self.all_reduce()
         sp = _lib.stream_ptr()
         ops._launch("sumsq", 0.0, lambda: lib.sb_sumsq(self.flat_g.data_ptr(), self.n,
-                                                       self.sumsq.data_ptr(), sp))
+                                                       self.sumsq.data_ptr(),
+                                                       self.sumsq_ws.data_ptr(), sp))
         ops._launch("sgd_clip_step", 0.0,
                     lambda: lib.sb_sgd_clip_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(),
                                                  _lib.ptr(self.mom), self.flat_p16.data_ptr(),
