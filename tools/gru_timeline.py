@@ -11,7 +11,8 @@ if len(sys.argv) > 3:
     lib.sb_debug_gru_flags(int(sys.argv[3]))      # 32: version-1 forward kernel
     print("flags:", sys.argv[3])
 torch.manual_seed(0)
-B, T, In, H = 64, 64, 2048, 1024
+import os
+B, T, In, H = int(os.environ.get('TL_B', '64')), 64, 2048, 1024
 rnn = torch.nn.GRU(In, H, 1, batch_first=True, bidirectional=True).cuda()
 x = torch.randn(B, T, In, device="cuda")
 dbg = torch.zeros(64 * 16 + 512, dtype=torch.int64, device="cuda")
