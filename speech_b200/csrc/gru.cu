@@ -55,7 +55,7 @@ struct GruFwdParams {
   unsigned int* barrier;  // [ndir] zero-initialised counters
   unsigned long long* dbg;  // optional timeline (CTA 0): [step][16] globaltimer stamps, or null
   int T, Bp, H, ndir, ring, gc;   // ring: slots (groups of gc chunks) in shared memory
-  int ablate;          // developer timing ablations (results become WRONG): see sb_debug_gru_flags
+  int ablate;          // developer knobs: see sb_debug_gru_flags
 };
 
 struct GruBwdParams {
@@ -334,11 +334,10 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       for (int step = 1; step < T; ++step) {
         const int t = dir == 0 ? step : (T - 1 - step);
         const int tp = dir == 0 ? t - 1 : t + 1;
-        if (!(p.ablate & 16)) grid_wait(ctr, (unsigned int)nC * step);   // all CTAs published h_{tp}
+        grid_wait(ctr, (unsigned int)nC * step);   // all CTAs published h_{tp}
         GRU_STAMP(0);
         // (the writers ran fence.proxy.async before their release; no reader-side proxy fence)
-        if (!(p.ablate & 4))
-          tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, p.gc, step - 1, crank, csize);
+        tma_gather(s, tm, tp * Bp, Bp, nchunks, p.ring, p.gc, step - 1, crank, csize);
         GRU_STAMP(1);
       }
     }
@@ -346,17 +345,6 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       for (int step = 1; step < T; ++step) {
-        if (p.ablate & 8) continue;
-        if (p.ablate & 4) {   // no loads: issue the same MMAs on whatever is in the ring
-          constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 48);
-          for (int c = 0; c < nchunks; ++c)
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(smem_u32(s.ring)) + kk * 2,
-                           umma_desc_sw128_kmajor(smem_u32(s.wtile + c * WCHUNK)) + kk * 2, idesc,
-                           (c > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(s.accfull);
-          continue;
-        }
         mma_consume<48>(s, tmem_base, nchunks, WCHUNK, Bp, p.ring, p.gc, step - 1, csize);
         GRU_STAMP(2);
       }
@@ -386,7 +374,7 @@ gru_fwd_kernel(const __grid_constant__ CUtensorMap tm_d0, const __grid_constant_
       }
       float acc[3][GRU_UPT];
       if (step > 0) {
-        if (!(p.ablate & 8)) mbar_wait(s.accfull, (step - 1) & 1);
+        mbar_wait(s.accfull, (step - 1) & 1);
         if (tid == 0) GRU_STAMP(3);
         tc_fence_after_sync();
         uint32_t v[8];
@@ -1372,8 +1360,9 @@ extern "C" int sb_debug_gru_timeline(void* dev_buffer) {
   sb::g_gru_dbg = reinterpret_cast<unsigned long long*>(dev_buffer);
   return SB_OK;
 }
-// timing ablations of gru_fwd (results become wrong): 1 no proxy fence, 2 no off-path stores,
-// 4 no TMA loads, 8 no MMA, 16 no grid-barrier wait
+// developer knobs: 1 / 2: gru_fwd_kernel without the proxy fence / the off-path stores (timing
+// only: results become wrong); 32: disable the K-split forward kernel; 64 / 128: polling mode of
+// the grid barrier in the K-split kernels (see grid_wait)
 extern "C" int sb_debug_gru_flags(int flags) {
   sb::g_gru_ablate = flags;
   return SB_OK;
