@@ -1225,6 +1225,605 @@ gru_fwd_ks_kernel(const __grid_constant__ CUtensorMap tm_d0,
   }
 }
 
+// =============================================================================================
+// forward, K split with the accumulator TRANSPOSED: D^T[(gate, unit) x batch].
+//
+// Same partition as gru_fwd_ks_kernel (cluster of 4 owns 64 units, CTA r contracts K quarter r),
+// but the resident weight slice is the M-side operand and h_{t-1} the N-side one:
+//     D0[128 x Bp] = W[(r|z) x 64 units, quarter r] * h_{t-1}[:, quarter r]^T     (TMEM cols 0..)
+//     D1[ 64 x Bp] = W[ n    x 64 units, quarter r] * h_{t-1}[:, quarter r]^T     (TMEM cols 64..)
+// An MMA of N = Bp costs Bp/256 of the N = 192 one, so the tensor-core share of the step falls
+// from 16 x 96 to 32 x (Bp/8) cycles (1536 -> 1024 at 64 rows, -> 128 at 8 rows), and every
+// accumulator lane is a weight row, so all 128 lanes (all four TMEM sub-partitions) carry data
+// whatever the batch is.  The weight rows are ordered by OWNER: tile 0 rows 32q..32q+31 are the
+// r and z rows of the 16 units CTA q of the cluster owns, tile 1 rows 16q..16q+15 its n rows, so
+// an epilogue thread's accumulator row goes to exactly one peer: it is written as one row of
+// [48][Bp] (pitch Bp+4: conflict-free) into the staging slice for that peer, the three slices leave
+// as one bulk copy each, and the gate math then runs on ALL 256 epilogue threads
+// (thread = batch row x UPT units) from the four received slices.
+// Requires cluster size 4, H % 256 == 0, Bp <= 64 (Bp % 8 == 0 as everywhere).
+// =============================================================================================
+template <int UPT>
+SB_DEVINL void ldu(const float* p, float (&v)[UPT]) {
+  if constexpr (UPT == 4) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else if constexpr (UPT == 2) {
+    const float2 a = __ldcs(reinterpret_cast<const float2*>(p));
+    v[0] = a.x; v[1] = a.y;
+  } else {
+    v[0] = __ldcs(p);
+  }
+}
+template <int UPT>
+SB_DEVINL void stu(float* p, const float (&v)[UPT]) {
+  if constexpr (UPT == 4) __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  else if constexpr (UPT == 2) __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  else __stcs(p, v[0]);
+}
+template <int UPT>
+SB_DEVINL void st_bf16u(bf16* p, const float (&v)[UPT]) {
+  if constexpr (UPT == 4) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  } else if constexpr (UPT == 2) {
+    *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v[0], v[1]);
+  } else {
+    *p = __float2bfloat16_rn(v[0]);
+  }
+}
+
+template <int UPT>
+__global__ void __launch_bounds__(GRU_THREADS, 1)
+gru_fwd_kt_kernel(const __grid_constant__ CUtensorMap tm_d0,
+                  const __grid_constant__ CUtensorMap tm_d1, const GruFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int H = p.H, Bp = p.Bp, T = p.T;
+  const int nC = H / GRU_HC;
+  const int dir = blockIdx.x / nC;
+  const int cta_in_dir = blockIdx.x % nC;
+  const int j0 = cta_in_dir * GRU_HC;                 // own 16 units (gate math, stores)
+  const uint32_t crank = cluster_rank();              // == cta_in_dir % 4
+  const int k0c = (cta_in_dir / KS) * (KS * GRU_HC);  // first of the cluster's 64 units
+  const int KQ = H / KS;                              // this CTA's share of the contraction
+  const int nchunks = KQ / 64;
+  constexpr int WROWS = 3 * KS * GRU_HC;              // 192 weight rows: 128 (r,z) + 64 (n)
+  constexpr int WCHUNK = WROWS * 128;                 // 192 rows x 64 bf16
+  constexpr int RW = 3 * GRU_HC;                      // 48 accumulator rows per owner
+  const int P = Bp + 4;                               // pitch of a staged row (floats)
+  const int slice = RW * P;                           // floats per (source, owner) slice
+  const int NB = (Bp + 15) & ~15;                     // MMA N (rows of h read per chunk)
+  const int stride = Bp * 128;
+  const int ring_bytes = nchunks * stride;            // the whole quarter is resident
+  const int wbytes = nchunks * WCHUNK;
+  // carve: ring | weights | recv | stage | barriers.  The N-side read of the last chunk may run
+  // up to 8 rows past the ring into the weights, and the 128-row M-side read of tile 1 runs 64
+  // rows past its 64 valid ones (into the next chunk / the receive buffer): both only feed
+  // accumulator columns / lanes that are never read.
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* ring = base;
+  uint8_t* wtile = ring + ring_bytes;
+  float* recv = reinterpret_cast<float*>(wtile + wbytes);          // [KS src][48][P]
+  float* stage = recv + KS * slice;                                // [KS-1 dst][48][P]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (KS - 1) * slice);
+  uint64_t* full = bars;
+  uint64_t* accfull = bars + 1;
+  uint64_t* recvbar = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* bias_s = reinterpret_cast<float*>(bars + 4);             // [48]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = p.ndir * H;
+  const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
+
+  for (int k = tid; k < (ring_bytes + wbytes + (2 * KS - 1) * slice * 4) / 16; k += GRU_THREADS)
+    reinterpret_cast<uint4*>(base)[k] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    // resident operand: rows ordered by owner (see above), columns = this CTA's K quarter
+    const int pieces_per_row = nchunks * 8;
+    for (int k = tid; k < WROWS * pieces_per_row; k += GRU_THREADS) {
+      const int r = k / pieces_per_row, pc = k % pieces_per_row;
+      int g, u;
+      if (r < 128) { g = (r & 31) >> 4; u = (r >> 5) * GRU_HC + (r & 15); }
+      else { g = 2; u = r - 128; }
+      const uint4 v = *reinterpret_cast<const uint4*>(
+          p.whh + ((long long)dir * 3 * H + (long long)g * H + k0c + u) * H + (long long)crank * KQ +
+          pc * 8);
+      *reinterpret_cast<uint4*>(wtile + (pc >> 3) * WCHUNK + sw128_offset(r, pc & 7)) = v;
+    }
+    if (tid < RW) {
+      const int g = tid / GRU_HC, jj = tid % GRU_HC;
+      bias_s[tid] = p.bhh[dir * 3 * H + g * H + j0 + jj];
+    }
+  }
+  if (tid == 0) {
+    mbar_init(full, 1);
+    mbar_init(accfull, 1);
+    mbar_init(recvbar, 1);   // one local arrive.expect_tx per step; the peers' copies complete_tx
+    mbar_fence_init();
+    tma_prefetch_desc(tm);
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 128);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  cluster_sync_all();
+  const uint32_t tmem_base = *tmem_slot;
+  unsigned int* ctr = p.barrier + dir * 32;   // one L2 line per direction
+
+  if (warp == 9) {
+    // ===================== TMA producer: this CTA's K quarter of h_{t-1} =====================
+    if (lane == 0) {
+      for (int step = 1; step < T; ++step) {
+        const int t = dir == 0 ? step : (T - 1 - step);
+        const int tp = dir == 0 ? t - 1 : t + 1;
+        grid_wait(ctr, (unsigned int)nC * step, p.ablate & 192);   // all CTAs published h_{tp}
+        GRU_STAMP(0);
+        if (p.dbg && step == 21) p.dbg[1024 + 256 + blockIdx.x] = gtime();   // skew probe
+        mbar_expect_tx(full, (uint32_t)(stride * nchunks));
+        for (int c = 0; c < nchunks; ++c)
+          tma_load_2d(ring + c * stride, tm, full, (int)crank * KQ + c * 64, tp * Bp);
+        GRU_STAMP(1);
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_f32(128, (uint32_t)NB);
+      for (int step = 1; step < T; ++step) {
+        mbar_wait(full, (step - 1) & 1);
+        tc_fence_after_sync();
+        for (int c = 0; c < nchunks; ++c) {
+          const uint64_t da0 = umma_desc_sw128_kmajor(smem_u32(wtile + c * WCHUNK));
+          const uint64_t da1 = umma_desc_sw128_kmajor(smem_u32(wtile + c * WCHUNK + 128 * 128));
+          const uint64_t db = umma_desc_sw128_kmajor(smem_u32(ring + c * stride));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
+            umma_bf16_ss(tmem_base, da0 + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc);
+            umma_bf16_ss(tmem_base + 64, da1 + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                         acc);
+          }
+        }
+        umma_commit(accfull);
+        GRU_STAMP(2);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    // phase A (scatter): warp w reads accumulator lanes 32*(w&3).. of tile 0 and, for w&3 < 2,
+    // of tile 1, for the column blocks (8 batch rows each) of its half (w>>2) of the batch
+    const int sub = warp & 3, hi = warp >> 2;
+    const int nblk = Bp >> 3;
+    const int blk0 = hi == 0 ? 0 : (nblk + 1) / 2;
+    const int myblk = hi == 0 ? (nblk + 1) / 2 : nblk / 2;          // <= 4
+    const uint32_t own0 = (uint32_t)sub;                            // owner of the tile-0 row
+    const uint32_t own1 = (uint32_t)(sub * 2 + (lane >> 4));        // owner of the tile-1 row
+    const uint32_t q0 = (own0 + KS - crank) % KS, q1 = (own1 + KS - crank) % KS;
+    float* dst0 = (q0 == 0 ? recv + crank * slice : stage + (q0 - 1) * slice) + lane * P;
+    float* dst1 = (q1 == 0 ? recv + crank * slice : stage + (q1 - 1) * slice) +
+                  (2 * GRU_HC + (lane & 15)) * P;
+    // phase B (gate math): thread = (batch row b, UPT of the CTA's 16 units)
+    const int b = tid % Bp, ug = tid / Bp;
+    const bool active = ug * UPT < GRU_HC;
+    const int u0 = ug * UPT;
+    const int ju = j0 + u0;
+    float hprev[UPT];
+#pragma unroll
+    for (int jj = 0; jj < UPT; ++jj) hprev[jj] = 0.f;
+    float bias[3][UPT];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int jj = 0; jj < UPT; ++jj) bias[g][jj] = active ? bias_s[g * GRU_HC + u0 + jj] : 0.f;
+
+    for (int step = 0; step < T; ++step) {
+      const int t = dir == 0 ? step : (T - 1 - step);
+      float gi[3][UPT];
+      if (active) {
+        const float* g = p.gi + ((long long)t * Bp + b) * (p.ndir * 3 * H) + dir * 3 * H + ju;
+#pragma unroll
+        for (int gg = 0; gg < 3; ++gg) ldu<UPT>(g + gg * H, gi[gg]);
+      }
+      float acc[3][UPT];
+#pragma unroll
+      for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+        for (int jj = 0; jj < UPT; ++jj) acc[gg][jj] = 0.f;
+      if (step > 0) {
+        mbar_wait(accfull, (step - 1) & 1);
+        if (tid == 0) GRU_STAMP(3);
+        tc_fence_after_sync();
+        if (tid == 0) mbar_expect_tx(recvbar, (uint32_t)((KS - 1) * slice * 4));
+        {
+          const uint32_t tl = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(blk0 * 8);
+#pragma unroll
+          for (int kb = 0; kb < 4; kb += 2) {
+            if (kb < myblk) {
+              uint32_t v0[2][8], v1[2][8];
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                if (kb + k < myblk) {
+                  tmem_ld_32x32b_x8(tl + (kb + k) * 8, v0[k]);
+                  if (sub < 2) tmem_ld_32x32b_x8(tl + 64 + (kb + k) * 8, v1[k]);
+                }
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                if (kb + k < myblk) {
+                  float4* o = reinterpret_cast<float4*>(dst0 + (blk0 + kb + k) * 8);
+                  o[0] = make_float4(__uint_as_float(v0[k][0]), __uint_as_float(v0[k][1]),
+                                     __uint_as_float(v0[k][2]), __uint_as_float(v0[k][3]));
+                  o[1] = make_float4(__uint_as_float(v0[k][4]), __uint_as_float(v0[k][5]),
+                                     __uint_as_float(v0[k][6]), __uint_as_float(v0[k][7]));
+                  if (sub < 2) {
+                    float4* o1 = reinterpret_cast<float4*>(dst1 + (blk0 + kb + k) * 8);
+                    o1[0] = make_float4(__uint_as_float(v1[k][0]), __uint_as_float(v1[k][1]),
+                                        __uint_as_float(v1[k][2]), __uint_as_float(v1[k][3]));
+                    o1[1] = make_float4(__uint_as_float(v1[k][4]), __uint_as_float(v1[k][5]),
+                                        __uint_as_float(v1[k][6]), __uint_as_float(v1[k][7]));
+                  }
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();   // generic st.shared -> the copy engine's (async proxy) reads
+        epi_barrier();              // all three outgoing slices (and the own one) are staged
+        if (lane == 0 && warp >= 1 && warp <= KS - 1) {
+          const uint32_t pr = (crank + (uint32_t)warp) % KS;
+          bulk_s2peer(mapa_shared(smem_u32(recv + (size_t)crank * slice), pr),
+                      stage + (size_t)(warp - 1) * slice, (uint32_t)(slice * 4),
+                      mapa_shared(smem_u32(recvbar), pr));
+        }
+        if (tid == 0) GRU_STAMP(4);
+        mbar_wait(recvbar, (step - 1) & 1);
+        if (active) {
+#pragma unroll
+          for (int src = 0; src < KS; ++src) {
+            const float* rp = recv + (size_t)src * slice + u0 * P + b;
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+              for (int jj = 0; jj < UPT; ++jj) acc[gg][jj] += rp[(gg * GRU_HC + jj) * P];
+          }
+        }
+      }
+      const long long m = (long long)t * Bp + b;
+      float hn[UPT], rr[UPT], zz[UPT], nn[UPT];
+      if (active) {
+#pragma unroll
+        for (int jj = 0; jj < UPT; ++jj) {
+          rr[jj] = fast_sigmoid(gi[0][jj] + acc[0][jj] + bias[0][jj]);
+          zz[jj] = fast_sigmoid(gi[1][jj] + acc[1][jj] + bias[1][jj]);
+          hn[jj] = acc[2][jj] + bias[2][jj];
+          nn[jj] = fast_tanh(gi[2][jj] + rr[jj] * hn[jj]);
+          hprev[jj] = (1.f - zz[jj]) * nn[jj] + zz[jj] * hprev[jj];
+        }
+        // critical path: only the bf16 h_t that the other CTAs gather next step
+        st_bf16u<UPT>(p.xn + m * D + dir * H + ju, hprev);
+        if (tid == 0) GRU_STAMP(5);
+        fence_proxy_async_global();   // generic writes -> other CTAs' TMA reads
+        if (tid == 0) GRU_STAMP(6);
+      }
+      epi_barrier();
+      if (tid == 0) {
+        GRU_STAMP(7);
+        if (p.dbg && step == 20) p.dbg[1024 + blockIdx.x] = gtime();         // skew probe
+        grid_arrive(ctr);
+        GRU_STAMP(9);
+      }
+      if (active) {
+        stu<UPT>(p.y + m * D + dir * H + ju, hprev);
+        if (p.gates) {
+          float* go = p.gates + ((m * p.ndir + dir) * 4) * H + ju;
+          stu<UPT>(go, rr);
+          stu<UPT>(go + H, zz);
+          stu<UPT>(go + 2 * H, nn);
+          stu<UPT>(go + 3 * H, hn);
+        }
+      }
+      if (tid == 0) GRU_STAMP(10);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// =============================================================================================
+// backward, K split with the accumulator TRANSPOSED (see gru_fwd_kt_kernel):
+//     D^T[64 units x Bp] = W_hh^T[64 units of the cluster, quarter r of 3H] * dgh[:, quarter r]^T
+// The weight tile is the one of gru_bwd_ks_kernel (its 64 rows are already grouped by owner:
+// rows 16q..16q+15 belong to CTA q of the cluster); an accumulator lane is a unit, so its row
+// of Bp partial sums goes to exactly one peer, and the elementwise work runs on all 256
+// epilogue threads (thread = batch row x UPT units).
+// =============================================================================================
+template <int UPT>
+SB_DEVINL void st_stream_bf16u(bf16* p, const float (&v)[UPT]) {
+  if constexpr (UPT == 4) {
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3])));
+  } else if constexpr (UPT == 2) {
+    __stcs(reinterpret_cast<unsigned int*>(p), pack_bf16x2(v[0], v[1]));
+  } else {
+    st_stream_bf16(p, v[0]);
+  }
+}
+
+template <int UPT>
+__global__ void __launch_bounds__(GRU_THREADS, 1)
+gru_bwd_kt_kernel(const __grid_constant__ CUtensorMap tm_d0,
+                  const __grid_constant__ CUtensorMap tm_d1, const GruBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int H = p.H, Bp = p.Bp, T = p.T;
+  const int nC = H / GRU_HC;
+  const int dir = blockIdx.x / nC;
+  const int cta_in_dir = blockIdx.x % nC;
+  const int j0 = cta_in_dir * GRU_HC;                 // own 16 units (elementwise work)
+  const uint32_t crank = cluster_rank();              // == cta_in_dir % 4
+  const int k0c = (cta_in_dir / KS) * (KS * GRU_HC);  // first of the cluster's 64 units
+  const int K3 = 3 * H;
+  const int KQ = K3 / KS;                             // this CTA's share of the contraction
+  const int nchunks = KQ / 64;
+  constexpr int WCHUNK = 64 * 128;                    // 64 rows (units) x 64 bf16
+  const int P = Bp + 4;                               // pitch of a staged row (floats)
+  const int slice = GRU_HC * P;                       // floats per (source, owner) slice
+  const int NB = (Bp + 15) & ~15;
+  const int stride = Bp * 128;
+  const int ring_bytes = nchunks * stride;            // the whole quarter is resident
+  const int wbytes = nchunks * WCHUNK;
+  // carve: ring | weights | recv | stage | barriers.  The 128-row M-side read covers the next
+  // weight chunk (last chunk: the receive buffer) with its lanes 64..127, which are never read.
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* ring = base;
+  uint8_t* wtile = ring + ring_bytes;
+  float* recv = reinterpret_cast<float*>(wtile + wbytes);          // [KS src][16][P]
+  float* stage = recv + KS * slice;                                // [KS-1 dst][16][P]
+  float* pad_end = stage + (KS - 1) * slice;
+  // the last chunk's 128-row read needs 8 KB after the weights: recv + stage cover it only for
+  // large batches, so reserve it explicitly
+  const int tail_floats = max(0, 2048 - (2 * KS - 1) * slice);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pad_end + tail_floats);
+  uint64_t* full = bars;          // [4] groups
+  uint64_t* accfull = bars + 4;
+  uint64_t* recvbar = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = p.ndir * H;
+  const CUtensorMap* tm = dir == 0 ? &tm_d0 : &tm_d1;
+  const int gc = (nchunks % 4 == 0) ? 4 : ((nchunks % 3 == 0) ? 3 : ((nchunks % 2 == 0) ? 2 : 1));
+  const int ngroups = nchunks / gc;                   // <= 4 for H <= 1024 ... checked on host
+
+  for (int k = tid; k < (ring_bytes + wbytes + ((2 * KS - 1) * slice + tail_floats) * 4) / 16;
+       k += GRU_THREADS)
+    reinterpret_cast<uint4*>(base)[k] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    // resident operand: see gru_bwd_ks_kernel
+    for (int k = tid; k < KQ * 8; k += GRU_THREADS) {
+      const int kl = k >> 3, piece = k & 7;       // local k, 8-unit piece of the 64 units
+      const uint4 v = *reinterpret_cast<const uint4*>(
+          p.whh + ((long long)dir * K3 + (long long)crank * KQ + kl) * H + k0c + piece * 8);
+      const unsigned short* e = reinterpret_cast<const unsigned short*>(&v);
+      uint8_t* chunk = wtile + (kl >> 6) * WCHUNK + (kl & 7) * 2;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<unsigned short*>(
+            chunk + sw128_offset((uint32_t)(piece * 8 + q), (uint32_t)((kl & 63) >> 3))) = e[q];
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&full[i], 1);
+    mbar_init(accfull, 1);
+    mbar_init(recvbar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(tm);
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 64);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  cluster_sync_all();
+  const uint32_t tmem_base = *tmem_slot;
+  unsigned int* ctr = p.barrier + dir * 32;   // one L2 line per direction
+
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int step = 0; step + 1 < T; ++step) {
+        grid_wait(ctr, (unsigned int)nC * (step + 1), p.ablate & 192);   // dgh of this step is complete
+        GRU_STAMP(0);
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_expect_tx(&full[g], (uint32_t)(stride * gc));
+          for (int i = 0; i < gc; ++i) {
+            const int c = g * gc + i;
+            tma_load_2d(ring + c * stride, tm, &full[g], (int)crank * KQ + c * 64,
+                        (step & 1) * Bp);
+          }
+        }
+        GRU_STAMP(1);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_f32(128, (uint32_t)NB);
+      for (int step = 0; step + 1 < T; ++step) {
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&full[g], step & 1);
+          tc_fence_after_sync();
+          for (int i = 0; i < gc; ++i) {
+            const int c = g * gc + i;
+            const uint64_t da = umma_desc_sw128_kmajor(smem_u32(wtile + c * WCHUNK));
+            const uint64_t db = umma_desc_sw128_kmajor(smem_u32(ring + c * stride));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ss(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                           (c > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(accfull);
+        GRU_STAMP(2);
+      }
+    }
+  } else {
+    // phase A (scatter): warps with (w&3) < 2 hold the 64 valid accumulator lanes
+    const int sub = warp & 3, hi = warp >> 2;
+    const int nblk = Bp >> 3;
+    const int blk0 = hi == 0 ? 0 : (nblk + 1) / 2;
+    const int myblk = hi == 0 ? (nblk + 1) / 2 : nblk / 2;          // <= 4
+    const uint32_t own = (uint32_t)(sub * 2 + (lane >> 4));
+    const uint32_t q0 = (own + KS - crank) % KS;
+    float* dst0 = (q0 == 0 ? recv + crank * slice : stage + (q0 - 1) * slice) + (lane & 15) * P;
+    // phase B: thread = (batch row b, UPT of the CTA's 16 units)
+    const int b = tid % Bp, ug = tid / Bp;
+    const bool active = ug * UPT < GRU_HC;
+    const int u0 = ug * UPT;
+    const int ju = j0 + u0;
+    float dh_rec[UPT];
+    float db_r[UPT], db_z[UPT], db_n[UPT], db_hn[UPT];
+#pragma unroll
+    for (int jj = 0; jj < UPT; ++jj) {
+      dh_rec[jj] = 0.f; db_r[jj] = 0.f; db_z[jj] = 0.f; db_n[jj] = 0.f; db_hn[jj] = 0.f;
+    }
+
+    for (int step = 0; step < T; ++step) {
+      const int t = dir == 0 ? (T - 1 - step) : step;
+      const int tp = dir == 0 ? t - 1 : t + 1;
+      const bool has_prev = dir == 0 ? (t > 0) : (t < T - 1);
+      bf16* xb = p.xchg + ((long long)(dir * 2 + (step & 1)) * Bp) * K3;
+      const long long m = (long long)t * Bp + b;
+      float rr[UPT], zz[UPT], nn[UPT], hn[UPT], dh[UPT], hp[UPT];
+      if (active) {
+        const float* go = p.gates + ((m * p.ndir + dir) * 4) * H + ju;
+        ldu<UPT>(go, rr);
+        ldu<UPT>(go + H, zz);
+        ldu<UPT>(go + 2 * H, nn);
+        ldu<UPT>(go + 3 * H, hn);
+        ldu<UPT>(p.dy + m * D + dir * H + ju, dh);
+        if (has_prev) {
+          ldu<UPT>(p.y + ((long long)tp * Bp + b) * D + dir * H + ju, hp);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < UPT; ++jj) hp[jj] = 0.f;
+        }
+      }
+      if (step > 0) {
+        mbar_wait(accfull, (step - 1) & 1);
+        if (tid == 0) GRU_STAMP(3);
+        tc_fence_after_sync();
+        if (tid == 0) mbar_expect_tx(recvbar, (uint32_t)((KS - 1) * slice * 4));
+        if (sub < 2) {
+          const uint32_t tl = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(blk0 * 8);
+          uint32_t v[4][8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < myblk) tmem_ld_32x32b_x8(tl + k * 8, v[k]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < myblk) {
+              float4* o = reinterpret_cast<float4*>(dst0 + (blk0 + k) * 8);
+              o[0] = make_float4(__uint_as_float(v[k][0]), __uint_as_float(v[k][1]),
+                                 __uint_as_float(v[k][2]), __uint_as_float(v[k][3]));
+              o[1] = make_float4(__uint_as_float(v[k][4]), __uint_as_float(v[k][5]),
+                                 __uint_as_float(v[k][6]), __uint_as_float(v[k][7]));
+            }
+          }
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        epi_barrier();
+        if (lane == 0 && warp >= 1 && warp <= KS - 1) {
+          const uint32_t pr = (crank + (uint32_t)warp) % KS;
+          bulk_s2peer(mapa_shared(smem_u32(recv + (size_t)crank * slice), pr),
+                      stage + (size_t)(warp - 1) * slice, (uint32_t)(slice * 4),
+                      mapa_shared(smem_u32(recvbar), pr));
+        }
+        if (tid == 0) GRU_STAMP(4);
+        mbar_wait(recvbar, (step - 1) & 1);
+        if (active) {
+#pragma unroll
+          for (int src = 0; src < KS; ++src) {
+            const float* rp = recv + (size_t)src * slice + u0 * P + b;
+#pragma unroll
+            for (int jj = 0; jj < UPT; ++jj) dh_rec[jj] += rp[jj * P];
+          }
+        }
+      }
+      float dr[UPT], dz[UPT], dn[UPT], dnr[UPT];
+      if (active) {
+#pragma unroll
+        for (int jj = 0; jj < UPT; ++jj) {
+          const float g = dh[jj] + dh_rec[jj];
+          dn[jj] = g * (1.f - zz[jj]) * (1.f - nn[jj] * nn[jj]);
+          dz[jj] = g * (hp[jj] - nn[jj]) * zz[jj] * (1.f - zz[jj]);
+          dr[jj] = dn[jj] * hn[jj] * rr[jj] * (1.f - rr[jj]);
+          dnr[jj] = dn[jj] * rr[jj];
+          dh_rec[jj] = g * zz[jj];
+          db_r[jj] += dr[jj];
+          db_z[jj] += dz[jj];
+          db_n[jj] += dn[jj];
+          db_hn[jj] += dnr[jj];
+        }
+        if (step + 1 < T) {
+          bf16* x = xb + (long long)b * K3 + ju;
+          st_bf16u<UPT>(x, dr);
+          st_bf16u<UPT>(x + H, dz);
+          st_bf16u<UPT>(x + 2 * H, dnr);
+          if (tid == 0) GRU_STAMP(5);
+          fence_proxy_async_global();
+          if (tid == 0) GRU_STAMP(6);
+        }
+      }
+      if (step + 1 < T) {
+        epi_barrier();
+        if (tid == 0) {
+          GRU_STAMP(7);
+          grid_arrive(ctr);
+          GRU_STAMP(9);
+        }
+      }
+      if (active) {
+        bf16* o = p.dgi + m * (p.ndir * K3) + dir * K3 + ju;
+        st_stream_bf16u<UPT>(o, dr);
+        st_stream_bf16u<UPT>(o + H, dz);
+        st_stream_bf16u<UPT>(o + 2 * H, dn);
+        st_stream_bf16u<UPT>(p.dghn + m * D + dir * H + ju, dnr);
+      }
+      if (tid == 0) GRU_STAMP(10);
+    }
+    if (active) {
+#pragma unroll
+      for (int jj = 0; jj < UPT; ++jj) {
+        const int bi = dir * K3 + ju + jj;
+        atomicAdd(p.dbih + bi, db_r[jj]);
+        atomicAdd(p.dbih + bi + H, db_z[jj]);
+        atomicAdd(p.dbih + bi + 2 * H, db_n[jj]);
+        atomicAdd(p.dbhh + bi, db_r[jj]);
+        atomicAdd(p.dbhh + bi + H, db_z[jj]);
+        atomicAdd(p.dbhh + bi + 2 * H, db_hn[jj]);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols,
                       long long ld, int box_rows);
 
@@ -1313,6 +1912,16 @@ static unsigned long long* g_gru_dbg = nullptr;
 static int g_gru_ablate = 0;
 static int g_gru_ksplit = 1;   // developer knob: 0 disables the K-split backward kernel
 
+// Which K-split flavour: the transposed-accumulator kernels (gru_*_kt_kernel) win while the batch
+// is small.  Measured us/step at H = 1024 (kt | ks): forward 3.8 | 4.8 at 8 rows, 4.3 | 4.9 at 16,
+// 5.3 | 5.4 at 32, 7.9 | 7.1 at 64; backward 4.6 | 5.3 at 8, 5.4 | 5.4 at 16, 6.2 | 5.8 at 32,
+// 8.3 | 7.8 at 64.  Developer knob (sb_debug_gru_flags): 16 forces them, 8 disables them.
+static bool gru_use_kt(int Bp, bool backward) {
+  if (g_gru_ablate & 8) return false;
+  if (g_gru_ablate & 16) return true;
+  return Bp <= (backward ? 8 : 32);
+}
+
 // cooperative launch with EXACTLY the given cluster size; fails if the grid is not co-resident
 static int gru_launch_exact(const void* kernel, int grid, int cs, size_t smem, void** args,
                             cudaStream_t stream) {
@@ -1361,8 +1970,9 @@ extern "C" int sb_debug_gru_timeline(void* dev_buffer) {
   return SB_OK;
 }
 // developer knobs: 1 / 2: gru_fwd_kernel without the proxy fence / the off-path stores (timing
-// only: results become wrong); 32: disable the K-split forward kernel; 64 / 128: polling mode of
-// the grid barrier in the K-split kernels (see grid_wait)
+// only: results become wrong); 8 / 16: never / always use the transposed-accumulator K-split
+// kernels (default: by batch size, see gru_use_kt); 32: disable the K-split forward kernels;
+// 64 / 128: polling mode of the grid barrier in the K-split kernels (see grid_wait)
 extern "C" int sb_debug_gru_flags(int flags) {
   sb::g_gru_ablate = flags;
   return SB_OK;
@@ -1442,6 +2052,15 @@ extern "C" int sb_gru_fwd(const float* gi, const void* whh_bf16, const float* bh
         if (rc != SB_OK) return rc;
       }
       void* kargs[] = {(void*)&tq[0], (void*)&tq[1], (void*)&q};
+      const size_t kt_smem = (size_t)nq * Bp * 128 + (size_t)nq * 192 * 128 +
+                             (size_t)(2 * KS - 1) * 48 * (Bp + 4) * 4 + 1024 + 512;
+      if (gru_use_kt(Bp, false) && kt_smem <= 227 * 1024) {
+        const void* kt = Bp > 32   ? (const void*)gru_fwd_kt_kernel<4>
+                         : Bp > 16 ? (const void*)gru_fwd_kt_kernel<2>
+                                   : (const void*)gru_fwd_kt_kernel<1>;
+        rc = gru_launch_exact(kt, ndir * nC, KS, kt_smem, kargs, stream);
+        if (rc == SB_OK) return SB_OK;
+      }
       rc = gru_launch_exact((const void*)gru_fwd_ks_kernel, ndir * nC, KS, ks_smem, kargs, stream);
       if (rc == SB_OK) return SB_OK;
     }
@@ -1521,6 +2140,16 @@ extern "C" int sb_gru_bwd(const float* dy, const float* y, const float* gates,
       }
       p.ring = nq; p.gc = 1;
       void* kargs[] = {(void*)&tq[0], (void*)&tq[1], (void*)&p};
+      const size_t ex = (size_t)(2 * KS - 1) * GRU_HC * (Bp + 4) * 4;
+      const size_t kt_smem = (size_t)nq * Bp * 128 + (size_t)nq * 64 * 128 +
+                             std::max(ex, (size_t)8192) + 1024 + 256;
+      if (gru_use_kt(Bp, true) && kt_smem <= 227 * 1024) {
+        const void* kt = Bp > 32   ? (const void*)gru_bwd_kt_kernel<4>
+                         : Bp > 16 ? (const void*)gru_bwd_kt_kernel<2>
+                                   : (const void*)gru_bwd_kt_kernel<1>;
+        rc = gru_launch_exact(kt, ndir * nC_, KS, kt_smem, kargs, stream);
+        if (rc == SB_OK) return SB_OK;
+      }
       rc = gru_launch_exact((const void*)gru_bwd_ks_kernel, ndir * nC_, KS, ks_smem, kargs, stream);
       if (rc == SB_OK) return SB_OK;
     }
