@@ -196,35 +196,47 @@ int sb_sgd_clip_step(float* params, const float* grads, float* momentum_buf, voi
  *                     at logits[b*logit_stride + c], optional log-softmax, arg-max, greedy history
  *                     and end-token count; `done` (device int, may be NULL): != 0 -> no-op
  *   sb_attn_step      the attention alone (NNAttention.forward on the decode path)
+ *   sb_s2s_dout       backward of the output projection for all (step, utterance) rows at once:
+ *                     d_o = dlogits W_fc, o = hx + sx (operand of the time-batched d W_fc)
  *   sb_s2s_attn_bwd / sb_s2s_cell_bwd   gradients of one step (see csrc/s2s.cu)
  *   sb_s2s_check_done greedy stop rule: every row emitted end_tok in the same step
  *   sb_s2s_beam_*     device-side beam bookkeeping with the reference's stable-sort tie order
- * Constraints: H % 4 == 0, H <= 1024, conv kernel width odd and <= 15, beam <= 32.
+ * Layouts that differ from the reference's parameters (transposed once per call by the host
+ * mirror): conv_wT (Kc, H) = NNAttention.conv.weight (H, 1, Kc) transposed; w_ihT / w_hhT (H, 3H)
+ * = GRUCell weights transposed (backward only).  g_conv_wT is (B, ceil(T/24), Kc, H): one slot
+ * per CTA, accumulated over the steps, to be summed over its two leading dims by the caller.
+ * workspace: >= sb_s2s_workspace_size(B, T, H) bytes, its first 4*B bytes ZERO before the first
+ * call (ticket counters; the kernels leave them zero); one workspace serves all steps.
+ * Constraints: H % 4 == 0, conv kernel width odd and <= 15, T <= 6144, beam <= 32.
  * ------------------------------------------------------------------------------------- */
-int sb_attn_step(const float* eh, const float* dhx, const float* ax_prev, const float* conv_w,
+int sb_s2s_workspace_size(int B, int T, int H, size_t* bytes);
+int sb_attn_step(const float* eh, const float* dhx, const float* ax_prev, const float* conv_wT,
                  const float* conv_b, const float* lin_w, float lin_b, int log_t, int B, int T,
-                 int H, int Kc, float* sx, float* ax, void* stream);
+                 int H, int Kc, float* sx, float* ax, void* workspace, size_t workspace_bytes,
+                 void* stream);
 int sb_s2s_cell_fwd(const float* emb, const int* tok, int tok_stride, const float* sx_prev,
                     const float* hx_prev, const float* w_ih, const float* w_hh, const float* b_ih,
                     const float* b_hh, float* hx, float* ix_save, float* gates_save,
                     const int* done, int B, int H, void* stream);
 int sb_s2s_attn_fwd(const float* eh, int eh_bcast, const float* hx, const float* ax_prev,
-                    const float* conv_w, const float* conv_b, const float* lin_w, float lin_b,
+                    const float* conv_wT, const float* conv_b, const float* lin_w, float lin_b,
                     int log_t, int B, int T, int H, int Kc, float* sx, float* ax,
                     const float* fc_w, const float* fc_b, int C, float* logits,
                     long long logit_stride, float* logp, int* argmax, int* history,
                     int hist_stride, int hist_col, int* end_count, int end_tok, const int* done,
-                    void* stream);
+                    void* workspace, size_t workspace_bytes, void* stream);
+int sb_s2s_dout(const float* dlogits, const float* fc_w, const float* hx, const float* sx,
+                float* d_o, float* o_all, long long rows, int C, int H, void* stream);
 int sb_s2s_attn_bwd(const float* eh, const float* hx, const float* hx_prev, const float* ax_prev,
-                    const float* ax, const float* sx, const float* conv_w, const float* conv_b,
-                    const float* lin_w, float lin_b, const float* fc_w, const float* dlogits,
-                    long long dl_stride, const float* d_ix_next, const float* d_ax_next,
-                    const float* d_hx_next, const float* gates, float* d_eh, float* d_ax_prev,
-                    float* d_gi, float* d_gh, float* d_hx_direct, float* o_save, float* g_conv_w,
-                    float* g_conv_b, float* g_lin_w, float* g_lin_b, int log_t, int B, int T, int H,
-                    int Kc, int C, void* stream);
+                    const float* ax, const float* conv_wT, const float* conv_b,
+                    const float* lin_w, const float* d_o, const float* d_ix_next,
+                    const float* d_ax_next, const float* d_hx_next, const float* gates,
+                    float* d_eh, float* d_ax_prev, float* d_gi, float* d_gh, float* d_hx_direct,
+                    float* g_conv_wT, float* g_conv_b, float* g_lin_w, float* g_lin_b, int log_t,
+                    int B, int T, int H, int Kc, void* workspace, size_t workspace_bytes,
+                    void* stream);
 int sb_s2s_cell_bwd(const float* d_gi, const float* d_gh, const float* d_hx_direct,
-                    const float* w_ih, const float* w_hh, float* d_ix, float* d_hx_prev, int B,
+                    const float* w_ihT, const float* w_hhT, float* d_ix, float* d_hx_prev, int B,
                     int H, void* stream);
 int sb_s2s_check_done(const int* end_count, int B, int* done, int* nsteps, int step1, void* stream);
 int sb_s2s_beam_state_size(size_t* bytes);
@@ -342,7 +354,9 @@ int sb_debug_gru_timeline(void* dev_buffer);
  * the CTA-pair (tcgen05 cta_group::2) kernel. */
 int sb_debug_gemm_mt1(int force);
 int sb_debug_umma_mn(int lbo_bytes, int sbo_bytes, int kadv_bytes);
-/* Developer hook: timing ablations of the forward GRU kernel (results become wrong; 0 = off). */
+/* Developer hook, GRU kernel selection / timing knobs (0 = defaults): 8 / 16 = never / always use
+ * the transposed-accumulator K-split kernels, 32 = no K-split forward kernel, 64 / 128 = polling
+ * mode of the grid barrier; 1 / 2 are timing ablations (results become wrong). */
 int sb_debug_gru_flags(int flags);
 /* Developer hook: enable (1, default) / disable (0) the K-split backward GRU kernel. */
 int sb_debug_gru_ksplit(int enable);

@@ -38,15 +38,16 @@ SIGNATURES = {
     "sb_sumsq_workspace_size": (_c_int, [ctypes.POINTER(_c_sz)]),
     "sb_sumsq": (_c_int, [_vp, _c_ll, _vp, _vp, _vp]),
     "sb_sgd_clip_step": (_c_int, [_vp, _vp, _vp, _vp, _c_ll, _vp, _fl, _fl, _fl, _vp]),
+    "sb_s2s_workspace_size": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_sz)]),
     "sb_attn_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _fl, _c_int, _c_int, _c_int, _c_int,
-                              _c_int, _vp, _vp, _vp]),
+                              _c_int, _vp, _vp, _vp, _c_sz, _vp]),
     "sb_s2s_cell_fwd": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _c_int, _c_int, _vp]),
     "sb_s2s_attn_fwd": (_c_int, [_vp, _c_int, _vp, _vp, _vp, _vp, _vp, _fl, _c_int, _c_int, _c_int,
                                  _c_int, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp, _c_ll, _vp, _vp,
-                                 _vp, _c_int, _c_int, _vp, _c_int, _vp, _vp]),
-    "sb_s2s_attn_bwd": (_c_int, [_vp] * 9 + [_fl, _vp, _vp, _c_ll] + [_vp] * 14 +
-                        [_c_int] * 6 + [_vp]),
+                                 _vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _c_sz, _vp]),
+    "sb_s2s_dout": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_ll, _c_int, _c_int, _vp]),
+    "sb_s2s_attn_bwd": (_c_int, [_vp] * 22 + [_c_int] * 5 + [_vp, _c_sz, _vp]),
     "sb_s2s_cell_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _vp]),
     "sb_s2s_check_done": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _vp]),
     "sb_s2s_beam_state_size": (_c_int, [ctypes.POINTER(_c_sz)]),

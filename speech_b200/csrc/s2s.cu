@@ -9,25 +9,27 @@
 //            score_t = w . relu(eh_t + hx_u + conv1d(ax_{u-1})_t) + b   (:345-353)
 //            ax_u = softmax_t(score [* log T]);  sx_u = sum_t ax_u[t] eh_t   (:354-359)
 //            out_u = fc(hx_u + sx_u)                                    (:108)
-// as TWO kernels per token in each direction of time:
-//   s2s_cell_fwd      embedding gather + context add + GRU cell, fp32 on CUDA cores (the (B x 2H)
-//                     x (2H x 3H) product of one token is 0.1 GFLOP: launch-latency-, not
-//                     throughput-bound; one warp per hidden unit, lanes over the batch);
-//   s2s_attn_fwd      one CTA per utterance: ONE pass over the encoder states with an online
-//                     softmax (the reference reads them twice and materialises a (B,T,H)
-//                     temporary), then the output projection, and for the decode path the
-//                     arg-max token / log-softmax of the step, so that greedy and beam decoding
-//                     never leave the device;
-//   s2s_attn_bwd      gradient of the step's attention + output projection for one utterance:
-//                     two passes over the encoder states (softmax Jacobian needs sum_t a_t da_t),
-//                     accumulates d eh in place, emits d ax_{u-1}, the per-utterance parameter
-//                     gradients of the attention, and the gate pre-activation gradients of the
-//                     cell (so the cell's backward is a pure matrix product);
-//   s2s_cell_bwd      d ix = d gi W_ih, d hx_{u-1} = d gh W_hh + z * d hx_u (lanes over the batch).
-// The weight gradients of the cell, the embedding and fc are time-batched contractions over all
-// (u, b) rows and run once per sequence on the tcgen05 GEMM (SB_GEMM_A_MN | SB_GEMM_B_MN).
-// Everything is fp32 (the reference's arithmetic); roofline: HBM/L2 bandwidth on eh per token
-// (B*T*H*4 bytes forward, 3x that backward), in practice launch/latency-bound at B <= 64.
+// as two kernels per token forward and three backward:
+//   s2s_cell_fwd      embedding gather + context add + GRU cell in fp32 on CUDA cores: one warp
+//                     per hidden unit, lanes over K, 16 batch rows in registers (every weight is
+//                     read once per token: 6 H^2 floats from L2, FMA-bound);
+//   s2s_attn_fwd      grid (T/24, B): every CTA scores 24 frames of one utterance with ONE pass
+//                     over its encoder states (online softmax; the reference reads them twice and
+//                     materialises a (B,T,H) temporary); the utterance's last CTA (ticket counter)
+//                     combines the partials in a fixed order and runs the output projection and,
+//                     for the decode path, the arg-max token / log-softmax of the step, so that
+//                     greedy and beam decoding never leave the device;
+//   s2s_attn_bwd_a/b  gradient of the step's attention on the same grid (the softmax Jacobian
+//                     needs sum_t a_t da_t over all frames: kernel A; everything else: kernel B),
+//                     accumulates d eh in place, emits d ax_{u-1}, the parameter gradients of the
+//                     attention, and the gate pre-activation gradients of the cell (so the cell's
+//                     backward is a pure matrix product);
+//   s2s_cell_bwd      d ix = d gi W_ih, d hx_{u-1} = d gh W_hh + z * d hx_u on transposed weights.
+// The output-projection backward (d o = dlogits W_fc) of ALL steps is one launch before the loop
+// (s2s_dout); the weight gradients of the cell, the embedding and fc are time-batched contractions
+// over all (u, b) rows and run once per sequence on the tcgen05 GEMM (SB_GEMM_A_MN | SB_GEMM_B_MN).
+// Everything is fp32 (the reference's arithmetic); roofline: L2 bandwidth on eh and the cell
+// weights per token (B*T*H*4 bytes forward, 3x that backward, + 24 H^2), in practice launch-bound.
 #include "common.cuh"
 #include <math.h>
 #include <string.h>
@@ -36,14 +38,38 @@
 
 namespace sb {
 
-static constexpr int S2S_UPC = 8;        // hidden units per CTA of the cell kernels (one per warp)
-static constexpr int S2S_KC = 512;       // K chunk staged in shared memory
+static constexpr int CELL_WARPS = 4;     // warps per CTA of the cell kernels
+static constexpr int CELL_NB = 8;        // batch rows per CTA (accumulators live in registers)
 static constexpr int ATT_THREADS = 256;
-static constexpr int ATT_MAXR = 32;      // H <= 32*32 = 1024
+static constexpr int ATT_NW = ATT_THREADS / 32;
+static constexpr int ATT_FG = 3;                        // consecutive frames per warp
+static constexpr int ATT_TT = ATT_NW * ATT_FG;          // frames per CTA
+static constexpr int ATT_KMAX = 16;                     // taps of the location conv: odd, <= 15
+static constexpr int ATT_WIN = ATT_FG + ATT_KMAX - 1;   // alignment window of one frame group
+static constexpr int ATT_MAX_TS = 256;                  // CTAs per utterance (T <= 6144)
+
+SB_DEVINL float dot4(const float4 a, const float4 b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+SB_DEVINL float4 add4(const float4 a, const float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+// a * s + c
+SB_DEVINL float4 fma4(const float4 a, const float s, const float4 c) {
+  return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w));
+}
 
 // ------------------------------------------------------------------------------------------------
-// cell forward
+// cell forward.  The (B x 2H) x (2H x 3H) product of one token is 0.1 GFLOP, but on a cold chain
+// of L2 round trips (~1 us each): the kernel is built to have as few of them as possible.  One
+// warp per hidden unit: its six weight rows (r, z, n of W_ih and W_hh), one K chunk of 512 at a
+// time, are loaded into REGISTERS up front (24 independent 16-byte loads per lane, one round
+// trip) while the CTA stages the 8 batch rows of ix = emb[tok] + sx and of hx in shared memory;
+// the products then run from registers and shared memory only.
 // ------------------------------------------------------------------------------------------------
+static constexpr int CELL_KC = 512;      // K chunk of the forward cell (weights in registers)
+static constexpr int CELL_KCB = 768;     // K chunk of the backward cell
+
 struct CellFwdParams {
   const float* emb;       // [Vocab][H]
   const int* tok;         // token of row b at tok[b * tok_stride]
@@ -61,84 +87,148 @@ struct CellFwdParams {
   int B, H;
 };
 
-__global__ void __launch_bounds__(32 * S2S_UPC) s2s_cell_fwd_kernel(const CellFwdParams p) {
-  extern __shared__ float cell_smem[];
+__global__ void __launch_bounds__(32 * CELL_WARPS) s2s_cell_fwd_kernel(const CellFwdParams p) {
+  extern __shared__ float4 cell_smem[];
   if (p.done && *p.done) return;
   const int H = p.H, B = p.B;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int j = blockIdx.x * S2S_UPC + warp;           // this warp's hidden unit
-  const int ld = S2S_KC + 4;                            // padded row: conflict-free float4 reads
-  float* xs = cell_smem;                                // [32][ld]  ix chunk
-  float* hs = cell_smem + 32 * ld;                      // [32][ld]  hx_prev chunk
-  for (int b0 = 0; b0 < B; b0 += 32) {
-    const int b = b0 + lane;
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // gi_r, gi_z, gi_n, gh_r, gh_z, gh_n
-    for (int k0 = 0; k0 < H; k0 += S2S_KC) {
-      const int kc = min(S2S_KC, H - k0);
-      __syncthreads();
-      // stage ix = emb[tok] + sx_prev and hx_prev for rows b0..b0+31, columns k0..k0+kc
-      for (int e = tid; e < 32 * (kc / 4); e += 32 * S2S_UPC) {
-        const int r = e / (kc / 4), c4 = e % (kc / 4);
-        const int rb = b0 + r;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), h = x;
-        if (rb < B) {
-          const int tk = p.tok[(long long)rb * p.tok_stride];
-          x = __ldg(reinterpret_cast<const float4*>(p.emb + (long long)tk * H + k0) + c4);
-          if (p.sx_prev) {
-            const float4 s = __ldg(reinterpret_cast<const float4*>(p.sx_prev + (long long)rb * H + k0) + c4);
-            x.x += s.x; x.y += s.y; x.z += s.z; x.w += s.w;
-          }
-          h = __ldg(reinterpret_cast<const float4*>(p.hx_prev + (long long)rb * H + k0) + c4);
-          if (p.ix_save && blockIdx.x == 0)
-            reinterpret_cast<float4*>(p.ix_save + (long long)rb * H + k0)[c4] = x;
-        }
-        reinterpret_cast<float4*>(xs + r * ld)[c4] = x;
-        reinterpret_cast<float4*>(hs + r * ld)[c4] = h;
-      }
-      __syncthreads();
-      if (j < H) {
-        const float* wi = p.w_ih + (long long)j * H + k0;
-        const float* wh = p.w_hh + (long long)j * H + k0;
-        const float4* xr = reinterpret_cast<const float4*>(xs + lane * ld);
-        const float4* hr = reinterpret_cast<const float4*>(hs + lane * ld);
-#pragma unroll 4
-        for (int c4 = 0; c4 < kc / 4; ++c4) {
-          const float4 x = xr[c4], h = hr[c4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = min(blockIdx.x * CELL_WARPS + warp, H - 1);   // (clamped: every warp takes part in the barriers)
+  const bool owner = blockIdx.x * CELL_WARPS + warp < H;
+  const int b0 = blockIdx.y * CELL_NB;
+  const int nb = min(CELL_NB, B - b0);
+  float4* xs = cell_smem;                                // [NB][KC/4] ix chunk
+  float4* hs = cell_smem + CELL_NB * (CELL_KC / 4);      // [NB][KC/4] hx_prev chunk
+  float acc[CELL_NB][6];
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(wi + (long long)g * H * H) + c4);
-            const float4 c = __ldg(reinterpret_cast<const float4*>(wh + (long long)g * H * H) + c4);
-            acc[g] += a.x * x.x + a.y * x.y + a.z * x.z + a.w * x.w;
-            acc[3 + g] += c.x * h.x + c.y * h.y + c.z * h.z + c.w * h.w;
+  for (int b = 0; b < CELL_NB; ++b)
+#pragma unroll
+    for (int d = 0; d < 6; ++d) acc[b][d] = 0.f;
+  const long long gstr = (long long)H * H / 4;          // float4s between the gates' rows
+  for (int kc0 = 0; kc0 < H; kc0 += CELL_KC) {
+    const int nk4 = min(CELL_KC, H - kc0) / 4;
+    const float4* wi = reinterpret_cast<const float4*>(p.w_ih + (long long)j * H + kc0);
+    const float4* wh = reinterpret_cast<const float4*>(p.w_hh + (long long)j * H + kc0);
+    float4 w[6][CELL_KC / 128];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int i = 0; i < CELL_KC / 128; ++i) {
+        const int idx = lane + 32 * i;
+        w[g][i] = idx < nk4 ? __ldg(wi + g * gstr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        w[3 + g][i] = idx < nk4 ? __ldg(wh + g * gstr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    __syncthreads();                                     // the previous chunk has been consumed
+    for (int e = tid; e < CELL_NB * nk4; e += 32 * CELL_WARPS) {
+      const int r = e / nk4, c4 = e - r * nk4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f), h = x;
+      if (r < nb) {
+        const long long ro = (long long)(b0 + r) * H + kc0;
+        const long long tk = p.tok[(long long)(b0 + r) * p.tok_stride];
+        x = __ldg(reinterpret_cast<const float4*>(p.emb + tk * H + kc0) + c4);
+        if (p.sx_prev) {
+          const float4 sv = __ldg(reinterpret_cast<const float4*>(p.sx_prev + ro) + c4);
+          x.x += sv.x; x.y += sv.y; x.z += sv.z; x.w += sv.w;
+        }
+        h = __ldg(reinterpret_cast<const float4*>(p.hx_prev + ro) + c4);
+        if (p.ix_save && blockIdx.x == 0) reinterpret_cast<float4*>(p.ix_save + ro)[c4] = x;
+      }
+      xs[r * (CELL_KC / 4) + c4] = x;
+      hs[r * (CELL_KC / 4) + c4] = h;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < CELL_NB; ++b) {
+      if (b < nb) {
+#pragma unroll
+        for (int i = 0; i < CELL_KC / 128; ++i) {
+          const int idx = lane + 32 * i;
+          if (idx < nk4) {
+            const float4 x = xs[b * (CELL_KC / 4) + idx], h = hs[b * (CELL_KC / 4) + idx];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              acc[b][g] += dot4(w[g][i], x);
+              acc[b][3 + g] += dot4(w[3 + g][i], h);
+            }
           }
         }
       }
     }
-    if (j < H && b < B) {
-      const float gir = acc[0] + p.b_ih[j], giz = acc[1] + p.b_ih[H + j], gin = acc[2] + p.b_ih[2 * H + j];
-      const float ghr = acc[3] + p.b_hh[j], ghz = acc[4] + p.b_hh[H + j], ghn = acc[5] + p.b_hh[2 * H + j];
-      const float r = 1.f / (1.f + expf(-(gir + ghr)));
-      const float z = 1.f / (1.f + expf(-(giz + ghz)));
-      const float n = tanhf(gin + r * ghn);
-      const float hp = p.hx_prev[(long long)b * H + j];
-      p.hx[(long long)b * H + j] = (1.f - z) * n + z * hp;
-      if (p.gates_save) {
-        float* g = p.gates_save + (long long)b * 4 * H + j;
-        g[0] = r; g[H] = z; g[2 * H] = n; g[3 * H] = ghn;
+  }
+  float mine[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int b = 0; b < CELL_NB; ++b) {
+    if (b < nb) {
+#pragma unroll
+      for (int d = 0; d < 6; ++d) {
+        const float v = warp_sum(acc[b][d]);
+        if (lane == b) mine[d] = v;
       }
+    }
+  }
+  if (owner && lane < nb) {
+    const int b = b0 + lane;
+    const float gir = mine[0] + p.b_ih[j], giz = mine[1] + p.b_ih[H + j], gin = mine[2] + p.b_ih[2 * H + j];
+    const float ghr = mine[3] + p.b_hh[j], ghz = mine[4] + p.b_hh[H + j], ghn = mine[5] + p.b_hh[2 * H + j];
+    const float r = 1.f / (1.f + expf(-(gir + ghr)));
+    const float z = 1.f / (1.f + expf(-(giz + ghz)));
+    const float n = tanhf(gin + r * ghn);
+    const float hp = p.hx_prev[(long long)b * H + j];
+    p.hx[(long long)b * H + j] = (1.f - z) * n + z * hp;
+    if (p.gates_save) {
+      float* g = p.gates_save + (long long)b * 4 * H + j;
+      g[0] = r; g[H] = z; g[2 * H] = n; g[3 * H] = ghn;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// attention + output projection forward (one CTA per utterance / beam entry)
+// attention + output projection forward.
+//
+// Grid (ceil(T/24), B): a CTA owns 24 consecutive frames of one utterance, a warp 3 of them.  The
+// warp keeps the 3+14 alignment values its location-conv window needs in registers, walks over
+// h with lanes (coalesced reads of eh, of the TRANSPOSED conv weights [Kc][H] and of the
+// query), and produces 3 scores; an online-softmax partial (max, sum, weighted eh sum) per warp
+// is combined per CTA and written to the workspace.  The LAST CTA of the utterance to finish (a
+// ticket counter) combines the partials in a fixed order - bit-reproducible - normalises the
+// alignment, and runs the output projection / arg-max / log-softmax of the step.
 // ------------------------------------------------------------------------------------------------
+struct AttnWs {
+  float* score;        // [B][T]
+  float* m;            // [B][TS]
+  float* l;            // [B][TS]
+  float* acc;          // [B][TS][H]
+  float* aux;          // [B][TS][H]   (backward: second per-CTA partial)
+  float* s;            // [B][TS]      (backward: per-CTA scalars)
+  float* s2;           // [B][TS]
+  unsigned int* cnt;   // [B] tickets, zero between launches
+};
+
+static size_t attn_ws_bytes(int B, int T, int H) {
+  const size_t TS = (size_t)(T + ATT_TT - 1) / ATT_TT;
+  return sizeof(float) * ((size_t)B * T + 4 * (size_t)B * TS + 2 * (size_t)B * TS * H) +
+         sizeof(unsigned int) * (size_t)B + 64;
+}
+static AttnWs attn_ws_carve(void* ws, int B, int T, int H) {
+  const size_t TS = (size_t)(T + ATT_TT - 1) / ATT_TT;
+  AttnWs w;
+  w.cnt = reinterpret_cast<unsigned int*>(ws);           // first: the caller zeroes B words once
+  float* f = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + (((size_t)B * 4 + 63) & ~(size_t)63));
+  w.score = f; f += (size_t)B * T;
+  w.m = f; f += (size_t)B * TS;
+  w.l = f; f += (size_t)B * TS;
+  w.s = f; f += (size_t)B * TS;
+  w.s2 = f; f += (size_t)B * TS;
+  w.acc = f; f += (size_t)B * TS * H;
+  w.aux = f;
+  return w;
+}
+
 struct AttnFwdParams {
-  const float* eh;        // (Beh, T, H) encoder states; row b uses utterance b % Beh... see eh_bcast
+  const float* eh;        // (Beh, T, H) encoder states
   int eh_bcast;           // 1: every row attends over utterance 0 (beam search of one utterance)
   const float* hx;        // (B, H) decoder state of this step
   const float* ax_prev;   // (B, T) or null
-  const float* conv_w;    // (H, Kc)
+  const float* conv_wT;   // (Kc, H)  transposed location-conv weights
   const float* conv_b;    // (H)
   const float* lin_w;     // (H)
   float lin_b;
@@ -156,110 +246,151 @@ struct AttnFwdParams {
   int* end_count;         // += 1 when this row's arg-max == end_tok (or null)
   int end_tok;
   const int* done;        // device flag: != 0 -> do nothing
+  AttnWs ws;
   int B, T, H, Kc, C, log_t;
 };
 
+// the warp's alignment window: a[i] = ax_prev[tw + i - pad] (zero outside [0, T))
+SB_DEVINL void load_window(const float* ax_prev_b, int tw, int pad, int T, int Kc,
+                           float (&a)[ATT_WIN]) {
+#pragma unroll
+  for (int i = 0; i < ATT_WIN; ++i) {
+    const int tt = tw + i - pad;
+    a[i] = (ax_prev_b && i < ATT_FG + Kc - 1 && tt >= 0 && tt < T) ? __ldg(ax_prev_b + tt) : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(ATT_THREADS) s2s_attn_fwd_kernel(const AttnFwdParams p) {
   extern __shared__ float att_smem[];
+  __shared__ int s_last;
   if (p.done && *p.done) return;
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, ts = blockIdx.x, TS = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = p.T, H = p.H, Kc = p.Kc, pad = (Kc - 1) / 2;
-  float* axp = att_smem;                       // [T + Kc - 1]  zero-padded previous alignment
-  float* cw = axp + T + Kc - 1;                // [H * Kc]
-  float* dc = cw + H * Kc;                     // [H] hx + conv bias
-  float* lw = dc + H;                          // [H]
-  float* score = lw + H;                       // [T]
-  float* wstat = score + T;                    // [8][2] per-warp (max, sum)
-  float* wsx = wstat + 16;                     // [8][H] per-warp weighted sums; later o = hx + sx
+  float* wacc = att_smem;                      // [NW][H] per-warp weighted sums; later o, logits
+  float* wst = wacc + ATT_NW * H;              // [NW][2] per-warp (max, sum)
+  float* sct = wst + 2 * ATT_NW;               // [TS] scale of each CTA partial (final combine)
   const bool has_prev = p.ax_prev != nullptr;
-
-  for (int k = tid; k < T + Kc - 1; k += ATT_THREADS) {
-    const int t = k - pad;
-    axp[k] = (has_prev && t >= 0 && t < T) ? p.ax_prev[(size_t)b * T + t] : 0.f;
-  }
-  if (has_prev)
-    for (int k = tid; k < H * Kc; k += ATT_THREADS) cw[k] = p.conv_w[k];
-  for (int h = tid; h < H; h += ATT_THREADS) {
-    dc[h] = p.hx[(size_t)b * H + h] + (has_prev ? p.conv_b[h] : 0.f);
-    lw[h] = p.lin_w[h];
-  }
-  __syncthreads();
-
   const float tscale = p.log_t ? logf((float)T) : 1.0f;
   const float* eh = p.eh + (p.eh_bcast ? 0 : (size_t)b * T * H);
-  float m_run = -INFINITY, l_run = 0.f;
-  float acc[ATT_MAXR];
-#pragma unroll
-  for (int r = 0; r < ATT_MAXR; ++r) acc[r] = 0.f;
+  const int tw = ts * ATT_TT + warp * ATT_FG;
+  const int nf = max(0, min(ATT_FG, T - tw));
 
-  for (int t = warp; t < T; t += ATT_THREADS / 32) {
-    float e[ATT_MAXR];
-    float part = 0.f;
+  float a[ATT_WIN];
+  load_window(has_prev ? p.ax_prev + (size_t)b * T : nullptr, tw, pad, T, Kc, a);
+  // lanes over h in groups of four (16-byte loads): the h loop is a chain of L2 round trips, so it
+  // has to be short - H/128 iterations
+  const int H4 = H >> 2;
+  const float4* eh4 = reinterpret_cast<const float4*>(eh);
+  float part[ATT_FG];
 #pragma unroll
-    for (int r = 0; r < ATT_MAXR; ++r) {
-      const int h = lane + 32 * r;
-      e[r] = 0.f;
-      if (h < H) {
-        e[r] = __ldg(eh + (size_t)t * H + h);
-        float v = e[r] + dc[h];
-        if (has_prev) {
-          const float* c = cw + h * Kc;
-          float s = 0.f;
-          for (int k = 0; k < Kc; ++k) s += c[k] * axp[t + k];
-          v += s;
+  for (int f = 0; f < ATT_FG; ++f) part[f] = 0.f;
+  if (nf > 0) {
+    for (int h4 = lane; h4 < H4; h4 += 32) {
+      float4 dch = reinterpret_cast<const float4*>(p.hx + (size_t)b * H)[h4];
+      if (has_prev) dch = add4(dch, __ldg(reinterpret_cast<const float4*>(p.conv_b) + h4));
+      const float4 lwh = __ldg(reinterpret_cast<const float4*>(p.lin_w) + h4);
+      float4 c[ATT_KMAX];
+#pragma unroll
+      for (int k = 0; k < ATT_KMAX; ++k)
+        c[k] = (has_prev && k < Kc) ? __ldg(reinterpret_cast<const float4*>(p.conv_wT) + (size_t)k * H4 + h4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 e[ATT_FG];
+#pragma unroll
+      for (int f = 0; f < ATT_FG; ++f)
+        e[f] = f < nf ? __ldg(eh4 + (size_t)(tw + f) * H4 + h4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int f = 0; f < ATT_FG; ++f) {
+        if (f < nf) {
+          float4 v = add4(e[f], dch);
+          if (has_prev) {
+            float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < ATT_KMAX; ++k) sacc = fma4(c[k], a[f + k], sacc);
+            v = add4(v, sacc);
+          }
+          part[f] += lwh.x * fmaxf(v.x, 0.f) + lwh.y * fmaxf(v.y, 0.f) + lwh.z * fmaxf(v.z, 0.f) +
+                     lwh.w * fmaxf(v.w, 0.f);
         }
-        part += lw[h] * fmaxf(v, 0.f);
       }
     }
-    const float sc = (warp_sum(part) + p.lin_b) * tscale;
-    if (lane == 0) score[t] = sc;
-    const float m_new = fmaxf(m_run, sc);
-    const float rescale = __expf(m_run - m_new);   // exp(-inf) = 0 on the first frame
-    const float w = __expf(sc - m_new);
-    l_run = l_run * rescale + w;
-#pragma unroll
-    for (int r = 0; r < ATT_MAXR; ++r) acc[r] = acc[r] * rescale + w * e[r];
-    m_run = m_new;
   }
-  if (lane == 0) { wstat[warp * 2] = m_run; wstat[warp * 2 + 1] = l_run; }
+  float sc[ATT_FG], m_w = -INFINITY;
 #pragma unroll
-  for (int r = 0; r < ATT_MAXR; ++r) {
-    const int h = lane + 32 * r;
-    if (h < H) wsx[warp * H + h] = acc[r];
-  }
-  __syncthreads();
-  float m = -INFINITY;
-  for (int w = 0; w < ATT_THREADS / 32; ++w) m = fmaxf(m, wstat[w * 2]);
-  float l = 0.f;
-  for (int w = 0; w < ATT_THREADS / 32; ++w)
-    l += (wstat[w * 2] == -INFINITY) ? 0.f : wstat[w * 2 + 1] * __expf(wstat[w * 2] - m);
-  const float inv = 1.0f / l;
-  float sxv[(ATT_MAXR * 32 + ATT_THREADS - 1) / ATT_THREADS];
-  {
-    int q = 0;
-    for (int h = tid; h < H; h += ATT_THREADS, ++q) {
-      float s = 0.f;
-      for (int w = 0; w < ATT_THREADS / 32; ++w)
-        if (wstat[w * 2] != -INFINITY) s += wsx[w * H + h] * __expf(wstat[w * 2] - m);
-      sxv[q] = s * inv;
-      p.sx[(size_t)b * H + h] = sxv[q];
+  for (int f = 0; f < ATT_FG; ++f) {
+    sc[f] = -INFINITY;
+    if (f < nf) {
+      sc[f] = (warp_sum(part[f]) + p.lin_b) * tscale;
+      m_w = fmaxf(m_w, sc[f]);
+      if (lane == 0) p.ws.score[(size_t)b * T + tw + f] = sc[f];
     }
   }
-  for (int t = tid; t < T; t += ATT_THREADS) p.ax[(size_t)b * T + t] = __expf(score[t] - m) * inv;
+  float w[ATT_FG], l_w = 0.f;
+#pragma unroll
+  for (int f = 0; f < ATT_FG; ++f) {
+    w[f] = f < nf ? __expf(sc[f] - m_w) : 0.f;
+    l_w += w[f];
+  }
+  for (int h4 = lane; h4 < H4; h4 += 32) {
+    float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < ATT_FG; ++f)
+      if (f < nf) sacc = fma4(__ldg(eh4 + (size_t)(tw + f) * H4 + h4), w[f], sacc);
+    reinterpret_cast<float4*>(wacc + warp * H)[h4] = sacc;
+  }
+  if (lane == 0) { wst[warp * 2] = m_w; wst[warp * 2 + 1] = l_w; }
+  __syncthreads();
+  // ---- CTA partial ----
+  float m_c = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < ATT_NW; ++q) m_c = fmaxf(m_c, wst[q * 2]);
+  float scl[ATT_NW], l_c = 0.f;
+#pragma unroll
+  for (int q = 0; q < ATT_NW; ++q) {
+    scl[q] = wst[q * 2] == -INFINITY ? 0.f : __expf(wst[q * 2] - m_c);
+    l_c += wst[q * 2 + 1] * scl[q];
+  }
+  const size_t slot = (size_t)b * TS + ts;
+  for (int h = tid; h < H; h += ATT_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < ATT_NW; ++q) s += wacc[q * H + h] * scl[q];
+    p.ws.acc[slot * H + h] = s;
+  }
+  if (tid == 0) { p.ws.m[slot] = m_c; p.ws.l[slot] = l_c; }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(p.ws.cnt + b, 1u) == (unsigned int)(TS - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- the utterance's last CTA: combine the TS partials in index order ----
+  float m = -INFINITY;
+  for (int q = 0; q < TS; ++q) m = fmaxf(m, __ldcg(p.ws.m + (size_t)b * TS + q));
+  for (int q = tid; q < TS; q += ATT_THREADS) sct[q] = __expf(__ldcg(p.ws.m + (size_t)b * TS + q) - m);
+  __syncthreads();
+  float l = 0.f;
+  for (int q = 0; q < TS; ++q) l += __ldcg(p.ws.l + (size_t)b * TS + q) * sct[q];
+  const float inv = 1.0f / l;
+  float* o = wacc;                 // [H]   hx + sx
+  float* lg = wacc + H;            // [C]
+  for (int h = tid; h < H; h += ATT_THREADS) {
+    float s = 0.f;
+    for (int q = 0; q < TS; ++q) s += __ldcg(p.ws.acc + ((size_t)b * TS + q) * H + h) * sct[q];
+    s *= inv;
+    p.sx[(size_t)b * H + h] = s;
+    o[h] = p.hx[(size_t)b * H + h] + s;
+  }
+  for (int t = tid; t < T; t += ATT_THREADS)
+    p.ax[(size_t)b * T + t] = __expf(__ldcg(p.ws.score + (size_t)b * T + t) - m) * inv;
+  if (tid == 0) p.ws.cnt[b] = 0u;
   if (!p.fc_w) return;
   // ---- output projection on o = hx + sx (seq2seq.py:108,131-132) ----
-  __syncthreads();                 // everyone is done reading wsx
-  float* o = wsx;                  // [H]
-  float* lg = wsx + H;             // [C]
-  {
-    int q = 0;
-    for (int h = tid; h < H; h += ATT_THREADS, ++q) o[h] = p.hx[(size_t)b * H + h] + sxv[q];
-  }
   __syncthreads();
-  for (int c = warp; c < p.C; c += ATT_THREADS / 32) {
-    const float* w = p.fc_w + (size_t)c * H;
+  for (int c = warp; c < p.C; c += ATT_NW) {
+    const float* wr = p.fc_w + (size_t)c * H;
     float s = 0.f;
-    for (int h = lane; h < H; h += 32) s += __ldg(w + h) * o[h];
+    for (int h = lane; h < H; h += 32) s += __ldg(wr + h) * o[h];
     s = warp_sum(s);
     if (lane == 0) {
       s += p.fc_b[c];
@@ -295,7 +426,37 @@ __global__ void __launch_bounds__(ATT_THREADS) s2s_attn_fwd_kernel(const AttnFwd
 }
 
 // ------------------------------------------------------------------------------------------------
-// attention + output projection backward (one CTA per utterance)
+// backward of the output projection for ALL steps at once (no dependence on the recurrence):
+//   d_o[r, :] = dlogits[r, :] W_fc,   o[r, :] = hx[r, :] + sx[r, :]      r = (step, utterance)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) s2s_dout_kernel(const float* __restrict__ dl,
+                                                       const float* __restrict__ fc_w,
+                                                       const float* __restrict__ hx,
+                                                       const float* __restrict__ sx,
+                                                       float* __restrict__ d_o,
+                                                       float* __restrict__ o_all, int C, int H) {
+  extern __shared__ float dl_s[];
+  const size_t r = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += 256) dl_s[c] = dl[r * C + c];
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += 256) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += dl_s[c] * __ldg(fc_w + (size_t)c * H + h);
+    d_o[r * H + h] = s;
+    o_all[r * H + h] = hx[r * H + h] + sx[r * H + h];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention backward of one step, same (frames, utterance) grid as the forward, two kernels
+// (the softmax Jacobian needs S = sum_t a_t da_t over ALL frames before anything else):
+//   A  da_t = eh_t . d sx + d ax_next[t]; per-CTA partial of S; zeroes d ax_prev
+//   B  d score_t = tscale a_t (da_t - S), back through linear / ReLU / location conv:
+//      d eh += a_t d sx + d pre_t (in place), d ax_prev (window sums; neighbouring CTAs overlap in
+//      at most two contributions per element, so the atomic adds are order-independent), per-CTA
+//      partials of the conv-weight gradient (accumulated over the steps in the CTA's own slot),
+//      of d lin_w and of sum_t d pre_t; the utterance's last CTA (ticket) adds the partials in
+//      index order and emits the gate pre-activation gradients of the cell.
 // ------------------------------------------------------------------------------------------------
 struct AttnBwdParams {
   const float* eh;         // (B, T, H)
@@ -303,182 +464,254 @@ struct AttnBwdParams {
   const float* hx_prev;    // (B, H)
   const float* ax_prev;    // (B, T) or null (first step)
   const float* ax;         // (B, T) this step's alignment (saved by forward)
-  const float* sx;         // (B, H) this step's context (saved by forward)
-  const float* conv_w; const float* conv_b; const float* lin_w; float lin_b;
-  const float* fc_w;       // (C, H)
-  const float* dlogits;    // dlogits[b*dl_stride + c]: gradient of the loss w.r.t. this step's logits
-  long long dl_stride;
+  const float* conv_wT;    // (Kc, H)
+  const float* conv_b; const float* lin_w;
+  const float* d_o;        // (B, H) gradient w.r.t. o = hx + sx of this step (s2s_dout_kernel)
   const float* d_ix_next;  // (B, H) gradient w.r.t. the NEXT step's ix (= d sx through ix = emb + sx); null at the last step
   const float* d_ax_next;  // (B, T) gradient w.r.t. ax from the next step's conv; null at the last step
   const float* d_hx_next;  // (B, H) gradient w.r.t. hx from the next step's cell; null at the last step
   const float* gates;      // (B, 4, H) r, z, n, hn saved by the cell
-  float* d_eh;             // (B, T, H) += 
+  float* d_eh;             // (B, T, H) +=
   float* d_ax_prev;        // (B, T) out (gradient w.r.t. the previous alignment), unused at the first step
   float* d_gi;             // (B, 3H) out: gate pre-activation gradients of the cell (input side)
   float* d_gh;             // (B, 3H) out: (hidden side: the n entry carries r)
   float* d_hx_direct;      // (B, H) out: z * d hx (direct path to hx_prev)
-  float* o_save;           // (B, H) out: hx + sx (operand of the time-batched d fc_w)
-  // per-utterance parameter gradients, accumulated over steps, reduced over b by the caller
-  float* g_conv_w;         // (B, H, Kc) +=
+  // parameter gradients accumulated over the steps, reduced over their leading dims by the caller
+  float* g_conv_wT;        // (B, TS, Kc, H) +=
   float* g_conv_b;         // (B, H) +=
   float* g_lin_w;          // (B, H) +=
   float* g_lin_b;          // (B) +=
-  int B, T, H, Kc, C, log_t;
+  AttnWs ws;
+  int B, T, H, Kc, log_t;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS) s2s_attn_bwd_kernel(const AttnBwdParams p) {
-  extern __shared__ float bw_smem[];
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int T = p.T, H = p.H, Kc = p.Kc, pad = (Kc - 1) / 2;
-  constexpr int NW = ATT_THREADS / 32;
-  float* axp = bw_smem;                        // [T + Kc - 1] zero-padded previous alignment
-  float* daxp = axp + T + Kc - 1;              // [T + Kc - 1] gradient w.r.t. the padded alignment
-  float* cw = daxp + T + Kc - 1;               // [H * Kc]
-  float* dc = cw + H * Kc;                     // [H] hx + conv bias
-  float* lw = dc + H;                          // [H]
-  float* dsx = lw + H;                         // [H] total gradient w.r.t. sx
-  float* dsc = dsx + H;                        // [T] da_t, then d score_t
-  float* red = dsc + T;                        // [NW]
-  float* dhx_att = red + NW;                   // [H] sum_t d pre[t, h]
-  float* gcw = dhx_att + H;                    // [H * Kc] this step's conv weight gradient
-  const bool has_prev = p.ax_prev != nullptr;
-  const float* eh = p.eh + (size_t)b * T * H;
-  const float* axv = p.ax + (size_t)b * T;
-  const float tscale = p.log_t ? logf((float)T) : 1.0f;
-
-  for (int k = tid; k < T + Kc - 1; k += ATT_THREADS) {
-    const int t = k - pad;
-    axp[k] = (has_prev && t >= 0 && t < T) ? p.ax_prev[(size_t)b * T + t] : 0.f;
-    daxp[k] = 0.f;
-  }
-  if (has_prev)
-    for (int k = tid; k < H * Kc; k += ATT_THREADS) { cw[k] = p.conv_w[k]; gcw[k] = 0.f; }
-  // d o = W_fc^T dlogits ; o = hx + sx  ->  d sx = d o + d ix_next ; d hx gets d o as well
-  for (int h = tid; h < H; h += ATT_THREADS) {
-    float s = 0.f;
-    for (int c = 0; c < p.C; ++c)
-      s += p.dlogits[(size_t)b * p.dl_stride + c] * __ldg(p.fc_w + (size_t)c * H + h);
-    dc[h] = p.hx[(size_t)b * H + h] + (has_prev ? p.conv_b[h] : 0.f);
-    lw[h] = p.lin_w[h];
-    dhx_att[h] = s;                                   // (d o; the attention part is added below)
-    dsx[h] = s + (p.d_ix_next ? p.d_ix_next[(size_t)b * H + h] : 0.f);
-    p.o_save[(size_t)b * H + h] = p.hx[(size_t)b * H + h] + p.sx[(size_t)b * H + h];
-  }
+__global__ void __launch_bounds__(ATT_THREADS) s2s_attn_bwd_a_kernel(const AttnBwdParams p) {
+  extern __shared__ float bwa_smem[];
+  const int b = blockIdx.y, ts = blockIdx.x, TS = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = p.T, H = p.H;
+  float* dsx = bwa_smem;             // [H]
+  float* red = dsx + H;              // [NW]
+  for (int h = tid; h < H; h += ATT_THREADS)
+    dsx[h] = p.d_o[(size_t)b * H + h] + (p.d_ix_next ? p.d_ix_next[(size_t)b * H + h] : 0.f);
   __syncthreads();
-  // ---- pass 1: da_t = eh_t . d sx + d ax_next[t];  S = sum_t a_t da_t ----
+  const float* eh = p.eh + (size_t)b * T * H;
+  const int tw = ts * ATT_TT + warp * ATT_FG;
+  const int nf = max(0, min(ATT_FG, T - tw));
+  float part[ATT_FG];
+#pragma unroll
+  for (int f = 0; f < ATT_FG; ++f) part[f] = 0.f;
+  const int H4 = H >> 2;
+  const float4* eh4 = reinterpret_cast<const float4*>(eh);
+  for (int h4 = lane; h4 < H4; h4 += 32) {
+    const float4 d = reinterpret_cast<const float4*>(dsx)[h4];
+#pragma unroll
+    for (int f = 0; f < ATT_FG; ++f)
+      if (f < nf) part[f] += dot4(__ldg(eh4 + (size_t)(tw + f) * H4 + h4), d);
+  }
   float spart = 0.f;
-  for (int t = warp; t < T; t += NW) {
-    float part = 0.f;
-    for (int h = lane; h < H; h += 32) part += __ldg(eh + (size_t)t * H + h) * dsx[h];
-    part = warp_sum(part);
-    const float da = part + (p.d_ax_next ? p.d_ax_next[(size_t)b * T + t] : 0.f);
-    if (lane == 0) dsc[t] = da;
-    spart += axv[t] * da;
+#pragma unroll
+  for (int f = 0; f < ATT_FG; ++f) {
+    if (f < nf) {
+      const size_t ix = (size_t)b * T + tw + f;
+      const float da = warp_sum(part[f]) + (p.d_ax_next ? p.d_ax_next[ix] : 0.f);
+      spart += p.ax[ix] * da;
+      if (lane == 0) {
+        p.ws.score[ix] = da;
+        if (p.ax_prev) p.d_ax_prev[ix] = 0.f;
+      }
+    }
   }
   if (lane == 0) red[warp] = spart;
   __syncthreads();
-  float S = 0.f;
-  for (int w = 0; w < NW; ++w) S += red[w];
-  __syncthreads();
-  // d score_t = tscale * a_t (da_t - S)
-  for (int t = tid; t < T; t += ATT_THREADS) dsc[t] = tscale * axv[t] * (dsc[t] - S);
-  __syncthreads();
-  // ---- pass 2a (warp per frame, lanes over h): through relu / linear / conv input; d eh ----
-  float glw[ATT_MAXR], gdh[ATT_MAXR];
+  if (tid == 0) {
+    float s = 0.f;
 #pragma unroll
-  for (int r = 0; r < ATT_MAXR; ++r) { glw[r] = 0.f; gdh[r] = 0.f; }
-  float glb = 0.f;
+    for (int q = 0; q < ATT_NW; ++q) s += red[q];
+    p.ws.s[(size_t)b * TS + ts] = s;
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS) s2s_attn_bwd_b_kernel(const AttnBwdParams p) {
+  extern __shared__ float bwb_smem[];
+  __shared__ int s_last;
+  const int b = blockIdx.y, ts = blockIdx.x, TS = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = p.T, H = p.H, Kc = p.Kc, pad = (Kc - 1) / 2;
+  float* dsx = bwb_smem;                         // [H]
+  float* dpre_s = dsx + H;                       // [TT][H]  d pre of the CTA's frames
+  float* glw_w = dpre_s + ATT_TT * H;            // [NW][H]  per-warp d lin_w
+  float* win_s = glw_w + ATT_NW * H;             // [NW][WIN] per-warp d alignment windows
+  float* axc = win_s + ATT_NW * ATT_WIN;         // [TT + KMAX - 1] the CTA's alignment window
+  float* red = axc + ATT_TT + ATT_KMAX - 1;      // [NW]
+  const bool has_prev = p.ax_prev != nullptr;
+  const float tscale = p.log_t ? logf((float)T) : 1.0f;
+  const float* eh = p.eh + (size_t)b * T * H;
   float* deh = p.d_eh + (size_t)b * T * H;
-  for (int t = warp; t < T; t += NW) {
-    const float ds = dsc[t];
-    const float at = axv[t];
-    if (lane == 0) glb += ds;
-    float dk[16];                      // this lane's share of d axp[t + k]  (Kc <= 16)
+  const int t0 = ts * ATT_TT;
+  const int tw = t0 + warp * ATT_FG;
+  const int nf = max(0, min(ATT_FG, T - tw));
+  for (int h = tid; h < H; h += ATT_THREADS)
+    dsx[h] = p.d_o[(size_t)b * H + h] + (p.d_ix_next ? p.d_ix_next[(size_t)b * H + h] : 0.f);
+  for (int j = tid; j < ATT_TT + ATT_KMAX - 1; j += ATT_THREADS) {
+    const int tt = t0 - pad + j;
+    axc[j] = (has_prev && tt >= 0 && tt < T) ? p.ax_prev[(size_t)b * T + tt] : 0.f;
+  }
+  float S = 0.f;
+  for (int q = 0; q < TS; ++q) S += p.ws.s[(size_t)b * TS + q];
+  __syncthreads();
+  // ---- (i) warp per frame group ----
+  float ds[ATT_FG], at[ATT_FG];
+  float glb = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) dk[k] = 0.f;
-#pragma unroll
-    for (int r = 0; r < ATT_MAXR; ++r) {
-      const int h = lane + 32 * r;
-      if (h < H) {
-        const float e = __ldg(eh + (size_t)t * H + h);
-        float v = e + dc[h];
-        const float* c = cw + h * Kc;
-        if (has_prev) {
-          float s = 0.f;
-          for (int k = 0; k < Kc; ++k) s += c[k] * axp[t + k];
-          v += s;
-        }
-        const float dpre = v > 0.f ? ds * lw[h] : 0.f;
-        glw[r] += ds * fmaxf(v, 0.f);
-        gdh[r] += dpre;
-        deh[(size_t)t * H + h] += at * dsx[h] + dpre;
-        if (has_prev) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            if (k < Kc) dk[k] += dpre * c[k];
-        }
-      }
-    }
-    if (has_prev) {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        if (k < Kc) {
-          const float sk = warp_sum(dk[k]);
-          if (lane == 0) atomicAdd(&daxp[t + k], sk);   // neighbouring frames overlap in t + k
-        }
-      }
+  for (int f = 0; f < ATT_FG; ++f) {
+    ds[f] = 0.f; at[f] = 0.f;
+    if (f < nf) {
+      const size_t ix = (size_t)b * T + tw + f;
+      at[f] = p.ax[ix];
+      ds[f] = tscale * at[f] * (p.ws.score[ix] - S);
+      glb += ds[f];
     }
   }
-  // ---- pass 2b (thread per h, all frames): conv weight gradient d cw[h, k] in registers ----
+  float a[ATT_WIN];
+  load_window(has_prev ? p.ax_prev + (size_t)b * T : nullptr, tw, pad, T, Kc, a);
+  float dwin[ATT_WIN];
+#pragma unroll
+  for (int i = 0; i < ATT_WIN; ++i) dwin[i] = 0.f;
+  const int H4 = H >> 2;
+  const float4* eh4 = reinterpret_cast<const float4*>(eh);
+  float4* deh4 = reinterpret_cast<float4*>(deh);
+  for (int h4 = lane; h4 < H4; h4 += 32) {
+    float4 dch = reinterpret_cast<const float4*>(p.hx + (size_t)b * H)[h4];
+    if (has_prev) dch = add4(dch, __ldg(reinterpret_cast<const float4*>(p.conv_b) + h4));
+    const float4 lwh = __ldg(reinterpret_cast<const float4*>(p.lin_w) + h4);
+    const float4 dsxh = reinterpret_cast<const float4*>(dsx)[h4];
+    float4 c[ATT_KMAX];
+#pragma unroll
+    for (int k = 0; k < ATT_KMAX; ++k)
+      c[k] = (has_prev && k < Kc) ? __ldg(reinterpret_cast<const float4*>(p.conv_wT) + (size_t)k * H4 + h4)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 e[ATT_FG], dold[ATT_FG];
+#pragma unroll
+    for (int f = 0; f < ATT_FG; ++f) {
+      e[f] = dold[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < nf) {
+        e[f] = __ldg(eh4 + (size_t)(tw + f) * H4 + h4);
+        dold[f] = deh4[(size_t)(tw + f) * H4 + h4];
+      }
+    }
+    float4 glw = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < ATT_FG; ++f) {
+      float4 dpre = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < nf) {
+        float4 v = add4(e[f], dch);
+        if (has_prev) {
+          float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < ATT_KMAX; ++k) sacc = fma4(c[k], a[f + k], sacc);
+          v = add4(v, sacc);
+        }
+        dpre.x = v.x > 0.f ? ds[f] * lwh.x : 0.f;
+        dpre.y = v.y > 0.f ? ds[f] * lwh.y : 0.f;
+        dpre.z = v.z > 0.f ? ds[f] * lwh.z : 0.f;
+        dpre.w = v.w > 0.f ? ds[f] * lwh.w : 0.f;
+        glw.x += ds[f] * fmaxf(v.x, 0.f); glw.y += ds[f] * fmaxf(v.y, 0.f);
+        glw.z += ds[f] * fmaxf(v.z, 0.f); glw.w += ds[f] * fmaxf(v.w, 0.f);
+        deh4[(size_t)(tw + f) * H4 + h4] = add4(dold[f], fma4(dsxh, at[f], dpre));
+        if (has_prev) {
+#pragma unroll
+          for (int k = 0; k < ATT_KMAX; ++k) dwin[f + k] += dot4(dpre, c[k]);
+        }
+      }
+      reinterpret_cast<float4*>(dpre_s + (warp * ATT_FG + f) * H)[h4] = dpre;
+    }
+    reinterpret_cast<float4*>(glw_w + warp * H)[h4] = glw;
+  }
   if (has_prev) {
-    for (int h = tid; h < H; h += ATT_THREADS) {
-      const float* c = cw + h * Kc;
-      float g[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) g[k] = 0.f;
-      const float dch = dc[h], lwh = lw[h];
-      for (int t = 0; t < T; ++t) {
-        float v = __ldg(eh + (size_t)t * H + h) + dch;
-        for (int k = 0; k < Kc; ++k) v += c[k] * axp[t + k];
-        if (v > 0.f) {
-          const float dpre = dsc[t] * lwh;
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            if (k < Kc) g[k] += dpre * axp[t + k];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 16; ++k)
-        if (k < Kc) gcw[h * Kc + k] = g[k];
-    }
-  }
-  // reduce the per-warp partials of d lin_w, d hx (attention part), d lin_b over the 8 warps
-  __syncthreads();
-  float* tmp = cw;                 // [2][H] scratch (cw is no longer needed)
-  for (int h = tid; h < 2 * H; h += ATT_THREADS) tmp[h] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < ATT_MAXR; ++r) {
-    const int h = lane + 32 * r;
-    if (h < H) {
-      atomicAdd(&tmp[h], glw[r]);
-      atomicAdd(&tmp[H + h], gdh[r]);
+    for (int i = 0; i < ATT_WIN; ++i) {
+      const float s = warp_sum(dwin[i]);
+      if (lane == 0) win_s[warp * ATT_WIN + i] = s;
     }
   }
   if (lane == 0) red[warp] = glb;
   __syncthreads();
+  // ---- (ii) d ax_prev of the CTA's window: the warps' windows added in warp order ----
+  if (has_prev) {
+    for (int j = tid; j < ATT_TT + Kc - 1; j += ATT_THREADS) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < ATT_NW; ++q) {
+        const int i = j - q * ATT_FG;
+        if (i >= 0 && i < ATT_FG + Kc - 1) s += win_s[q * ATT_WIN + i];
+      }
+      const int tt = t0 - pad + j;
+      if (tt >= 0 && tt < T) atomicAdd(p.d_ax_prev + (size_t)b * T + tt, s);
+    }
+  }
+  // ---- (iii) thread per h over the CTA's frames: partial sums, conv weight gradient ----
+  const size_t slot = (size_t)b * TS + ts;
+  for (int h = tid; h < H; h += ATT_THREADS) {
+    float gdh = 0.f, glw = 0.f;
+#pragma unroll
+    for (int q = 0; q < ATT_NW; ++q) glw += glw_w[q * H + h];
+    float g[ATT_KMAX];
+#pragma unroll
+    for (int k = 0; k < ATT_KMAX; ++k) g[k] = 0.f;
+#pragma unroll 1
+    for (int q = 0; q < ATT_NW; ++q) {
+      float aw[ATT_WIN];
+#pragma unroll
+      for (int i = 0; i < ATT_WIN; ++i) aw[i] = axc[q * ATT_FG + i < ATT_TT + ATT_KMAX - 1 ? q * ATT_FG + i : 0];
+#pragma unroll
+      for (int f = 0; f < ATT_FG; ++f) {
+        const float d = dpre_s[(q * ATT_FG + f) * H + h];
+        gdh += d;
+#pragma unroll
+        for (int k = 0; k < ATT_KMAX; ++k) g[k] += d * aw[f + k];
+      }
+    }
+    p.ws.acc[slot * H + h] = gdh;
+    p.ws.aux[slot * H + h] = glw;
+    if (has_prev) {
+      float* gw = p.g_conv_wT + slot * (size_t)Kc * H + h;
+#pragma unroll
+      for (int k = 0; k < ATT_KMAX; ++k)
+        if (k < Kc) gw[(size_t)k * H] += g[k];
+    }
+  }
   if (tid == 0) {
     float s = 0.f;
-    for (int w = 0; w < NW; ++w) s += red[w];
-    p.g_lin_b[b] += s;
+#pragma unroll
+    for (int q = 0; q < ATT_NW; ++q) s += red[q];
+    p.ws.s2[slot] = s;
   }
-  // ---- outputs: parameter gradients, d ax_prev, gate gradients of the cell ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(p.ws.cnt + b, 1u) == (unsigned int)(TS - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- the utterance's last CTA: totals in index order, gate gradients of the cell ----
+  if (tid == 0) {
+    float s = 0.f;
+    for (int q = 0; q < TS; ++q) s += __ldcg(p.ws.s2 + (size_t)b * TS + q);
+    p.g_lin_b[b] += s;
+    p.ws.cnt[b] = 0u;
+  }
   const float* gt = p.gates + (size_t)b * 4 * H;
   for (int h = tid; h < H; h += ATT_THREADS) {
-    p.g_lin_w[(size_t)b * H + h] += tmp[h];
-    if (has_prev) p.g_conv_b[(size_t)b * H + h] += tmp[H + h];
+    float gdh = 0.f, glw = 0.f;
+    for (int q = 0; q < TS; ++q) {
+      gdh += __ldcg(p.ws.acc + ((size_t)b * TS + q) * H + h);
+      glw += __ldcg(p.ws.aux + ((size_t)b * TS + q) * H + h);
+    }
+    p.g_lin_w[(size_t)b * H + h] += glw;
+    if (has_prev) p.g_conv_b[(size_t)b * H + h] += gdh;
     // total gradient w.r.t. hx_u: output projection + attention query + next step's cell
-    const float dh = dhx_att[h] + tmp[H + h] + (p.d_hx_next ? p.d_hx_next[(size_t)b * H + h] : 0.f);
+    const float dh = p.d_o[(size_t)b * H + h] + gdh +
+                     (p.d_hx_next ? p.d_hx_next[(size_t)b * H + h] : 0.f);
     const float r = gt[h], z = gt[H + h], n = gt[2 * H + h], hn = gt[3 * H + h];
     const float hp = p.hx_prev[(size_t)b * H + h];
     const float dn = dh * (1.f - z) * (1.f - n * n);
@@ -490,73 +723,103 @@ __global__ void __launch_bounds__(ATT_THREADS) s2s_attn_bwd_kernel(const AttnBwd
     gh[h] = dr; gh[H + h] = dz; gh[2 * H + h] = dn * r;
     p.d_hx_direct[(size_t)b * H + h] = dh * z;
   }
-  if (has_prev) {
-    for (int k = tid; k < H * Kc; k += ATT_THREADS) p.g_conv_w[(size_t)b * H * Kc + k] += gcw[k];
-    for (int t = tid; t < T; t += ATT_THREADS) p.d_ax_prev[(size_t)b * T + t] = daxp[t + pad];
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// cell backward: d ix = d gi W_ih ; d hx_prev = d gh W_hh + d_hx_direct   (lanes over the batch)
+// cell backward: d ix = d gi W_ih ; d hx_prev = d gh W_hh + d_hx_direct.  Same structure as the
+// forward on TRANSPOSED weights (W^T [H][3H], made once per backward by the caller): one warp per
+// two output columns, their four weight rows of one 768-wide K chunk in registers, the 8 batch
+// rows of d gi / d gh staged in shared memory.
 // ------------------------------------------------------------------------------------------------
 struct CellBwdParams {
   const float* d_gi;        // (B, 3H)
   const float* d_gh;        // (B, 3H)
   const float* d_hx_direct; // (B, H)
-  const float* w_ih;        // [3H][H]
-  const float* w_hh;        // [3H][H]
+  const float* w_ihT;       // [H][3H]
+  const float* w_hhT;       // [H][3H]
   float* d_ix;              // (B, H) out
   float* d_hx_prev;         // (B, H) out
   int B, H;
 };
 
-__global__ void __launch_bounds__(32 * S2S_UPC) s2s_cell_bwd_kernel(const CellBwdParams p) {
-  extern __shared__ float cb_smem[];
+__global__ void __launch_bounds__(32 * CELL_WARPS) s2s_cell_bwd_kernel(const CellBwdParams p) {
+  extern __shared__ float4 cell_smem[];
   const int H = p.H, B = p.B, N3 = 3 * H;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int k = blockIdx.x * S2S_UPC + warp;            // output column (input / hidden unit)
-  const int ld = S2S_KC + 4;
-  float* gis = cb_smem;                                 // [32][ld] d gi chunk
-  float* ghs = cb_smem + 32 * ld;                       // [32][ld] d gh chunk
-  for (int b0 = 0; b0 < B; b0 += 32) {
-    const int b = b0 + lane;
-    float ai = 0.f, ah = 0.f;
-    for (int n0 = 0; n0 < N3; n0 += S2S_KC) {
-      const int nc = min(S2S_KC, N3 - n0);
-      __syncthreads();
-      for (int e = tid; e < 32 * (nc / 4); e += 32 * S2S_UPC) {
-        const int r = e / (nc / 4), c4 = e % (nc / 4);
-        const int rb = b0 + r;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-        if (rb < B) {
-          a = __ldg(reinterpret_cast<const float4*>(p.d_gi + (long long)rb * N3 + n0) + c4);
-          c = __ldg(reinterpret_cast<const float4*>(p.d_gh + (long long)rb * N3 + n0) + c4);
-        }
-        reinterpret_cast<float4*>(gis + r * ld)[c4] = a;
-        reinterpret_cast<float4*>(ghs + r * ld)[c4] = c;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kraw = (blockIdx.x * CELL_WARPS + warp) * 2;  // this warp's two output columns
+  const bool owner = kraw < H;
+  const int k0 = owner ? kraw : 0;
+  const bool two = k0 + 1 < H;
+  const int b0 = blockIdx.y * CELL_NB;
+  const int nb = min(CELL_NB, B - b0);
+  float4* gis = cell_smem;                                 // [NB][KCB/4] d gi chunk
+  float4* ghs = cell_smem + CELL_NB * (CELL_KCB / 4);      // [NB][KCB/4] d gh chunk
+  float acc[CELL_NB][4];
+#pragma unroll
+  for (int b = 0; b < CELL_NB; ++b)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) acc[b][d] = 0.f;
+  const int row4 = N3 / 4;
+  for (int n0 = 0; n0 < N3; n0 += CELL_KCB) {
+    const int nk4 = min(CELL_KCB, N3 - n0) / 4;
+    const float4* wi = reinterpret_cast<const float4*>(p.w_ihT + (long long)k0 * N3 + n0);
+    const float4* wh = reinterpret_cast<const float4*>(p.w_hhT + (long long)k0 * N3 + n0);
+    float4 w[4][CELL_KCB / 128];
+#pragma unroll
+    for (int i = 0; i < CELL_KCB / 128; ++i) {
+      const int idx = lane + 32 * i;
+      const bool ok = idx < nk4;
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      w[0][i] = ok ? __ldg(wi + idx) : zero;
+      w[1][i] = ok ? __ldg(wh + idx) : zero;
+      w[2][i] = ok && two ? __ldg(wi + row4 + idx) : zero;
+      w[3][i] = ok && two ? __ldg(wh + row4 + idx) : zero;
+    }
+    __syncthreads();
+    for (int e = tid; e < CELL_NB * nk4; e += 32 * CELL_WARPS) {
+      const int r = e / nk4, c4 = e - r * nk4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+      if (r < nb) {
+        a = __ldg(reinterpret_cast<const float4*>(p.d_gi + (long long)(b0 + r) * N3 + n0) + c4);
+        c = __ldg(reinterpret_cast<const float4*>(p.d_gh + (long long)(b0 + r) * N3 + n0) + c4);
       }
-      __syncthreads();
-      if (k < H) {
-        const float4* gr = reinterpret_cast<const float4*>(gis + lane * ld);
-        const float4* hr = reinterpret_cast<const float4*>(ghs + lane * ld);
-        // column k of W: consecutive n are H floats apart; the 8 warps of the CTA read 8
-        // adjacent columns of the same 32-byte sector (broadcast over the lanes)
-        const float* wi = p.w_ih + (long long)n0 * H + k;
-        const float* wh = p.w_hh + (long long)n0 * H + k;
-#pragma unroll 2
-        for (int n4 = 0; n4 < nc / 4; ++n4) {
-          const float4 a = gr[n4], c = hr[n4];
-          const long long o = (long long)n4 * 4 * H;
-          ai += a.x * __ldg(wi + o) + a.y * __ldg(wi + o + H) + a.z * __ldg(wi + o + 2 * H) +
-                a.w * __ldg(wi + o + 3 * H);
-          ah += c.x * __ldg(wh + o) + c.y * __ldg(wh + o + H) + c.z * __ldg(wh + o + 2 * H) +
-                c.w * __ldg(wh + o + 3 * H);
+      gis[r * (CELL_KCB / 4) + c4] = a;
+      ghs[r * (CELL_KCB / 4) + c4] = c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < CELL_NB; ++b) {
+      if (b < nb) {
+#pragma unroll
+        for (int i = 0; i < CELL_KCB / 128; ++i) {
+          const int idx = lane + 32 * i;
+          if (idx < nk4) {
+            const float4 gi = gis[b * (CELL_KCB / 4) + idx], gh = ghs[b * (CELL_KCB / 4) + idx];
+            acc[b][0] += dot4(w[0][i], gi); acc[b][1] += dot4(w[1][i], gh);
+            acc[b][2] += dot4(w[2][i], gi); acc[b][3] += dot4(w[3][i], gh);
+          }
         }
       }
     }
-    if (k < H && b < B) {
-      p.d_ix[(long long)b * H + k] = ai;
-      p.d_hx_prev[(long long)b * H + k] = ah + p.d_hx_direct[(long long)b * H + k];
+  }
+  float mine[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int b = 0; b < CELL_NB; ++b) {
+    if (b < nb) {
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const float v = warp_sum(acc[b][d]);
+        if (lane == b) mine[d] = v;
+      }
+    }
+  }
+  if (owner && lane < nb) {
+    const long long o = (long long)(b0 + lane) * H + k0;
+    p.d_ix[o] = mine[0];
+    p.d_hx_prev[o] = mine[1] + p.d_hx_direct[o];
+    if (two) {
+      p.d_ix[o + 1] = mine[2];
+      p.d_hx_prev[o + 1] = mine[3] + p.d_hx_direct[o + 1];
     }
   }
 }
@@ -723,6 +986,12 @@ __global__ void s2s_check_done_kernel(const int* end_count, int B, int* done, in
 
 using namespace sb;
 
+extern "C" int sb_s2s_workspace_size(int B, int T, int H, size_t* bytes) {
+  if (!bytes || B <= 0 || T <= 0 || H <= 0) return SB_ERR_INVALID;
+  *bytes = attn_ws_bytes(B, T, H);
+  return SB_OK;
+}
+
 extern "C" int sb_s2s_cell_fwd(const float* emb, const int* tok, int tok_stride, const float* sx_prev,
                                const float* hx_prev, const float* w_ih, const float* w_hh,
                                const float* b_ih, const float* b_hh, float* hx, float* ix_save,
@@ -735,31 +1004,33 @@ extern "C" int sb_s2s_cell_fwd(const float* emb, const int* tok, int tok_stride,
   p.emb = emb; p.tok = tok; p.tok_stride = tok_stride; p.sx_prev = sx_prev; p.hx_prev = hx_prev;
   p.w_ih = w_ih; p.w_hh = w_hh; p.b_ih = b_ih; p.b_hh = b_hh; p.hx = hx; p.ix_save = ix_save;
   p.gates_save = gates_save; p.done = done; p.B = B; p.H = H;
-  const size_t smem = (size_t)2 * 32 * (S2S_KC + 4) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(s2s_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem) != cudaSuccess)
-      return SB_ERR_CUDA;
-    attr = true;
-  }
-  s2s_cell_fwd_kernel<<<(H + S2S_UPC - 1) / S2S_UPC, 32 * S2S_UPC, smem, stream>>>(p);
+  const dim3 grid((H + CELL_WARPS - 1) / CELL_WARPS, (B + CELL_NB - 1) / CELL_NB);
+  const size_t smem = (size_t)2 * CELL_NB * CELL_KC * sizeof(float);
+  s2s_cell_fwd_kernel<<<grid, 32 * CELL_WARPS, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
+static int attn_dims_ok(int B, int T, int H, int Kc) {
+  if (B <= 0 || T <= 0 || H <= 0 || Kc <= 0 || (Kc & 1) == 0) return SB_ERR_INVALID;
+  if (Kc >= ATT_KMAX || (T + ATT_TT - 1) / ATT_TT > ATT_MAX_TS || B > 65535)
+    return SB_ERR_UNSUPPORTED;
+  return SB_OK;
+}
+
 extern "C" int sb_s2s_attn_fwd(const float* eh, int eh_bcast, const float* hx, const float* ax_prev,
-                               const float* conv_w, const float* conv_b, const float* lin_w,
+                               const float* conv_wT, const float* conv_b, const float* lin_w,
                                float lin_b, int log_t, int B, int T, int H, int Kc, float* sx,
                                float* ax, const float* fc_w, const float* fc_b, int C,
                                float* logits, long long logit_stride, float* logp, int* argmax,
                                int* history, int hist_stride, int hist_col, int* end_count,
-                               int end_tok, const int* done, void* stream_) {
-  if (!eh || !hx || !conv_w || !conv_b || !lin_w || !sx || !ax) return SB_ERR_INVALID;
-  if (B <= 0 || T <= 0 || H <= 0 || Kc <= 0 || (Kc & 1) == 0) return SB_ERR_INVALID;
-  if (H > 32 * ATT_MAXR) return SB_ERR_UNSUPPORTED;
-  if (fc_w && (!fc_b || C <= 0 || C > (ATT_THREADS / 32 - 1) * H)) return SB_ERR_INVALID;
-  const size_t smem = sizeof(float) * ((size_t)T + Kc - 1 + (size_t)H * Kc + 2 * H + T + 16 +
-                                       (size_t)(ATT_THREADS / 32) * H);
+                               int end_tok, const int* done, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+  if (!eh || !hx || !conv_wT || !conv_b || !lin_w || !sx || !ax || !workspace) return SB_ERR_INVALID;
+  int rc = attn_dims_ok(B, T, H, Kc);
+  if (rc != SB_OK) return rc;
+  if (workspace_bytes < attn_ws_bytes(B, T, H)) return SB_ERR_WORKSPACE;
+  if (fc_w && (!fc_b || C <= 0 || C > (ATT_NW - 1) * H)) return SB_ERR_INVALID;
+  const size_t smem = sizeof(float) * ((size_t)ATT_NW * H + 2 * ATT_NW + ATT_MAX_TS);
   if (smem > 220 * 1024) return SB_ERR_UNSUPPORTED;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (smem > 40 * 1024 &&
@@ -767,73 +1038,90 @@ extern "C" int sb_s2s_attn_fwd(const float* eh, int eh_bcast, const float* hx, c
                            (int)smem) != cudaSuccess)
     return SB_ERR_CUDA;
   AttnFwdParams p;
-  p.eh = eh; p.eh_bcast = eh_bcast; p.hx = hx; p.ax_prev = ax_prev; p.conv_w = conv_w;
+  p.eh = eh; p.eh_bcast = eh_bcast; p.hx = hx; p.ax_prev = ax_prev; p.conv_wT = conv_wT;
   p.conv_b = conv_b; p.lin_w = lin_w; p.lin_b = lin_b; p.sx = sx; p.ax = ax; p.fc_w = fc_w;
   p.fc_b = fc_b; p.logits = logits; p.logit_stride = logit_stride; p.logp = logp;
   p.argmax = argmax; p.history = history; p.hist_stride = hist_stride; p.hist_col = hist_col;
   p.end_count = end_count; p.end_tok = end_tok; p.done = done;
+  p.ws = attn_ws_carve(workspace, B, T, H);
   p.B = B; p.T = T; p.H = H; p.Kc = Kc; p.C = C; p.log_t = log_t;
-  s2s_attn_fwd_kernel<<<B, ATT_THREADS, smem, stream>>>(p);
+  s2s_attn_fwd_kernel<<<dim3((T + ATT_TT - 1) / ATT_TT, B), ATT_THREADS, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
 // the standalone attention step (no output projection): NNAttention.forward on the decode path
 extern "C" int sb_attn_step(const float* eh, const float* dhx, const float* ax_prev,
-                            const float* conv_w, const float* conv_b, const float* lin_w,
+                            const float* conv_wT, const float* conv_b, const float* lin_w,
                             float lin_b, int log_t, int B, int T, int H, int Kc, float* sx,
-                            float* ax, void* stream_) {
-  return sb_s2s_attn_fwd(eh, 0, dhx, ax_prev, conv_w, conv_b, lin_w, lin_b, log_t, B, T, H, Kc, sx,
-                         ax, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, 0,
-                         nullptr, 0, nullptr, stream_);
+                            float* ax, void* workspace, size_t workspace_bytes, void* stream_) {
+  return sb_s2s_attn_fwd(eh, 0, dhx, ax_prev, conv_wT, conv_b, lin_w, lin_b, log_t, B, T, H, Kc,
+                         sx, ax, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, 0,
+                         nullptr, 0, nullptr, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int sb_s2s_dout(const float* dlogits, const float* fc_w, const float* hx, const float* sx,
+                           float* d_o, float* o_all, long long rows, int C, int H, void* stream_) {
+  if (!dlogits || !fc_w || !hx || !sx || !d_o || !o_all || rows <= 0 || C <= 0 || H <= 0)
+    return SB_ERR_INVALID;
+  if (rows > 0x7fffffffLL || C > 8192) return SB_ERR_UNSUPPORTED;
+  s2s_dout_kernel<<<(unsigned int)rows, 256, C * sizeof(float),
+                    reinterpret_cast<cudaStream_t>(stream_)>>>(dlogits, fc_w, hx, sx, d_o, o_all, C, H);
+  return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
 extern "C" int sb_s2s_attn_bwd(const float* eh, const float* hx, const float* hx_prev,
-                               const float* ax_prev, const float* ax, const float* sx,
-                               const float* conv_w, const float* conv_b, const float* lin_w,
-                               float lin_b, const float* fc_w, const float* dlogits,
-                               long long dl_stride, const float* d_ix_next, const float* d_ax_next,
+                               const float* ax_prev, const float* ax, const float* conv_wT,
+                               const float* conv_b, const float* lin_w, const float* d_o,
+                               const float* d_ix_next, const float* d_ax_next,
                                const float* d_hx_next, const float* gates, float* d_eh,
                                float* d_ax_prev, float* d_gi, float* d_gh, float* d_hx_direct,
-                               float* o_save, float* g_conv_w, float* g_conv_b, float* g_lin_w,
-                               float* g_lin_b, int log_t, int B, int T, int H, int Kc, int C,
-                               void* stream_) {
-  if (!eh || !hx || !hx_prev || !ax || !sx || !conv_w || !conv_b || !lin_w || !fc_w || !dlogits ||
-      !gates || !d_eh || !d_ax_prev || !d_gi || !d_gh || !d_hx_direct || !o_save || !g_conv_w ||
-      !g_conv_b || !g_lin_w || !g_lin_b)
+                               float* g_conv_wT, float* g_conv_b, float* g_lin_w, float* g_lin_b,
+                               int log_t, int B, int T, int H, int Kc, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+  if (!eh || !hx || !hx_prev || !ax || !conv_wT || !conv_b || !lin_w || !d_o || !gates || !d_eh ||
+      !d_ax_prev || !d_gi || !d_gh || !d_hx_direct || !g_conv_wT || !g_conv_b || !g_lin_w ||
+      !g_lin_b || !workspace)
     return SB_ERR_INVALID;
-  if (B <= 0 || T <= 0 || H <= 0 || Kc <= 0 || (Kc & 1) == 0 || C <= 0) return SB_ERR_INVALID;
-  if (H > 32 * ATT_MAXR || Kc > 16 || Kc < 2) return SB_ERR_UNSUPPORTED;   // (tmp = cw needs Kc >= 2)
-  const size_t smem = sizeof(float) * (2 * ((size_t)T + Kc - 1) + 2 * (size_t)H * Kc + 4 * H + T +
-                                       ATT_THREADS / 32 + 16);
-  if (smem > 220 * 1024) return SB_ERR_UNSUPPORTED;
+  int rc = attn_dims_ok(B, T, H, Kc);
+  if (rc != SB_OK) return rc;
+  if (workspace_bytes < attn_ws_bytes(B, T, H)) return SB_ERR_WORKSPACE;
+  const size_t smem_a = sizeof(float) * ((size_t)H + ATT_NW);
+  const size_t smem_b = sizeof(float) * ((size_t)H * (1 + ATT_TT + ATT_NW) + ATT_NW * ATT_WIN +
+                                         ATT_TT + ATT_KMAX - 1 + ATT_NW);
+  if (smem_b > 220 * 1024) return SB_ERR_UNSUPPORTED;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (smem > 40 * 1024 &&
-      cudaFuncSetAttribute(s2s_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem) != cudaSuccess)
+  if (smem_b > 40 * 1024 &&
+      cudaFuncSetAttribute(s2s_attn_bwd_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem_b) != cudaSuccess)
     return SB_ERR_CUDA;
   AttnBwdParams p;
-  p.eh = eh; p.hx = hx; p.hx_prev = hx_prev; p.ax_prev = ax_prev; p.ax = ax; p.sx = sx;
-  p.conv_w = conv_w; p.conv_b = conv_b; p.lin_w = lin_w; p.lin_b = lin_b; p.fc_w = fc_w;
-  p.dlogits = dlogits; p.dl_stride = dl_stride; p.d_ix_next = d_ix_next; p.d_ax_next = d_ax_next;
+  p.eh = eh; p.hx = hx; p.hx_prev = hx_prev; p.ax_prev = ax_prev; p.ax = ax;
+  p.conv_wT = conv_wT; p.conv_b = conv_b; p.lin_w = lin_w; p.d_o = d_o;
+  p.d_ix_next = d_ix_next; p.d_ax_next = d_ax_next;
   p.d_hx_next = d_hx_next; p.gates = gates; p.d_eh = d_eh; p.d_ax_prev = d_ax_prev; p.d_gi = d_gi;
-  p.d_gh = d_gh; p.d_hx_direct = d_hx_direct; p.o_save = o_save; p.g_conv_w = g_conv_w;
+  p.d_gh = d_gh; p.d_hx_direct = d_hx_direct; p.g_conv_wT = g_conv_wT;
   p.g_conv_b = g_conv_b; p.g_lin_w = g_lin_w; p.g_lin_b = g_lin_b;
-  p.B = B; p.T = T; p.H = H; p.Kc = Kc; p.C = C; p.log_t = log_t;
-  s2s_attn_bwd_kernel<<<B, ATT_THREADS, smem, stream>>>(p);
+  p.ws = attn_ws_carve(workspace, B, T, H);
+  p.B = B; p.T = T; p.H = H; p.Kc = Kc; p.log_t = log_t;
+  const dim3 grid((T + ATT_TT - 1) / ATT_TT, B);
+  s2s_attn_bwd_a_kernel<<<grid, ATT_THREADS, smem_a, stream>>>(p);
+  s2s_attn_bwd_b_kernel<<<grid, ATT_THREADS, smem_b, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
 extern "C" int sb_s2s_cell_bwd(const float* d_gi, const float* d_gh, const float* d_hx_direct,
-                               const float* w_ih, const float* w_hh, float* d_ix, float* d_hx_prev,
-                               int B, int H, void* stream_) {
-  if (!d_gi || !d_gh || !d_hx_direct || !w_ih || !w_hh || !d_ix || !d_hx_prev || B <= 0 || H <= 0)
+                               const float* w_ihT, const float* w_hhT, float* d_ix,
+                               float* d_hx_prev, int B, int H, void* stream_) {
+  if (!d_gi || !d_gh || !d_hx_direct || !w_ihT || !w_hhT || !d_ix || !d_hx_prev || B <= 0 || H <= 0)
     return SB_ERR_INVALID;
   if ((3 * H) % 4 != 0) return SB_ERR_UNSUPPORTED;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CellBwdParams p;
-  p.d_gi = d_gi; p.d_gh = d_gh; p.d_hx_direct = d_hx_direct; p.w_ih = w_ih; p.w_hh = w_hh;
+  p.d_gi = d_gi; p.d_gh = d_gh; p.d_hx_direct = d_hx_direct; p.w_ihT = w_ihT; p.w_hhT = w_hhT;
   p.d_ix = d_ix; p.d_hx_prev = d_hx_prev; p.B = B; p.H = H;
-  const size_t smem = (size_t)2 * 32 * (S2S_KC + 4) * sizeof(float);
+  const int cols = (H + 1) / 2;
+  const dim3 grid((cols + CELL_WARPS - 1) / CELL_WARPS, (B + CELL_NB - 1) / CELL_NB);
+  const size_t smem = (size_t)2 * CELL_NB * CELL_KCB * sizeof(float);
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(s2s_cell_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -841,7 +1129,7 @@ extern "C" int sb_s2s_cell_bwd(const float* d_gi, const float* d_gh, const float
       return SB_ERR_CUDA;
     attr = true;
   }
-  s2s_cell_bwd_kernel<<<(H + S2S_UPC - 1) / S2S_UPC, 32 * S2S_UPC, smem, stream>>>(p);
+  s2s_cell_bwd_kernel<<<grid, 32 * CELL_WARPS, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 

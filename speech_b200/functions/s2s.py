@@ -1,9 +1,10 @@
 """Attention-decoder operators over the C ABI (csrc/s2s.cu): the per-token step of
 Seq2Seq.decode / decode_step / infer / beam_search (speech/models/seq2seq.py:78-227) and
 NNAttention.forward (:344-360) as two kernels per token (GRU cell; attention + output projection),
-with a hand-written backward (two kernels per token, the weight gradients time-batched on the
-tcgen05 GEMM), a greedy loop and a beam search that never leave the device: the host only enqueues
-kernels and reads the final hypothesis back once.
+with a hand-written backward (three kernels per token, the output-projection backward of all
+steps in one launch, the weight gradients time-batched on the tcgen05 GEMM), a greedy loop and a
+beam search that never leave the device: the host only enqueues kernels and reads the final
+hypothesis back once.
 """
 import ctypes
 
@@ -24,42 +25,57 @@ class DecoderWeights:
         self.w_ih, self.w_hh = _f(m.dec_rnn.weight_ih), _f(m.dec_rnn.weight_hh)
         self.b_ih, self.b_hh = _f(m.dec_rnn.bias_ih), _f(m.dec_rnn.bias_hh)
         conv, lin = m.attend.conv, m.attend.nn[1].fc
-        self.conv_w = _f(conv.weight).reshape(conv.weight.shape[0], -1)
+        self.conv_wT = _f(conv.weight).reshape(conv.weight.shape[0], -1).t().contiguous()  # (Kc, H)
         self.conv_b = _f(conv.bias)
         self.lin_w = _f(lin.weight).reshape(-1)
         self.lin_b = float(lin.bias.detach().float().item()) if lin.bias is not None else 0.0
         self.fc_w, self.fc_b = _f(m.fc.fc.weight), _f(m.fc.fc.bias)
         self.log_t = 1 if m.attend.log_t else 0
         self.H = self.w_hh.shape[1]
-        self.Kc = self.conv_w.shape[1]
+        self.Kc = self.conv_wT.shape[0]
         self.C = self.fc_w.shape[0]
         if self.emb.shape[1] != self.H:
             raise _lib.SpeechB200Error("Seq2Seq: embedding_dim must equal the encoder dim (ix + sx)")
+        # device addresses, looked up once: the per-token loops only do integer arithmetic
+        for n in ("emb", "w_ih", "w_hh", "b_ih", "b_hh", "conv_wT", "conv_b", "lin_w", "fc_w",
+                  "fc_b"):
+            setattr(self, "p_" + n, getattr(self, n).data_ptr())
+
+
+def attn_workspace(lib, B, T, H, dev):
+    """zeroed scratch of the attention kernels (per-CTA softmax partials + ticket counters); one
+    buffer serves every step of a decode on the same stream"""
+    n = ctypes.c_size_t(0)
+    _lib.check(lib.sb_s2s_workspace_size(B, T, H, ctypes.byref(n)), "s2s workspace")
+    return torch.zeros(n.value, dtype=torch.uint8, device=dev)
+
+
+def _a(x):
+    """device address of a tensor; ints (addresses computed by the caller) and None pass through"""
+    return x if x is None or isinstance(x, int) else x.data_ptr()
 
 
 def _cell_fwd(lib, w, tok, tok_stride, sx_prev, hx_prev, hx, ix_save, gates_save, done, B, sp):
     from .. import ops
     ops._launch("s2s_cell_fwd", 0.0,
-                lambda: lib.sb_s2s_cell_fwd(w.emb.data_ptr(), tok, tok_stride, _lib.ptr(sx_prev),
-                                            hx_prev.data_ptr(), w.w_ih.data_ptr(), w.w_hh.data_ptr(),
-                                            w.b_ih.data_ptr(), w.b_hh.data_ptr(), hx.data_ptr(),
-                                            _lib.ptr(ix_save), _lib.ptr(gates_save), done, B, w.H, sp))
+                lambda: lib.sb_s2s_cell_fwd(w.p_emb, tok, tok_stride, _a(sx_prev), _a(hx_prev),
+                                            w.p_w_ih, w.p_w_hh, w.p_b_ih, w.p_b_hh, _a(hx),
+                                            _a(ix_save), _a(gates_save), done, B, w.H, sp))
 
 
-def _attn_fwd(lib, w, eh, bcast, hx, ax_prev, sx, ax, B, T, sp, logits=None, logit_stride=0,
+def _attn_fwd(lib, w, ws, eh, bcast, hx, ax_prev, sx, ax, B, T, sp, logits=None, logit_stride=0,
               logp=None, argmax=None, history=None, hist_stride=0, hist_col=0, end_count=None,
               end_tok=-1, done=None, with_fc=True):
     from .. import ops
     ops._launch("s2s_attn_fwd", 0.0,
-                lambda: lib.sb_s2s_attn_fwd(eh.data_ptr(), bcast, hx.data_ptr(), _lib.ptr(ax_prev),
-                                            w.conv_w.data_ptr(), w.conv_b.data_ptr(),
-                                            w.lin_w.data_ptr(), w.lin_b, w.log_t, B, T, w.H, w.Kc,
-                                            sx.data_ptr(), ax.data_ptr(),
-                                            w.fc_w.data_ptr() if with_fc else None,
-                                            w.fc_b.data_ptr() if with_fc else None, w.C,
-                                            logits, logit_stride, _lib.ptr(logp), _lib.ptr(argmax),
+                lambda: lib.sb_s2s_attn_fwd(_a(eh), bcast, _a(hx), _a(ax_prev), w.p_conv_wT,
+                                            w.p_conv_b, w.p_lin_w, w.lin_b, w.log_t, B, T, w.H,
+                                            w.Kc, _a(sx), _a(ax),
+                                            w.p_fc_w if with_fc else None,
+                                            w.p_fc_b if with_fc else None, w.C,
+                                            logits, logit_stride, _a(logp), _a(argmax),
                                             history, hist_stride, hist_col, end_count, end_tok,
-                                            done, sp))
+                                            done, _a(ws), ws.numel(), sp))
 
 
 class DecodeFunction(torch.autograd.Function):
@@ -90,18 +106,27 @@ class DecodeFunction(torch.autograd.Function):
         amax = torch.zeros(B, dtype=torch.int32, device=dev) if sampling else None
         used = tok[:, :steps].t().contiguous() if need else None          # (steps, B) tokens fed
         sp = _lib.stream_ptr()
+        ws = attn_workspace(lib, B, T, H, dev)
+        # per-token launches: addresses by integer arithmetic (no tensor slicing in the loop)
+        BH, BT = 4 * B * H, 4 * B * T
+        p_hx, p_sx, p_ax = hx_all.data_ptr(), sx_all.data_ptr(), ax_all.data_ptr()
+        p_ix = ix_all.data_ptr() if need else None
+        p_gt = gates_all.data_ptr() if need else None
+        p_tok, p_logits = tok.data_ptr(), logits.data_ptr()
+        p_amax = amax.data_ptr() if sampling else None
         for u in range(steps):
             if u > 0 and sample_flags[u]:
                 if need:
                     used[u].copy_(amax)
-                tk, ts = amax.data_ptr(), 1
+                tk, ts = p_amax, 1
             else:
-                tk, ts = tok.data_ptr() + 4 * u, U
-            _cell_fwd(lib, w, tk, ts, sx_all[u - 1] if u > 0 else None, hx_all[u], hx_all[u + 1],
-                      ix_all[u] if need else None, gates_all[u] if need else None, None, B, sp)
-            _attn_fwd(lib, w, ehc, 0, hx_all[u + 1], ax_all[u - 1] if u > 0 else None, sx_all[u],
-                      ax_all[u], B, T, sp, logits=logits.data_ptr() + 4 * u * w.C,
-                      logit_stride=steps * w.C, argmax=amax)
+                tk, ts = p_tok + 4 * u, U
+            _cell_fwd(lib, w, tk, ts, p_sx + (u - 1) * BH if u > 0 else None, p_hx + u * BH,
+                      p_hx + (u + 1) * BH, p_ix + u * BH if need else None,
+                      p_gt + 4 * u * BH if need else None, None, B, sp)
+            _attn_fwd(lib, w, ws, ehc, 0, p_hx + (u + 1) * BH, p_ax + (u - 1) * BT if u > 0 else None,
+                      p_sx + u * BH, p_ax + u * BT, B, T, sp, logits=p_logits + 4 * u * w.C,
+                      logit_stride=steps * w.C, argmax=p_amax)
         ctx.w = w
         ctx.saved = (ehc, hx_all, sx_all, ax_all, ix_all, gates_all, used)
         ctx.dims = (B, T, H, steps)
@@ -131,31 +156,45 @@ class DecodeFunction(torch.autograd.Function):
         o_all = torch.empty(steps, B, H, dtype=torch.float32, device=dev)
         d_hx_direct = torch.empty(B, H, dtype=torch.float32, device=dev)
         d_hx_prev = torch.empty(B, H, dtype=torch.float32, device=dev)
+        d_o = torch.empty(steps, B, H, dtype=torch.float32, device=dev)
         d_ax = [torch.zeros(B, T, dtype=torch.float32, device=dev) for _ in range(2)]
-        g_conv_w = torch.zeros(B, H, Kc, dtype=torch.float32, device=dev)
+        TS = (T + 23) // 24                                  # CTAs per utterance (csrc/s2s.cu)
+        g_conv_wT = torch.zeros(B, TS, Kc, H, dtype=torch.float32, device=dev)
         g_conv_b = torch.zeros(B, H, dtype=torch.float32, device=dev)
         g_lin_w = torch.zeros(B, H, dtype=torch.float32, device=dev)
         g_lin_b = torch.zeros(B, dtype=torch.float32, device=dev)
         sp = _lib.stream_ptr()
+        ws = attn_workspace(lib, B, T, H, dev)
+        w_ihT, w_hhT = w.w_ih.t().contiguous(), w.w_hh.t().contiguous()
+        ops._launch("s2s_dout", 0.0, lambda: lib.sb_s2s_dout(
+            dl.data_ptr(), w.fc_w.data_ptr(), hx_all[1:].data_ptr(), sx_all.data_ptr(),
+            d_o.data_ptr(), o_all.data_ptr(), steps * B, C, H, sp))
+        BH, BT = 4 * B * H, 4 * B * T
+        p_eh, p_hx, p_ax = ehc.data_ptr(), hx_all.data_ptr(), ax_all.data_ptr()
+        p_gt, p_do, p_dix = gates_all.data_ptr(), d_o.data_ptr(), d_ix.data_ptr()
+        p_dgi, p_dgh = d_gi.data_ptr(), d_gh.data_ptr()
+        p_dax = (d_ax[0].data_ptr(), d_ax[1].data_ptr())
+        p_dhd, p_dhp, p_deh = d_hx_direct.data_ptr(), d_hx_prev.data_ptr(), d_eh.data_ptr()
+        p_gcw, p_gcb = g_conv_wT.data_ptr(), g_conv_b.data_ptr()
+        p_glw, p_glb = g_lin_w.data_ptr(), g_lin_b.data_ptr()
+        p_wihT, p_whhT, p_ws, n_ws = w_ihT.data_ptr(), w_hhT.data_ptr(), ws.data_ptr(), ws.numel()
         for u in reversed(range(steps)):
             last = (u == steps - 1)
-            d_ax_next = None if last else d_ax[(u + 1) & 1]
+            d_ax_next = None if last else p_dax[(u + 1) & 1]
             if da_ext is not None:
-                d_ax_next = da_ext[u] if d_ax_next is None else d_ax_next + da_ext[u]
+                if last:
+                    d_ax_next = da_ext[u].data_ptr()
+                else:
+                    d_ax[(u + 1) & 1].add_(da_ext[u])
             ops._launch("s2s_attn_bwd", 0.0, lambda: lib.sb_s2s_attn_bwd(
-                ehc.data_ptr(), hx_all[u + 1].data_ptr(), hx_all[u].data_ptr(),
-                ax_all[u - 1].data_ptr() if u > 0 else None, ax_all[u].data_ptr(),
-                sx_all[u].data_ptr(), w.conv_w.data_ptr(), w.conv_b.data_ptr(), w.lin_w.data_ptr(),
-                w.lin_b, w.fc_w.data_ptr(), dl[u].data_ptr(), C,
-                None if last else d_ix[u + 1].data_ptr(), _lib.ptr(d_ax_next),
-                None if last else d_hx_prev.data_ptr(), gates_all[u].data_ptr(), d_eh.data_ptr(),
-                d_ax[u & 1].data_ptr(), d_gi[u].data_ptr(), d_gh[u].data_ptr(),
-                d_hx_direct.data_ptr(), o_all[u].data_ptr(), g_conv_w.data_ptr(),
-                g_conv_b.data_ptr(), g_lin_w.data_ptr(), g_lin_b.data_ptr(), w.log_t, B, T, H, Kc,
-                C, sp))
+                p_eh, p_hx + (u + 1) * BH, p_hx + u * BH, p_ax + (u - 1) * BT if u > 0 else None,
+                p_ax + u * BT, w.p_conv_wT, w.p_conv_b, w.p_lin_w, p_do + u * BH,
+                None if last else p_dix + (u + 1) * BH, d_ax_next, None if last else p_dhp,
+                p_gt + 4 * u * BH, p_deh, p_dax[u & 1], p_dgi + 3 * u * BH, p_dgh + 3 * u * BH,
+                p_dhd, p_gcw, p_gcb, p_glw, p_glb, w.log_t, B, T, H, Kc, p_ws, n_ws, sp))
             ops._launch("s2s_cell_bwd", 0.0, lambda: lib.sb_s2s_cell_bwd(
-                d_gi[u].data_ptr(), d_gh[u].data_ptr(), d_hx_direct.data_ptr(), w.w_ih.data_ptr(),
-                w.w_hh.data_ptr(), d_ix[u].data_ptr(), d_hx_prev.data_ptr(), B, H, sp))
+                p_dgi + 3 * u * BH, p_dgh + 3 * u * BH, p_dhd, p_wihT, p_whhT, p_dix + u * BH,
+                p_dhp, B, H, sp))
         # ---- time-batched weight gradients: contractions over all (u, b) rows on the tcgen05 GEMM
         R = steps * B
 
@@ -178,7 +217,7 @@ class DecodeFunction(torch.autograd.Function):
         d_fc_b = dl.sum((0, 1))
         d_emb = torch.zeros(ctx.vocab, H, dtype=torch.float32, device=dev)
         d_emb.index_add_(0, used.reshape(-1).long(), d_ix.view(R, H))
-        d_conv_w = g_conv_w.sum(0).reshape(ctx.conv_shape)
+        d_conv_w = g_conv_wT.sum((0, 1)).t().reshape(ctx.conv_shape)
         d_conv_b = g_conv_b.sum(0)
         d_lin_w = g_lin_w.sum(0).reshape(ctx.lin_shape)
         d_lin_b = g_lin_b.sum().reshape(1) if ctx.has_lin_b else None
@@ -218,8 +257,9 @@ def decode_step(m, eh, y, state, softmax):
     out = torch.empty(B, w.C, dtype=torch.float32, device=dev)
     logp = torch.empty(B, w.C, dtype=torch.float32, device=dev) if softmax else None
     sp = _lib.stream_ptr()
+    ws = attn_workspace(lib, B, T, H, dev)
     _cell_fwd(lib, w, tok.data_ptr(), 1, sx_prev, hx_prev, hx, None, None, None, B, sp)
-    _attn_fwd(lib, w, ehc, 0, hx, ax_prev, sx, ax, B, T, sp, logits=out.data_ptr(),
+    _attn_fwd(lib, w, ws, ehc, 0, hx, ax_prev, sx, ax, B, T, sp, logits=out.data_ptr(),
               logit_stride=w.C, logp=logp)
     return (logp if softmax else out), (hx, ax, sx.unsqueeze(1))
 
@@ -241,12 +281,13 @@ def greedy(m, eh, start, end_tok, max_len):
     sx = [torch.empty(B, H, dtype=torch.float32, device=dev) for _ in range(2)]
     ax = [torch.empty(B, T, dtype=torch.float32, device=dev) for _ in range(2)]
     sp = _lib.stream_ptr()
+    ws = attn_workspace(lib, B, T, H, dev)
     from .. import ops
     for e in range(max_len):
         cur, prv = e & 1, (e & 1) ^ 1
         _cell_fwd(lib, w, hist.data_ptr() + 4 * e, max_len + 1, sx[prv] if e > 0 else None,
                   hx[prv], hx[cur], None, None, done.data_ptr(), B, sp)
-        _attn_fwd(lib, w, ehc, 0, hx[cur], ax[prv] if e > 0 else None, sx[cur], ax[cur], B, T, sp,
+        _attn_fwd(lib, w, ws, ehc, 0, hx[cur], ax[prv] if e > 0 else None, sx[cur], ax[cur], B, T, sp,
                   history=hist.data_ptr(), hist_stride=max_len + 1, hist_col=e + 1,
                   end_count=ctl.data_ptr() + 4 * e, end_tok=int(end_tok), done=done.data_ptr())
         ops._launch("s2s_check_done", 0.0,
@@ -282,6 +323,7 @@ def beam_search(m, eh, start_tok, end_tok, beam_size, max_len):
     ax = [torch.zeros(K, T, dtype=torch.float32, device=dev) for _ in range(3)]
     logp = torch.empty(K, C, dtype=torch.float32, device=dev)
     sp = _lib.stream_ptr()
+    ws = attn_workspace(lib, K, T, H, dev)
     _lib.check(lib.sb_s2s_beam_init(state.data_ptr(), nodes.data_ptr(), tok.data_ptr(),
                                     int(start_tok), sp), "beam init")
     # the `done` word of the state struct doubles as the no-op flag of the step kernels
@@ -290,7 +332,7 @@ def beam_search(m, eh, start_tok, end_tok, beam_size, max_len):
     for e in range(max_len):
         _cell_fwd(lib, w, tok.data_ptr(), 1, sx[0] if e > 0 else None, hx[0], hx[1], None, None,
                   done_ptr, K, sp)
-        _attn_fwd(lib, w, ehc, 1, hx[1], ax[0] if e > 0 else None, sx[1], ax[1], K, T, sp,
+        _attn_fwd(lib, w, ws, ehc, 1, hx[1], ax[0] if e > 0 else None, sx[1], ax[1], K, T, sp,
                   logp=logp, done=done_ptr)
         ops._launch("s2s_beam_select", 0.0, lambda: lib.sb_s2s_beam_select(
             logp.data_ptr(), state.data_ptr(), c_scores.data_ptr(), nodes.data_ptr(),

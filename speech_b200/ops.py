@@ -775,16 +775,19 @@ def attn_step(eh, dhx, ax_prev, conv, lin, log_t):
     B, T, H = eh.shape
     d = dhx.detach().float().reshape(B, H).contiguous()
     axp = None if ax_prev is None else ax_prev.detach().float().contiguous()
-    cw = conv.weight.detach().float().reshape(H, -1).contiguous()
-    Kc = cw.shape[1]
+    cw = conv.weight.detach().float().reshape(H, -1).t().contiguous()     # (Kc, H)
+    Kc = cw.shape[0]
     cb = conv.bias.detach().float().contiguous()
     lw = lin.weight.detach().float().reshape(-1).contiguous()
     lb = float(lin.bias.detach().float().item()) if lin.bias is not None else 0.0
     sx = torch.empty(B, H, dtype=torch.float32, device=eh.device)
     ax = torch.empty(B, T, dtype=torch.float32, device=eh.device)
     sp = _lib.stream_ptr()
+    from .functions.s2s import attn_workspace
+    ws = attn_workspace(lib, B, T, H, eh.device)
     _launch("attn_step", 0.0,
             lambda: lib.sb_attn_step(eh.data_ptr(), d.data_ptr(), _lib.ptr(axp), cw.data_ptr(),
                                      cb.data_ptr(), lw.data_ptr(), lb, 1 if log_t else 0, B, T, H,
-                                     Kc, sx.data_ptr(), ax.data_ptr(), sp))
+                                     Kc, sx.data_ptr(), ax.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     sp))
     return sx.unsqueeze(1), ax

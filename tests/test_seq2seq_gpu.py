@@ -101,7 +101,10 @@ def test_teacher_forced_decode_forward_and_backward(cuda_lib, B, T, H, V, U, log
         got = p.grad.double().cpu().reshape(ref.shape)
         # time-batched on the tcgen05 GEMM (bf16 operands): cell weights and the output projection
         tol = 2e-2 if name in ("dec_rnn.weight_ih", "dec_rnn.weight_hh", "fc.fc.weight") else 2e-3
-        assert (got - ref).abs().max().item() < tol * ref.abs().max().item() + 1e-6, name
+        # the softmax is invariant to a shift of the scores, so d(attention bias) is EXACTLY zero:
+        # what both sides hold is the rounding residue of sum_t d score_t (fp64: 1e-16, fp32: 1e-6)
+        floor = 1e-5 if name == "attend.nn.1.fc.bias" else 1e-6
+        assert (got - ref).abs().max().item() < tol * ref.abs().max().item() + floor, name
 
 
 def test_decode_step_loop_equals_teacher_forced_decode(cuda_lib):
