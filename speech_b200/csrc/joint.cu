@@ -8,9 +8,10 @@
 // (blank and the next label), so the training path here writes a COMPACT lattice
 // lat[node] = {log p(blank), log p(label_u)} (8 bytes per node) and the hidden tensor only ever
 // exists as 16 KB operand tiles in shared memory:
-//   * 4 producer warps (thread = node row) build A tiles [128 nodes x 64] bf16 of
-//     relu(fx[b,t,:] + fy[b,u,:]) straight into the UMMA K-major SWIZZLE_128B layout
-//     (fx, fy: fp32 outputs of the fc1 GEMMs, L1/L2 resident: 7.9 K and 3.2 K rows);
+//   * 2 x 4 producer warps (thread = node row; the two groups take alternate k-blocks) build
+//     A tiles [128 nodes x 64] bf16 of relu(fx[b,t,:] + fy[b,u,:]) straight into the UMMA
+//     K-major SWIZZLE_128B layout (fx, fy: fp32 outputs of the fc1 GEMMs, L2 resident: 7.9 K
+//     and 3.2 K rows);
 //   * fc2's weight (V+1 <= 64 rows x H, bf16) stays resident in shared memory;
 //   * one thread issues tcgen05.mma  D[128 x NV] += A * W2^T  (accumulators in TMEM, 2 stages);
 //   * 4 epilogue warps (thread = node) add the bias, take the log-softmax over the V+1 classes
@@ -31,7 +32,9 @@ namespace sb {
 typedef __nv_bfloat16 bf16;
 
 static constexpr int JT_STAGES = 4;
-static constexpr int JT_THREADS = 32 * 9;   // warps 0-3 producers, 4 MMA, 5-8 epilogue
+static constexpr int JT_GROUPS = 2;                   // producer groups (4 warps each)
+static constexpr int JT_PW = 4 * JT_GROUPS;           // producer warps
+static constexpr int JT_THREADS = 32 * (JT_PW + 5);   // warps 0..7 producers, 8 MMA, 9..12 epilogue
 
 struct JointParams {
   const float* fx;      // [B*T][H]   fc1(encoder states)   (bias included)
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_kernel(const JointParams 
     }
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 2 * NV < 32 ? 32 : 2 * NV);
+  if (warp == JT_PW) tmem_alloc(tmem_slot, 2 * NV < 32 ? 32 : 2 * NV);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -106,12 +109,17 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_kernel(const JointParams 
   const uint32_t tmem_base = *tmem_slot;
   const long long ntiles = (p.nodes + 127) / 128;
 
-  if (warp < 4) {
+  if (warp < JT_PW) {
     // ===================== producers: thread = node row of the tile =====================
-    int stage = 0;
-    uint32_t phase = 0;
+    // Two groups of 4 warps build ALTERNATE k-blocks (item i = running (tile, k-block) index goes
+    // to group i % 2, ring stage i % JT_STAGES): a k-block is one L2 round trip (128 rows x 256 B
+    // of fy), so two are in flight per CTA.  Measured with one group: 2.36 ms per pass against
+    // an L2-ingest floor of 0.73 ms (3.3 GB of fy rows at ~30 GB/s per SM).
+    const int grp = warp >> 2;
+    const int rowt = tid & 127;
+    long long item = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const long long n = tile * 128 + tid;
+      const long long n = tile * 128 + rowt;
       const bool ok = n < p.nodes;
       // nodes are TIME-major: n = (t * B + b) * U1 + u (a range of frames is a contiguous slab)
       const long long tb = ok ? n / p.U1 : 0;
@@ -120,7 +128,10 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_kernel(const JointParams 
       const int t = (int)(tb / p.B);
       const float* xr = p.fx + ((long long)b * p.T + t) * H;
       const float* yr = p.fy + ((long long)b * p.U1 + u) * H;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb, ++item) {
+        if ((int)(item % JT_GROUPS) != grp) continue;
+        const int stage = (int)(item % JT_STAGES);
+        const uint32_t phase = (uint32_t)((item / JT_STAGES) & 1);
         if (lane == 0) mbar_wait(&empty[stage], phase ^ 1);
         __syncwarp();
         uint8_t* a = a_ring + stage * A_BYTES;
@@ -138,15 +149,14 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_kernel(const JointParams 
             o.z = pack_bf16x2(fmaxf(x1.x + y1.x, 0.f), fmaxf(x1.y + y1.y, 0.f));
             o.w = pack_bf16x2(fmaxf(x1.z + y1.z, 0.f), fmaxf(x1.w + y1.w, 0.f));
           }
-          *reinterpret_cast<uint4*>(a + sw128_offset((uint32_t)tid, (uint32_t)c16)) = o;
+          *reinterpret_cast<uint4*>(a + sw128_offset((uint32_t)rowt, (uint32_t)c16)) = o;
         }
         fence_proxy_async_smem();     // generic st.shared -> tcgen05.mma (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[stage]);
-        if (++stage == JT_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == JT_PW) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NV);
     int stage = 0, acc = 0;
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_kernel(const JointParams 
     }
   } else {
     // ===================== epilogue: thread = node =====================
-    const int sub = warp & 3;                  // TMEM sub-partition of this warp (warps 5..8)
+    const int sub = warp & 3;                  // TMEM sub-partition of this warp (warps 9..12)
     const int row = sub * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_kernel(const JointParams 
   tc_fence_before_sync();
   __syncthreads();
   if (p.mode == 1 && tid < p.V1) atomicAdd(p.db2 + tid, db_s[tid]);
-  if (warp == 4) {
+  if (warp == JT_PW) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 2 * NV < 32 ? 32 : 2 * NV);
   }

@@ -45,8 +45,9 @@ KERNELS = {"r01": ["gru_bwd_ks_kernel", "gru_fwd_kernel", "gemm_bf16_tn_pair_ker
                    "gemm_bf16_tn_kernel", "ctc_fwd_bwd_kernel"]}.get(
     R, ["gru_fwd_ks_kernel", "gru_bwd_ks_kernel", "gemm_bf16_tn_pair_kernel", "im2col_kernel",
         "col2im_relu_kernel", "ctc_fwd_bwd_kernel", "sgd_clip_step_kernel", "joint_kernel",
-        "rnnt_fwd_bwd_kernel", "rnnt_decode_static_kernel", "s2s_cell_fwd_kernel",
-        "s2s_attn_fwd_kernel", "s2s_attn_bwd_kernel", "s2s_cell_bwd_kernel"])
+        "joint_reduce_slab_kernel", "rnnt_fwd_bwd_kernel", "rnnt_decode_static_kernel",
+        "gru_fwd_kt_kernel", "gru_bwd_kt_kernel", "s2s_cell_fwd_kernel", "s2s_attn_fwd_kernel",
+        "s2s_attn_bwd_a_kernel", "s2s_attn_bwd_b_kernel", "s2s_cell_bwd_kernel"])
 for k in KERNELS:
     txt = subprocess.run(["ncu", "-i", "gpurun_out/prof_%s_%s.ncu-rep" % (R, k), "--page", "raw", "--csv"],
                          capture_output=True, text=True).stdout
