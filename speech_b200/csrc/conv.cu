@@ -187,6 +187,68 @@ col2im_relu_kernel(const float* __restrict__ dA, long long ldA, const float* __r
     if (dbs[c] != 0.f) atomicAdd(db + c, dbs[c]);
 }
 
+// Same gather with FOUR channels per thread (Ci % 4 == 0): 16-byte tap loads, a quarter of the
+// index arithmetic per element (the scalar kernel was instruction-bound: 0.70 ms at 1.9 TB/s).
+template <int MAXI, int MAXJ>
+__global__ void __launch_bounds__(256)
+col2im_relu_v4_kernel(const float* __restrict__ dA, long long ldA, const float* __restrict__ Pprev,
+                      const unsigned char* __restrict__ maskprev, float mscale,
+                      bf16* __restrict__ dCprev, float* __restrict__ db, int B, int Ti, int Fi,
+                      int Ci, int kh, int kw, int s, int To, int Fo) {
+  extern __shared__ float dbs[];
+  for (int c = threadIdx.x; c < Ci; c += 256) dbs[c] = 0.f;
+  __syncthreads();
+  const int C4 = Ci >> 2;
+  const long long total = (long long)B * Ti * Fi * C4;
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * 256) {
+    const int c4 = (int)(idx % C4);
+    const int px = (int)(idx / C4);
+    const int fi = px % Fi;
+    const int bt = px / Fi;
+    const int ti = bt % Ti;
+    const int b = bt / Ti;
+    const float4 mask = __ldg(reinterpret_cast<const float4*>(Pprev) + idx);
+    float4 v[MAXI * MAXJ];
+#pragma unroll
+    for (int a = 0; a < MAXI; ++a) {
+      const int i = ti % s + a * s;
+      const int t = (ti - i) / s;
+      const bool okt = (i < kh) && (ti - i >= 0) && (t < To);
+#pragma unroll
+      for (int c = 0; c < MAXJ; ++c) {
+        const int j = fi % s + c * s;
+        const int f = (fi - j) / s;
+        const bool ok = okt && (j < kw) && (fi - j >= 0) && (f < Fo);
+        v[a * MAXJ + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok)
+          v[a * MAXJ + c] = __ldcs(reinterpret_cast<const float4*>(
+              dA + (((long long)b * To + t) * Fo + f) * ldA + (i * kw + j) * Ci + c4 * 4));
+      }
+    }
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < MAXI * MAXJ; ++e) { g.x += v[e].x; g.y += v[e].y; g.z += v[e].z; g.w += v[e].w; }
+    if (mask.x <= 0.f) g.x = 0.f;
+    if (mask.y <= 0.f) g.y = 0.f;
+    if (mask.z <= 0.f) g.z = 0.f;
+    if (mask.w <= 0.f) g.w = 0.f;
+    if (maskprev) {
+      const uchar4 mk = reinterpret_cast<const uchar4*>(maskprev)[idx];
+      g.x = mk.x ? g.x * mscale : 0.f; g.y = mk.y ? g.y * mscale : 0.f;
+      g.z = mk.z ? g.z * mscale : 0.f; g.w = mk.w ? g.w * mscale : 0.f;
+    }
+    reinterpret_cast<uint2*>(dCprev)[idx] = make_uint2(pack_bf16x2(g.x, g.y), pack_bf16x2(g.z, g.w));
+    if (g.x != 0.f) atomicAdd(&dbs[c4 * 4], g.x);
+    if (g.y != 0.f) atomicAdd(&dbs[c4 * 4 + 1], g.y);
+    if (g.z != 0.f) atomicAdd(&dbs[c4 * 4 + 2], g.z);
+    if (g.w != 0.f) atomicAdd(&dbs[c4 * 4 + 3], g.w);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Ci; c += 256)
+    if (dbs[c] != 0.f) atomicAdd(db + c, dbs[c]);
+}
+
 // Any tap count (runtime loops): the TIMIT recipes' second layer [*, 5, 32, 1] has 5 x 32 taps per
 // input pixel, far beyond the unrolled instantiations above.  The inner loop over j is unrolled by
 // 4 with the loads issued before their use, so 4 loads are in flight per thread.
@@ -353,7 +415,19 @@ extern "C" int sb_conv_col2im_relu(const float* dA, long long ldA, const float* 
       dA, ldA, Pprev, reinterpret_cast<const unsigned char*>(maskprev_u8), mscale, out, db, B, Ti,  \
       Fi, Ci, kh, kw,                                                                                 \
       stride, To, Fo)
-  if (ni <= 2 && nj <= 2) SB_C2I(2, 2);
+  // four channels per thread when the layout allows 16-byte tap loads
+  const bool v4 = (Ci % 4 == 0) && (ldA % 4 == 0) && ((reinterpret_cast<uintptr_t>(dA) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(Pprev) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(dCprev_bf16) & 7) == 0) &&
+                  (!maskprev_u8 || (reinterpret_cast<uintptr_t>(maskprev_u8) & 3) == 0);
+  const int g4 = grid_for((long long)B * Ti * Fi * (Ci / 4));
+#define SB_C2I4(I, J)                                                                             \
+  col2im_relu_v4_kernel<I, J><<<g4, 256, sm, stream>>>(                                            \
+      dA, ldA, Pprev, reinterpret_cast<const unsigned char*>(maskprev_u8), mscale, out, db, B, Ti,  \
+      Fi, Ci, kh, kw, stride, To, Fo)
+  if (v4 && ni <= 2 && nj <= 2) SB_C2I4(2, 2);
+  else if (v4 && ni <= 3 && nj <= 4) SB_C2I4(3, 4);
+  else if (ni <= 2 && nj <= 2) SB_C2I(2, 2);
   else if (ni <= 3 && nj <= 4) SB_C2I(3, 4);
   else if (ni <= 5 && nj <= 8) SB_C2I(5, 8);
   else
@@ -361,6 +435,7 @@ extern "C" int sb_conv_col2im_relu(const float* dA, long long ldA, const float* 
         dA, ldA, Pprev, reinterpret_cast<const unsigned char*>(maskprev_u8), mscale, out, db, B, Ti,
         Fi, Ci, kh, kw, stride, To, Fo);
 #undef SB_C2I
+#undef SB_C2I4
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
