@@ -207,7 +207,8 @@ int sb_sgd_clip_step(float* params, const float* grads, float* momentum_buf, voi
  * per CTA, accumulated over the steps, to be summed over its two leading dims by the caller.
  * workspace: >= sb_s2s_workspace_size(B, T, H) bytes, its first 4*B bytes ZERO before the first
  * call (ticket counters; the kernels leave them zero); one workspace serves all steps.
- * Constraints: H % 4 == 0, conv kernel width odd and <= 15, T <= 6144, beam <= 32.
+ * Constraints: H % 4 == 0 (attention backward: H <= 1664, its shared-memory tile is 33 H floats),
+ * conv kernel width odd and <= 15, T <= 6144, beam <= 32.
  * ------------------------------------------------------------------------------------- */
 int sb_s2s_workspace_size(int B, int T, int H, size_t* bytes);
 int sb_attn_step(const float* eh, const float* dhx, const float* ax_prev, const float* conv_wT,
