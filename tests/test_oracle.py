@@ -109,6 +109,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.sb_version() >= 100
 
 
+def test_workspace_size_queries_need_no_gpu():
+    """The size queries of the C ABI are pure host arithmetic: they answer on a CPU box, grow with
+    the problem and reject non-positive sizes (-1 = SB_ERR_INVALID)."""
+    from speech_b200 import _lib
+    lib = _lib.load()
+    n = ctypes.c_size_t(0)
+    assert lib.sb_s2s_workspace_size(16, 200, 512, ctypes.byref(n)) == 0
+    small = n.value
+    # tickets + scores (B*T) + 4 scalars and 2 H-wide partials per CTA of 24 frames
+    ts = (200 + 23) // 24
+    assert small >= 4 * (16 * 200 + 4 * 16 * ts + 2 * 16 * ts * 512)
+    assert lib.sb_s2s_workspace_size(16, 400, 512, ctypes.byref(n)) == 0 and n.value > small
+    assert lib.sb_s2s_workspace_size(0, 200, 512, ctypes.byref(n)) != 0
+    assert lib.sb_gru_fwd_workspace_size(64, 1024, 2, ctypes.byref(n)) == 0 and n.value >= 1024
+    assert lib.sb_gru_bwd_workspace_size(64, 1024, 2, ctypes.byref(n)) == 0
+    assert n.value >= 1024 + 2 * 2 * 64 * 3 * 1024 * 2          # counters + bf16 exchange tiles
+    assert lib.sb_gru_fwd_workspace_size(64, 1024, 3, ctypes.byref(n)) != 0
+
+
 def test_c_oracle_matches_numpy_oracle():
     from oracle import build as ob
     rng = np.random.RandomState(4)
