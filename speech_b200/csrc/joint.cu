@@ -8,7 +8,7 @@
 // (blank and the next label), so the training path here writes a COMPACT lattice
 // lat[node] = {log p(blank), log p(label_u)} (8 bytes per node) and the hidden tensor only ever
 // exists as 16 KB operand tiles in shared memory:
-//   * 2 x 4 producer warps (thread = node row; the two groups take alternate k-blocks) build
+//   * 3 x 4 producer warps (thread = node row; the groups take the k-blocks in turn) build
 //     A tiles [128 nodes x 64] bf16 of relu(fx[b,t,:] + fy[b,u,:]) straight into the UMMA
 //     K-major SWIZZLE_128B layout (fx, fy: fp32 outputs of the fc1 GEMMs, L2 resident: 7.9 K
 //     and 3.2 K rows);
@@ -31,10 +31,14 @@ namespace sb {
 
 typedef __nv_bfloat16 bf16;
 
-static constexpr int JT_STAGES = 4;
-static constexpr int JT_GROUPS = 2;                   // producer groups (4 warps each)
-static constexpr int JT_PW = 4 * JT_GROUPS;           // producer warps
-static constexpr int JT_THREADS = 32 * (JT_PW + 5);   // warps 0..7 producers, 8 MMA, 9..12 epilogue
+static constexpr int JT_STAGES = 6;
+// producer groups of 4 warps: 3 for the 32-class kernel, 2 for the 64-class one (whose epilogue
+// keeps 2 x 64 values per thread and would spill under the register cap of 17 warps)
+template <int NV> struct JtCfg {
+  static constexpr int kGroups = NV <= 32 ? 3 : 2;
+  static constexpr int kPW = 4 * kGroups;              // producer warps
+  static constexpr int kThreads = 32 * (kPW + 5);      // producers | MMA warp | 4 epilogue warps
+};
 
 struct JointParams {
   const float* fx;      // [B*T][H]   fc1(encoder states)   (bias included)
@@ -52,7 +56,8 @@ struct JointParams {
 };
 
 template <int NV>
-__global__ void __launch_bounds__(JT_THREADS, 1) joint_kernel(const JointParams p) {
+__global__ void __launch_bounds__(JtCfg<NV>::kThreads, 1) joint_kernel(const JointParams p) {
+  constexpr int JT_GROUPS = JtCfg<NV>::kGroups, JT_PW = JtCfg<NV>::kPW, JT_THREADS = JtCfg<NV>::kThreads;
   extern __shared__ uint8_t smem_raw[];
   const int H = p.H;
   const int nkb = (H + 63) / 64;
@@ -111,10 +116,11 @@ __global__ void __launch_bounds__(JT_THREADS, 1) joint_kernel(const JointParams 
 
   if (warp < JT_PW) {
     // ===================== producers: thread = node row of the tile =====================
-    // Two groups of 4 warps build ALTERNATE k-blocks (item i = running (tile, k-block) index goes
-    // to group i % 2, ring stage i % JT_STAGES): a k-block is one L2 round trip (128 rows x 256 B
-    // of fy), so two are in flight per CTA.  Measured with one group: 2.36 ms per pass against
-    // an L2-ingest floor of 0.73 ms (3.3 GB of fy rows at ~30 GB/s per SM).
+    // The groups of 4 warps take k-blocks in turn (item i = running (tile, k-block) index goes to
+    // group i % JT_GROUPS, ring stage i % JT_STAGES): a k-block is one L2 round trip (128 rows x
+    // 256 B of fy), so JT_GROUPS of them are in flight per CTA.  Measured: 2.36 ms per pass with
+    // one group, 1.05 ms with two, against an L2-ingest floor of 0.73 ms (3.3 GB of fy rows at
+    // ~30 GB/s per SM).
     const int grp = warp >> 2;
     const int rowt = tid & 127;
     long long item = 0;
@@ -391,11 +397,11 @@ static int joint_launch(JointParams& p, void* stream_) {
   if (nv == 32) {
     e = cudaFuncSetAttribute(joint_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return SB_ERR_CUDA;
-    joint_kernel<32><<<grid, JT_THREADS, smem, stream>>>(p);
+    joint_kernel<32><<<grid, JtCfg<32>::kThreads, smem, stream>>>(p);
   } else {
     e = cudaFuncSetAttribute(joint_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return SB_ERR_CUDA;
-    joint_kernel<64><<<grid, JT_THREADS, smem, stream>>>(p);
+    joint_kernel<64><<<grid, JtCfg<64>::kThreads, smem, stream>>>(p);
   }
   return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
